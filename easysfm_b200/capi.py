@@ -1,0 +1,338 @@
+"""ctypes binding of include/esfm_match.h (libesfm_match.so).
+
+Thin by design: every function maps 1:1 onto a C entry point; numpy arrays are passed as raw
+pointers + sizes.  Loading fails loudly if the library has not been built -- there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+KIND_F32X64 = 0
+KIND_B256 = 1
+
+DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+PAIR_DTYPE = np.dtype([("query", "<i4"), ("train", "<i4")])
+
+
+class EsfmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"esfm error {code}: {msg}")
+        self.code = code
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [
+        ("kernel_launches", c_uint64),
+        ("h2d_bytes", c_uint64),
+        ("d2h_bytes", c_uint64),
+        ("comparisons", c_uint64),
+        ("pairs", c_uint64),
+        ("last_sweep_ms", c_double),
+        ("last_finalize_ms", c_double),
+        ("sweep_ms_total", c_double),
+        ("sweep_launches", c_uint64),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header.
+SIGNATURES = {
+    "esfm_abi_version": (c_int, []),
+    "esfm_last_error": (c_char_p, []),
+    "esfm_init": (c_int, [c_int, c_void_p, POINTER(c_void_p)]),
+    "esfm_destroy": (c_int, [c_void_p]),
+    "esfm_synchronize": (c_int, [c_void_p]),
+    "esfm_get_stats": (c_int, [c_void_p, POINTER(Stats)]),
+    "esfm_set_profiling": (c_int, [c_void_p, c_int]),
+    "esfm_device_sm_count": (c_int, [c_void_p, POINTER(c_int)]),
+    "esfm_bank_create": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "esfm_bank_set_frame": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_size_t]),
+    "esfm_bank_set_frame_rows": (c_int, [c_void_p, c_int, c_int]),
+    "esfm_bank_commit": (c_int, [c_void_p]),
+    "esfm_bank_alloc_device": (c_int, [c_void_p]),
+    "esfm_bank_device_rows": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t)]),
+    "esfm_bank_commit_device": (c_int, [c_void_p]),
+    "esfm_bank_n_frames": (c_int, [c_void_p, POINTER(c_int)]),
+    "esfm_bank_frame_rows": (c_int, [c_void_p, c_int, POINTER(c_int)]),
+    "esfm_bank_device_bytes": (c_int, [c_void_p, POINTER(c_size_t)]),
+    "esfm_bank_destroy": (c_int, [c_void_p]),
+    "esfm_match_all_pairs": (c_int, [c_void_p, c_double, c_int, POINTER(c_void_p)]),
+    "esfm_match_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_int, POINTER(c_void_p)]),
+    "esfm_match_pairs_device": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_int, POINTER(c_void_p)]),
+    "esfm_results_fetch": (c_int, [c_void_p]),
+    "esfm_match_pair": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_void_p, c_int, POINTER(c_int)]),
+    "esfm_match_descriptors": (c_int, [c_void_p, c_int, c_void_p, c_int, c_size_t, c_void_p, c_int, c_size_t, c_int,
+                                       c_double, c_int, c_void_p, c_int, POINTER(c_int)]),
+    "esfm_knn2_pair": (c_int, [c_void_p, c_int, c_int, POINTER(c_int32), POINTER(c_float)]),
+    "esfm_results_counts": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
+    "esfm_results_pair_at": (c_int, [c_void_p, c_int64, POINTER(c_int), POINTER(c_int), POINTER(c_void_p), POINTER(c_int)]),
+    "esfm_results_pair": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p), POINTER(c_int)]),
+    "esfm_results_pair_counts": (c_int, [c_void_p, POINTER(c_int32)]),
+    "esfm_results_destroy": (c_int, [c_void_p]),
+}
+
+_LIB = None
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "lib", "libesfm_match.so")
+
+
+def load_library():
+    """dlopen libesfm_match.so; raises if it was not built (python __graft_entry__.py build, or make -C easysfm_b200/csrc)."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} is missing: build it with `make -C easysfm_b200/csrc` (nvcc, sm_100a). "
+                "easysfm_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def _check(rc: int):
+    if rc != 0:
+        msg = load_library().esfm_last_error()
+        raise EsfmError(rc, msg.decode("utf-8", "replace") if msg else "")
+
+
+def _as_desc(arr, kind=None):
+    arr = np.asarray(arr)
+    if arr.ndim != 2:
+        raise ValueError("descriptor matrix must be 2-D (rows x cols)")
+    if arr.dtype == np.float32:
+        k = KIND_F32X64
+    elif arr.dtype == np.uint8:
+        k = KIND_B256
+    else:
+        raise TypeError(f"descriptors must be float32 (SURF) or uint8 (ORB), got {arr.dtype}")
+    if kind is not None and k != kind:
+        raise TypeError("descriptor dtype does not match the bank kind")
+    if arr.shape[0] and arr.strides[1] != arr.itemsize:
+        arr = np.ascontiguousarray(arr)
+    return arr, k
+
+
+class Context:
+    """One CUDA device + stream (esfm_ctx_t)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = load_library()
+        h = c_void_p()
+        _check(self._lib.esfm_init(int(device), c_void_p(stream) if stream else None, ctypes.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.esfm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def synchronize(self):
+        _check(self._lib.esfm_synchronize(self._h))
+
+    def stats(self) -> dict:
+        s = Stats()
+        _check(self._lib.esfm_get_stats(self._h, ctypes.byref(s)))
+        return s.as_dict()
+
+    def set_profiling(self, on: bool):
+        _check(self._lib.esfm_set_profiling(self._h, int(bool(on))))
+
+    @property
+    def sm_count(self) -> int:
+        n = c_int()
+        _check(self._lib.esfm_device_sm_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def bank(self, kind: int, n_frames: int) -> "Bank":
+        return Bank(self, kind, n_frames)
+
+    def bank_from_frames(self, frames) -> "Bank":
+        """frames: sequence of 2-D numpy arrays (all float32 x64 or all uint8 x32)."""
+        frames = list(frames)
+        if not frames:
+            raise ValueError("no frames")
+        _, kind = _as_desc(frames[0])
+        b = Bank(self, kind, len(frames))
+        for i, f in enumerate(frames):
+            b.set_frame(i, f)
+        b.commit()
+        return b
+
+    def match_descriptors(self, query, train, ratio: float, cross_check: bool = False) -> np.ndarray:
+        """Two host matrices in, matches out (esfm_match_descriptors)."""
+        q, kind = _as_desc(query)
+        t, _ = _as_desc(train, kind)
+        cols = q.shape[1] if q.shape[0] else (t.shape[1] if t.shape[0] else (64 if kind == KIND_F32X64 else 32))
+        out = np.zeros(max(q.shape[0], 1), DMATCH_DTYPE)
+        n = c_int(0)
+        _check(self._lib.esfm_match_descriptors(
+            self._h, kind, q.ctypes.data, q.shape[0], q.strides[0] if q.shape[0] else 0,
+            t.ctypes.data, t.shape[0], t.strides[0] if t.shape[0] else 0, cols, float(ratio), int(bool(cross_check)),
+            out.ctypes.data, out.shape[0], ctypes.byref(n)))
+        return out[: n.value].copy()
+
+
+class Bank:
+    """Device-resident descriptor bank (esfm_bank_t)."""
+
+    def __init__(self, ctx: Context, kind: int, n_frames: int):
+        self._lib = ctx._lib
+        self.ctx = ctx
+        self.kind = int(kind)
+        h = c_void_p()
+        _check(self._lib.esfm_bank_create(ctx._h, int(kind), int(n_frames), ctypes.byref(h)))
+        self._h = h
+        self.n_frames = int(n_frames)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.esfm_bank_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_frame(self, frame_id: int, desc):
+        a, _ = _as_desc(desc, self.kind)
+        _check(self._lib.esfm_bank_set_frame(self._h, int(frame_id), a.ctypes.data, a.shape[0], a.shape[1],
+                                             a.strides[0] if a.shape[0] else a.shape[1] * a.itemsize))
+
+    def set_frame_rows(self, frame_id: int, rows: int):
+        _check(self._lib.esfm_bank_set_frame_rows(self._h, int(frame_id), int(rows)))
+
+    def commit(self):
+        _check(self._lib.esfm_bank_commit(self._h))
+
+    def alloc_device(self):
+        _check(self._lib.esfm_bank_alloc_device(self._h))
+
+    def device_rows(self):
+        """(device pointer, bytes) of the raw row-major bank, e.g. to wrap as a torch tensor for a broadcast."""
+        p, n = c_void_p(), c_size_t()
+        _check(self._lib.esfm_bank_device_rows(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def commit_device(self):
+        _check(self._lib.esfm_bank_commit_device(self._h))
+
+    def frame_rows(self, frame_id: int) -> int:
+        r = c_int()
+        _check(self._lib.esfm_bank_frame_rows(self._h, int(frame_id), ctypes.byref(r)))
+        return r.value
+
+    def device_bytes(self) -> int:
+        n = c_size_t()
+        _check(self._lib.esfm_bank_device_bytes(self._h, ctypes.byref(n)))
+        return n.value
+
+    # ---- matching ----
+    def match_all_pairs(self, ratio: float, cross_check: bool = False) -> "Results":
+        h = c_void_p()
+        _check(self._lib.esfm_match_all_pairs(self._h, float(ratio), int(bool(cross_check)), ctypes.byref(h)))
+        return Results(self._lib, h)
+
+    def match_pairs(self, pairs, ratio: float, cross_check: bool = False, device_resident: bool = False) -> "Results":
+        p = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        h = c_void_p()
+        fn = self._lib.esfm_match_pairs_device if device_resident else self._lib.esfm_match_pairs
+        _check(fn(self._h, p.ctypes.data, p.shape[0], float(ratio), int(bool(cross_check)), ctypes.byref(h)))
+        return Results(self._lib, h)
+
+    def match_pair(self, query_frame: int, train_frame: int, ratio: float, cross_check: bool = False) -> np.ndarray:
+        cap = max(self.frame_rows(query_frame), 1)
+        out = np.zeros(cap, DMATCH_DTYPE)
+        n = c_int(0)
+        _check(self._lib.esfm_match_pair(self._h, int(query_frame), int(train_frame), float(ratio), int(bool(cross_check)),
+                                         out.ctypes.data, cap, ctypes.byref(n)))
+        return out[: n.value].copy()
+
+    def knn2_pair(self, query_frame: int, train_frame: int):
+        fq = self.frame_rows(query_frame)
+        idx = np.full((fq, 2), -1, np.int32)
+        dist = np.full((fq, 2), np.inf, np.float32)
+        _check(self._lib.esfm_knn2_pair(self._h, int(query_frame), int(train_frame),
+                                        idx.ctypes.data_as(POINTER(c_int32)), dist.ctypes.data_as(POINTER(c_float))))
+        return idx, dist
+
+
+class Results:
+    """Host-resident compacted matches of a batch of pairs (esfm_results_t)."""
+
+    def __init__(self, lib, handle):
+        self._lib = lib
+        self._h = handle
+        n_pairs, n_matches = c_int64(), c_int64()
+        _check(lib.esfm_results_counts(handle, ctypes.byref(n_pairs), ctypes.byref(n_matches)))
+        self.n_pairs = n_pairs.value
+        self.n_matches = n_matches.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.esfm_results_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def fetch(self):
+        _check(self._lib.esfm_results_fetch(self._h))
+
+    def pair_counts(self) -> np.ndarray:
+        out = np.zeros(self.n_pairs, np.int32)
+        if self.n_pairs:
+            _check(self._lib.esfm_results_pair_counts(self._h, out.ctypes.data_as(POINTER(c_int32))))
+        return out
+
+    def _view(self, ptr, n):
+        if n == 0 or not ptr:
+            return np.zeros(0, DMATCH_DTYPE)
+        buf = (ctypes.c_char * (n * DMATCH_DTYPE.itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=DMATCH_DTYPE, count=n).copy()
+
+    def pair_at(self, k: int):
+        q, t, n, p = c_int(), c_int(), c_int(), c_void_p()
+        _check(self._lib.esfm_results_pair_at(self._h, int(k), ctypes.byref(q), ctypes.byref(t), ctypes.byref(p), ctypes.byref(n)))
+        return q.value, t.value, self._view(p.value, n.value)
+
+    def pair(self, query_frame: int, train_frame: int) -> np.ndarray:
+        n, p = c_int(), c_void_p()
+        _check(self._lib.esfm_results_pair(self._h, int(query_frame), int(train_frame), ctypes.byref(p), ctypes.byref(n)))
+        return self._view(p.value, n.value)
+
+    def __iter__(self):
+        for k in range(self.n_pairs):
+            yield self.pair_at(k)

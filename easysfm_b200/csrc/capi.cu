@@ -1,0 +1,750 @@
+// capi.cu -- host side of libesfm_match.so: the C ABI declared in include/esfm_match.h.
+//
+// Host logic only (bank packing, pair-batch chunking, scratch management, result bookkeeping); every
+// distance, selection, ratio, cross-check and compaction step runs in the CUDA kernels of this library.
+// There is no CPU fallback: if the device or a kernel fails the call fails.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "esfm_internal.cuh"
+
+using namespace esfm;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t e__ = (expr);                                                                               \
+        if (e__ != cudaSuccess)                                                                                 \
+            return fail(ESFM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------------
+struct esfm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    bool profiling = true;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    esfm_stats_t stats{};
+    // device scratch, grown on demand
+    u64* keys = nullptr;           size_t keys_bytes = 0;
+    esfm_dmatch_t* arena = nullptr; size_t arena_cap = 0;   // in matches
+    PairDesc* d_pairs = nullptr;   size_t pairs_cap = 0;
+    unsigned long long* d_pair_off = nullptr;
+    int32_t* d_pair_cnt = nullptr;
+    unsigned long long* d_cursor = nullptr;  // [0] cursor, [1] overflow flag (as int)
+    // pinned host staging
+    void* h_stage = nullptr;       size_t h_stage_bytes = 0;
+    uint64_t arena_generation = 0;
+};
+
+struct esfm_bank {
+    esfm_ctx* ctx = nullptr;
+    int kind = 0;
+    int n_frames = 0;
+    std::vector<int> rows;                    // per frame, -1 = not set
+    std::vector<std::vector<uint8_t>> host;   // staged frame data until commit
+    bool committed = false;
+    bool device_allocated = false;
+    // device
+    void* d_rows = nullptr;  size_t rows_bytes = 0;
+    float* d_kmajor = nullptr; size_t kmajor_bytes = 0;
+    int* d_frame_rows = nullptr;
+    int* d_row_off = nullptr;
+    int* d_tile_off = nullptr;
+    // host copies
+    std::vector<int> row_off, tile_off;
+    int max_rows = 0;
+    size_t row_bytes() const { return kind == ESFM_KIND_F32X64 ? kDim * sizeof(float) : 32; }
+};
+
+struct esfm_results {
+    esfm_ctx* ctx = nullptr;
+    std::vector<PairDesc> pairs;
+    std::vector<int32_t> counts;
+    std::vector<uint64_t> offsets;          // into `matches`
+    std::vector<esfm_dmatch_t> matches;     // host copy (empty until fetched for device-resident results)
+    std::unordered_map<uint64_t, int64_t> index;
+    bool fetched = true;
+    // device-resident variant (single chunk only)
+    uint64_t arena_generation = 0;
+    uint64_t device_matches = 0;
+    int64_t total_matches = 0;
+};
+
+static int set_device(esfm_ctx* ctx) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return ESFM_OK;
+}
+
+template <typename T>
+static int grow(T** ptr, size_t* cap_elems, size_t need_elems) {
+    if (*cap_elems >= need_elems && *ptr) return ESFM_OK;
+    if (*ptr) CUDA_TRY(cudaFree(*ptr));
+    *ptr = nullptr;
+    *cap_elems = 0;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, need_elems * sizeof(T));
+    if (e != cudaSuccess) return fail(ESFM_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", need_elems * sizeof(T), cudaGetErrorString(e));
+    *ptr = (T*)p;
+    *cap_elems = need_elems;
+    return ESFM_OK;
+}
+
+static int grow_stage(esfm_ctx* ctx, size_t bytes) {
+    if (ctx->h_stage_bytes >= bytes) return ESFM_OK;
+    if (ctx->h_stage) CUDA_TRY(cudaFreeHost(ctx->h_stage));
+    ctx->h_stage = nullptr;
+    ctx->h_stage_bytes = 0;
+    size_t want = std::max(bytes, (size_t)1 << 20);
+    cudaError_t e = cudaMallocHost(&ctx->h_stage, want);
+    if (e != cudaSuccess) return fail(ESFM_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+    ctx->h_stage_bytes = want;
+    return ESFM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int esfm_abi_version(void) { return ESFM_ABI_VERSION; }
+extern "C" const char* esfm_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int esfm_init(int device, void* cuda_stream, esfm_ctx_t** out) {
+    if (!out) return fail(ESFM_ERR_INVALID, "esfm_init: ctx is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(ESFM_ERR_CUDA, "esfm_init: no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(ESFM_ERR_INVALID, "esfm_init: device %d out of range [0,%d)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(ESFM_ERR_CUDA, "esfm_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    esfm_ctx* ctx = new (std::nothrow) esfm_ctx();
+    if (!ctx) return fail(ESFM_ERR_NOMEM, "esfm_init: out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete ctx; return fail(ESFM_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
+        ctx->own_stream = true;
+    }
+    for (auto& ev : ctx->ev) {
+        e = cudaEventCreate(&ev);
+        if (e != cudaSuccess) { delete ctx; return fail(ESFM_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
+    }
+    e = cudaMalloc((void**)&ctx->d_cursor, 2 * sizeof(unsigned long long));
+    if (e != cudaSuccess) { delete ctx; return fail(ESFM_ERR_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    *out = ctx;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_destroy(esfm_ctx_t* ctx) {
+    if (!ctx) return ESFM_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->keys); cudaFree(ctx->arena); cudaFree(ctx->d_pairs); cudaFree(ctx->d_pair_off);
+    cudaFree(ctx->d_pair_cnt); cudaFree(ctx->d_cursor);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_synchronize(esfm_ctx_t* ctx) {
+    if (!ctx) return fail(ESFM_ERR_INVALID, "ctx is NULL");
+    if (int rc = set_device(ctx)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return ESFM_OK;
+}
+
+extern "C" int esfm_get_stats(esfm_ctx_t* ctx, esfm_stats_t* out) {
+    if (!ctx || !out) return fail(ESFM_ERR_INVALID, "esfm_get_stats: NULL argument");
+    *out = ctx->stats;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_set_profiling(esfm_ctx_t* ctx, int enabled) {
+    if (!ctx) return fail(ESFM_ERR_INVALID, "ctx is NULL");
+    ctx->profiling = enabled != 0;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_device_sm_count(esfm_ctx_t* ctx, int* sms) {
+    if (!ctx || !sms) return fail(ESFM_ERR_INVALID, "esfm_device_sm_count: NULL argument");
+    *sms = ctx->sm_count;
+    return ESFM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bank
+// ------------------------------------------------------------------------------------------------
+extern "C" int esfm_bank_create(esfm_ctx_t* ctx, esfm_kind kind, int n_frames, esfm_bank_t** out) {
+    if (!ctx || !out) return fail(ESFM_ERR_INVALID, "esfm_bank_create: NULL argument");
+    *out = nullptr;
+    if (kind != ESFM_KIND_F32X64 && kind != ESFM_KIND_B256) return fail(ESFM_ERR_INVALID, "esfm_bank_create: unknown kind %d", (int)kind);
+    if (n_frames < 0) return fail(ESFM_ERR_INVALID, "esfm_bank_create: n_frames < 0");
+    esfm_bank* b = new (std::nothrow) esfm_bank();
+    if (!b) return fail(ESFM_ERR_NOMEM, "out of host memory");
+    b->ctx = ctx;
+    b->kind = kind;
+    b->n_frames = n_frames;
+    b->rows.assign(n_frames, -1);
+    b->host.resize(n_frames);
+    *out = b;
+    return ESFM_OK;
+}
+
+static int check_frame_limits(esfm_bank* b, int rows) {
+    const int lim = b->kind == ESFM_KIND_F32X64 ? sweep_l2_max_rows() : sweep_hamming_max_rows();
+    if (rows > lim) return fail(ESFM_ERR_CAPACITY, "frame has %d rows; this build supports at most %d per frame for kind %d", rows, lim, b->kind);
+    return ESFM_OK;
+}
+
+extern "C" int esfm_bank_set_frame(esfm_bank_t* b, int frame_id, const void* data, int rows, int cols, size_t step_bytes) {
+    if (!b) return fail(ESFM_ERR_INVALID, "bank is NULL");
+    if (b->committed || b->device_allocated) return fail(ESFM_ERR_STATE, "esfm_bank_set_frame: bank already committed");
+    if (frame_id < 0 || frame_id >= b->n_frames) return fail(ESFM_ERR_INVALID, "frame_id %d out of range [0,%d)", frame_id, b->n_frames);
+    if (rows < 0) return fail(ESFM_ERR_INVALID, "rows < 0");
+    const int want_cols = b->kind == ESFM_KIND_F32X64 ? kDim : 32;
+    if (rows > 0 && cols != want_cols)
+        return fail(ESFM_ERR_INVALID, "kind %d needs %d columns per descriptor, got %d", b->kind, want_cols, cols);
+    const size_t rb = b->row_bytes();
+    if (rows > 0 && !data) return fail(ESFM_ERR_INVALID, "data is NULL with rows > 0");
+    if (rows > 0 && step_bytes < rb) return fail(ESFM_ERR_INVALID, "step_bytes %zu smaller than a row (%zu)", step_bytes, rb);
+    if (int rc = check_frame_limits(b, rows)) return rc;
+    std::vector<uint8_t>& dst = b->host[frame_id];
+    dst.resize((size_t)rows * rb);
+    for (int r = 0; r < rows; ++r) memcpy(dst.data() + (size_t)r * rb, (const uint8_t*)data + (size_t)r * step_bytes, rb);
+    b->rows[frame_id] = rows;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_bank_set_frame_rows(esfm_bank_t* b, int frame_id, int rows) {
+    if (!b) return fail(ESFM_ERR_INVALID, "bank is NULL");
+    if (b->committed || b->device_allocated) return fail(ESFM_ERR_STATE, "bank already committed");
+    if (frame_id < 0 || frame_id >= b->n_frames) return fail(ESFM_ERR_INVALID, "frame_id %d out of range", frame_id);
+    if (rows < 0) return fail(ESFM_ERR_INVALID, "rows < 0");
+    if (int rc = check_frame_limits(b, rows)) return rc;
+    b->rows[frame_id] = rows;
+    b->host[frame_id].clear();
+    return ESFM_OK;
+}
+
+static int bank_alloc_layout(esfm_bank* b) {
+    esfm_ctx* ctx = b->ctx;
+    if (int rc = set_device(ctx)) return rc;
+    for (int f = 0; f < b->n_frames; ++f)
+        if (b->rows[f] < 0) return fail(ESFM_ERR_STATE, "frame %d was never set", f);
+    b->row_off.assign(b->n_frames + 1, 0);
+    b->tile_off.assign(b->n_frames + 1, 0);
+    b->max_rows = 0;
+    for (int f = 0; f < b->n_frames; ++f) {
+        b->row_off[f + 1] = b->row_off[f] + b->rows[f];
+        b->tile_off[f + 1] = b->tile_off[f] + (b->rows[f] + kTile - 1) / kTile;
+        b->max_rows = std::max(b->max_rows, b->rows[f]);
+        if (b->row_off[f + 1] < b->row_off[f]) return fail(ESFM_ERR_CAPACITY, "bank exceeds 2^31 rows");
+    }
+    const size_t total_rows = (size_t)b->row_off[b->n_frames];
+    // one extra tile of slack so tile-granular reads past the last frame stay inside the allocation
+    b->rows_bytes = (total_rows + kHamTile) * b->row_bytes();
+    cudaError_t e = cudaMalloc(&b->d_rows, b->rows_bytes);
+    if (e != cudaSuccess) return fail(ESFM_ERR_NOMEM, "cudaMalloc(%zu) for the descriptor bank failed: %s", b->rows_bytes, cudaGetErrorString(e));
+    CUDA_TRY(cudaMemsetAsync(b->d_rows, 0, b->rows_bytes, ctx->stream));
+    if (b->kind == ESFM_KIND_F32X64) {
+        b->kmajor_bytes = ((size_t)b->tile_off[b->n_frames] + 1) * kTileBytes;
+        e = cudaMalloc((void**)&b->d_kmajor, b->kmajor_bytes);
+        if (e != cudaSuccess) return fail(ESFM_ERR_NOMEM, "cudaMalloc(%zu) for the k-major bank failed: %s", b->kmajor_bytes, cudaGetErrorString(e));
+    }
+    const size_t nb = (size_t)(b->n_frames + 1) * sizeof(int);
+    CUDA_TRY(cudaMalloc((void**)&b->d_frame_rows, nb));
+    CUDA_TRY(cudaMalloc((void**)&b->d_row_off, nb));
+    CUDA_TRY(cudaMalloc((void**)&b->d_tile_off, nb));
+    CUDA_TRY(cudaMemcpyAsync(b->d_frame_rows, b->rows.data(), (size_t)b->n_frames * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(b->d_row_off, b->row_off.data(), nb, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(b->d_tile_off, b->tile_off.data(), nb, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.h2d_bytes += 3 * nb;
+    b->device_allocated = true;
+    return ESFM_OK;
+}
+
+static int bank_build_derived(esfm_bank* b) {
+    esfm_ctx* ctx = b->ctx;
+    if (b->kind == ESFM_KIND_F32X64) {
+        const int n_tiles = b->tile_off[b->n_frames];
+        cudaError_t e = launch_pack_f32((const float*)b->d_rows, b->d_frame_rows, b->d_row_off, b->d_tile_off, b->n_frames,
+                                        n_tiles, b->d_kmajor, ctx->stream);
+        if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "pack_f32 kernel launch failed: %s", cudaGetErrorString(e));
+        if (n_tiles > 0) ctx->stats.kernel_launches += 1;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    b->committed = true;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_bank_alloc_device(esfm_bank_t* b) {
+    if (!b) return fail(ESFM_ERR_INVALID, "bank is NULL");
+    if (b->device_allocated) return fail(ESFM_ERR_STATE, "bank already allocated");
+    return bank_alloc_layout(b);
+}
+
+extern "C" int esfm_bank_commit(esfm_bank_t* b) {
+    if (!b) return fail(ESFM_ERR_INVALID, "bank is NULL");
+    if (b->committed) return fail(ESFM_ERR_STATE, "bank already committed");
+    if (!b->device_allocated) {
+        for (int f = 0; f < b->n_frames; ++f)
+            if (b->rows[f] > 0 && b->host[f].empty())
+                return fail(ESFM_ERR_STATE, "frame %d has rows declared but no host data; use esfm_bank_alloc_device + esfm_bank_commit_device", f);
+        if (int rc = bank_alloc_layout(b)) return rc;
+    }
+    esfm_ctx* ctx = b->ctx;
+    // pack all frames into pinned staging, one H2D copy
+    const size_t rb = b->row_bytes();
+    const size_t total = (size_t)b->row_off[b->n_frames] * rb;
+    if (total > 0) {
+        if (int rc = grow_stage(ctx, total)) return rc;
+        for (int f = 0; f < b->n_frames; ++f)
+            if (b->rows[f] > 0) memcpy((uint8_t*)ctx->h_stage + (size_t)b->row_off[f] * rb, b->host[f].data(), (size_t)b->rows[f] * rb);
+        CUDA_TRY(cudaMemcpyAsync(b->d_rows, ctx->h_stage, total, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stats.h2d_bytes += total;
+    }
+    for (auto& v : b->host) std::vector<uint8_t>().swap(v);
+    return bank_build_derived(b);
+}
+
+extern "C" int esfm_bank_device_rows(esfm_bank_t* b, void** dev_ptr, size_t* bytes) {
+    if (!b || !dev_ptr || !bytes) return fail(ESFM_ERR_INVALID, "esfm_bank_device_rows: NULL argument");
+    if (!b->device_allocated) return fail(ESFM_ERR_STATE, "bank has no device storage yet");
+    *dev_ptr = b->d_rows;
+    *bytes = (size_t)b->row_off[b->n_frames] * b->row_bytes();
+    return ESFM_OK;
+}
+
+extern "C" int esfm_bank_commit_device(esfm_bank_t* b) {
+    if (!b) return fail(ESFM_ERR_INVALID, "bank is NULL");
+    if (!b->device_allocated) return fail(ESFM_ERR_STATE, "call esfm_bank_alloc_device first");
+    if (int rc = set_device(b->ctx)) return rc;
+    return bank_build_derived(b);
+}
+
+extern "C" int esfm_bank_n_frames(esfm_bank_t* b, int* n) {
+    if (!b || !n) return fail(ESFM_ERR_INVALID, "NULL argument");
+    *n = b->n_frames;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_bank_frame_rows(esfm_bank_t* b, int frame_id, int* rows) {
+    if (!b || !rows) return fail(ESFM_ERR_INVALID, "NULL argument");
+    if (frame_id < 0 || frame_id >= b->n_frames) return fail(ESFM_ERR_INVALID, "frame_id %d out of range", frame_id);
+    *rows = b->rows[frame_id];
+    return ESFM_OK;
+}
+
+extern "C" int esfm_bank_device_bytes(esfm_bank_t* b, size_t* bytes) {
+    if (!b || !bytes) return fail(ESFM_ERR_INVALID, "NULL argument");
+    *bytes = b->device_allocated ? b->rows_bytes + b->kmajor_bytes : 0;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_bank_destroy(esfm_bank_t* b) {
+    if (!b) return ESFM_OK;
+    if (b->ctx) {
+        cudaSetDevice(b->ctx->device);
+        cudaStreamSynchronize(b->ctx->stream);
+    }
+    cudaFree(b->d_rows); cudaFree(b->d_kmajor); cudaFree(b->d_frame_rows); cudaFree(b->d_row_off); cudaFree(b->d_tile_off);
+    delete b;
+    return ESFM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// matching
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct ChunkPlan {
+    int stride;        // keys per array
+    int col_cap;       // smem threshold entries
+    size_t chunk_pairs;
+};
+
+ChunkPlan plan_chunks(const esfm_bank* b, int64_t n_pairs) {
+    ChunkPlan pl;
+    const int padded = ((b->max_rows + kTile - 1) / kTile) * kTile;
+    pl.stride = std::max(padded, kTile);
+    pl.col_cap = pl.stride;
+    const size_t key_bytes_per_pair = (size_t)4 * pl.stride * sizeof(u64);
+    const size_t arena_bytes_per_pair = (size_t)std::max(b->max_rows, 1) * sizeof(esfm_dmatch_t);
+    const size_t budget_keys = (size_t)4 << 30, budget_arena = (size_t)2 << 30;
+    size_t c = std::min(budget_keys / key_bytes_per_pair, budget_arena / arena_bytes_per_pair);
+    c = std::max<size_t>(1, std::min<size_t>(c, 65536));
+    pl.chunk_pairs = (size_t)std::min<int64_t>((int64_t)c, std::max<int64_t>(n_pairs, 1));
+    return pl;
+}
+
+int ensure_scratch(esfm_ctx* ctx, const esfm_bank* b, const ChunkPlan& pl) {
+    size_t key_elems = pl.chunk_pairs * 4 * (size_t)pl.stride;
+    size_t cap = ctx->keys_bytes / sizeof(u64);
+    if (int rc = grow(&ctx->keys, &cap, key_elems)) return rc;
+    ctx->keys_bytes = cap * sizeof(u64);
+    size_t arena_need = pl.chunk_pairs * (size_t)std::max(b->max_rows, 1);
+    if (int rc = grow(&ctx->arena, &ctx->arena_cap, arena_need)) return rc;
+    if (ctx->pairs_cap < pl.chunk_pairs) {
+        size_t c1 = ctx->pairs_cap, c2 = ctx->pairs_cap, c3 = ctx->pairs_cap;
+        if (int rc = grow(&ctx->d_pairs, &c1, pl.chunk_pairs)) return rc;
+        if (int rc = grow(&ctx->d_pair_off, &c2, pl.chunk_pairs)) return rc;
+        if (int rc = grow(&ctx->d_pair_cnt, &c3, pl.chunk_pairs)) return rc;
+        ctx->pairs_cap = pl.chunk_pairs;
+    }
+    return ESFM_OK;
+}
+
+int units_per_pair(const esfm_ctx* ctx, const esfm_bank* b, size_t n_chunk_pairs) {
+    if (n_chunk_pairs >= (size_t)2 * ctx->sm_count) return 1;
+    const int qblock_rows = b->kind == ESFM_KIND_F32X64 ? kQTiles * kTile : kConsumerThreads * kHamRQ;
+    const int max_blocks = std::max(1, (b->max_rows + qblock_rows - 1) / qblock_rows);
+    const int want = (int)((2 * (size_t)ctx->sm_count + n_chunk_pairs - 1) / std::max<size_t>(n_chunk_pairs, 1));
+    return std::max(1, std::min(want, max_blocks));
+}
+
+// Runs sweep + finalize for one chunk that is already described in ctx->d_pairs.
+int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double ratio, int cross_check, int32_t* knn_idx,
+              float* knn_dist) {
+    CUDA_TRY(cudaMemsetAsync(ctx->keys, 0xFF, n * 4 * (size_t)pl.stride * sizeof(u64), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_cursor, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    SweepParams sp{};
+    sp.kmajor = b->d_kmajor;
+    sp.rows_b256 = (const uint4*)b->d_rows;
+    sp.frame_rows = b->d_frame_rows;
+    sp.frame_row_off = b->d_row_off;
+    sp.frame_tile_off = b->d_tile_off;
+    sp.pairs = ctx->d_pairs;
+    sp.n_pairs = (int)n;
+    sp.units_per_pair = units_per_pair(ctx, b, n);
+    sp.keys = ctx->keys;
+    sp.stride = pl.stride;
+    sp.col_cap = pl.col_cap;
+    if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+    cudaError_t e = b->kind == ESFM_KIND_F32X64 ? launch_sweep_l2(sp, ctx->sm_count, ctx->stream)
+                                                : launch_sweep_hamming(sp, ctx->sm_count, ctx->stream);
+    if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(e));
+    if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+    FinalizeParams fp{};
+    fp.kind = b->kind;
+    fp.rows_f32 = (const float*)b->d_rows;
+    fp.rows_b256 = (const uint4*)b->d_rows;
+    fp.frame_rows = b->d_frame_rows;
+    fp.frame_row_off = b->d_row_off;
+    fp.pairs = ctx->d_pairs;
+    fp.n_pairs = (int)n;
+    fp.keys = ctx->keys;
+    fp.stride = pl.stride;
+    fp.ratio = ratio;
+    fp.cross_check = cross_check ? 1 : 0;
+    fp.arena = ctx->arena;
+    fp.arena_cap = ctx->arena_cap;
+    fp.cursor = ctx->d_cursor;
+    fp.overflow = (int*)(ctx->d_cursor + 1);
+    fp.pair_off = ctx->d_pair_off;
+    fp.pair_cnt = ctx->d_pair_cnt;
+    fp.knn_idx = knn_idx;
+    fp.knn_dist = knn_dist;
+    e = launch_finalize(fp, ctx->stream);
+    if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "finalize kernel launch failed: %s", cudaGetErrorString(e));
+    if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+    ctx->stats.kernel_launches += 2;
+    ctx->stats.sweep_launches += 1;
+    ctx->arena_generation += 1;
+    return ESFM_OK;
+}
+
+int collect_timing(esfm_ctx* ctx) {
+    if (!ctx->profiling) return ESFM_OK;
+    float a = 0.f, c = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&c, ctx->ev[1], ctx->ev[2]));
+    ctx->stats.last_sweep_ms = a;
+    ctx->stats.last_finalize_ms = c;
+    ctx->stats.sweep_ms_total += a;
+    return ESFM_OK;
+}
+
+int match_pairs_impl(esfm_bank* b, const esfm_pair_t* pairs, int64_t n_pairs, double ratio, int cross_check, bool fetch,
+                     esfm_results** out) {
+    if (!b || !out) return fail(ESFM_ERR_INVALID, "esfm_match_pairs: NULL argument");
+    *out = nullptr;
+    if (!b->committed) return fail(ESFM_ERR_STATE, "esfm_match_pairs: bank not committed");
+    if (n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(ESFM_ERR_INVALID, "esfm_match_pairs: bad pair list");
+    if (!(ratio == ratio)) return fail(ESFM_ERR_INVALID, "ratio is NaN");
+    esfm_ctx* ctx = b->ctx;
+    if (int rc = set_device(ctx)) return rc;
+    for (int64_t k = 0; k < n_pairs; ++k)
+        if (pairs[k].query < 0 || pairs[k].query >= b->n_frames || pairs[k].train < 0 || pairs[k].train >= b->n_frames)
+            return fail(ESFM_ERR_INVALID, "pair %lld = (%d,%d) out of range [0,%d)", (long long)k, pairs[k].query, pairs[k].train, b->n_frames);
+
+    esfm_results* res = new (std::nothrow) esfm_results();
+    if (!res) return fail(ESFM_ERR_NOMEM, "out of host memory");
+    res->ctx = ctx;
+    res->pairs.resize((size_t)n_pairs);
+    res->counts.assign((size_t)n_pairs, 0);
+    res->offsets.assign((size_t)n_pairs, 0);
+    res->fetched = fetch;
+    for (int64_t k = 0; k < n_pairs; ++k) {
+        res->pairs[(size_t)k].q_frame = pairs[k].query;
+        res->pairs[(size_t)k].t_frame = pairs[k].train;
+    }
+    if (n_pairs == 0) { *out = res; return ESFM_OK; }
+
+    const ChunkPlan pl = plan_chunks(b, n_pairs);
+    if (int rc = ensure_scratch(ctx, b, pl)) { delete res; return rc; }
+    const size_t n_chunks = ((size_t)n_pairs + pl.chunk_pairs - 1) / pl.chunk_pairs;
+    for (size_t c0 = 0; c0 < (size_t)n_pairs; c0 += pl.chunk_pairs) {
+        const size_t n = std::min(pl.chunk_pairs, (size_t)n_pairs - c0);
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_pairs, res->pairs.data() + c0, n * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stats.h2d_bytes += n * sizeof(PairDesc);
+        if (int rc = run_chunk(ctx, b, pl, n, ratio, cross_check, nullptr, nullptr)) { delete res; return rc; }
+        // counts + offsets + cursor back
+        const size_t meta = n * (sizeof(int32_t) + sizeof(unsigned long long)) + 2 * sizeof(unsigned long long);
+        if (int rc = grow_stage(ctx, meta)) { delete res; return rc; }
+        unsigned long long* h_cur = (unsigned long long*)ctx->h_stage;
+        unsigned long long* h_off = h_cur + 2;
+        int32_t* h_cnt = (int32_t*)(h_off + n);
+        CUDA_TRY(cudaMemcpyAsync(h_cur, ctx->d_cursor, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(h_off, ctx->d_pair_off, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(h_cnt, ctx->d_pair_cnt, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->stats.d2h_bytes += meta;
+        if (int rc = collect_timing(ctx)) { delete res; return rc; }
+        const unsigned long long n_matches = h_cur[0];
+        if ((int)h_cur[1] != 0 || n_matches > ctx->arena_cap) { delete res; return fail(ESFM_ERR_CAPACITY, "match arena overflow (internal sizing error)"); }
+        const uint64_t base = res->matches.size();
+        const uint64_t vbase = (uint64_t)res->total_matches;
+        for (size_t k = 0; k < n; ++k) {
+            res->counts[c0 + k] = h_cnt[k];
+            res->offsets[c0 + k] = (fetch ? base : vbase) + h_off[k];
+            const PairDesc& pd = res->pairs[c0 + k];
+            ctx->stats.comparisons += (uint64_t)b->rows[pd.q_frame] * (uint64_t)b->rows[pd.t_frame];
+        }
+        ctx->stats.pairs += n;
+        res->total_matches += (int64_t)n_matches;
+        if (fetch && n_matches > 0) {
+            const size_t bytes = (size_t)n_matches * sizeof(esfm_dmatch_t);
+            res->matches.resize((size_t)base + (size_t)n_matches);
+            if (int rc = grow_stage(ctx, bytes)) { delete res; return rc; }
+            CUDA_TRY(cudaMemcpyAsync(ctx->h_stage, ctx->arena, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            memcpy(res->matches.data() + base, ctx->h_stage, bytes);
+            ctx->stats.d2h_bytes += bytes;
+        } else if (!fetch) {
+            res->device_matches = n_matches;
+            res->arena_generation = ctx->arena_generation;
+            if (n_chunks > 1) res->arena_generation = 0;  // cannot be fetched later: arena is reused per chunk
+        }
+    }
+    *out = res;
+    return ESFM_OK;
+}
+
+void build_index(esfm_results* r) {
+    if (!r->index.empty() || r->pairs.empty()) return;
+    r->index.reserve(r->pairs.size() * 2);
+    for (size_t k = 0; k < r->pairs.size(); ++k) {
+        const uint64_t key = ((uint64_t)(uint32_t)r->pairs[k].q_frame << 32) | (uint32_t)r->pairs[k].t_frame;
+        r->index.emplace(key, (int64_t)k);
+    }
+}
+
+}  // namespace
+
+extern "C" int esfm_match_pairs(esfm_bank_t* b, const esfm_pair_t* pairs, int64_t n_pairs, double ratio, int cross_check,
+                                esfm_results_t** results) {
+    return match_pairs_impl(b, pairs, n_pairs, ratio, cross_check, true, results);
+}
+
+extern "C" int esfm_match_pairs_device(esfm_bank_t* b, const esfm_pair_t* pairs, int64_t n_pairs, double ratio,
+                                       int cross_check, esfm_results_t** results) {
+    return match_pairs_impl(b, pairs, n_pairs, ratio, cross_check, false, results);
+}
+
+extern "C" int esfm_results_fetch(esfm_results_t* r) {
+    if (!r) return fail(ESFM_ERR_INVALID, "results is NULL");
+    if (r->fetched) return ESFM_OK;
+    esfm_ctx* ctx = r->ctx;
+    if (r->arena_generation == 0 || r->arena_generation != ctx->arena_generation)
+        return fail(ESFM_ERR_STATE, "device-resident matches are gone (the arena was reused by a later batch or the batch spanned several chunks)");
+    if (int rc = set_device(ctx)) return rc;
+    if (r->device_matches > 0) {
+        const size_t bytes = (size_t)r->device_matches * sizeof(esfm_dmatch_t);
+        r->matches.resize((size_t)r->device_matches);
+        if (int rc = grow_stage(ctx, bytes)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_stage, ctx->arena, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        memcpy(r->matches.data(), ctx->h_stage, bytes);
+        ctx->stats.d2h_bytes += bytes;
+    }
+    r->fetched = true;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_match_all_pairs(esfm_bank_t* b, double ratio, int cross_check, esfm_results_t** results) {
+    if (!b || !results) return fail(ESFM_ERR_INVALID, "esfm_match_all_pairs: NULL argument");
+    std::vector<esfm_pair_t> pairs;
+    const int n = b->n_frames;
+    pairs.reserve((size_t)n * (size_t)(n > 0 ? n - 1 : 0) / 2);
+    for (int i = 0; i < n; ++i)           // cpp_code/test/sfm.cpp:140
+        for (int j = 0; j < i; ++j) {     // cpp_code/test/sfm.cpp:143
+            esfm_pair_t p;
+            p.query = i;                  // frames[i] is cur_frame_1 = query  (sfm.cpp:153,156)
+            p.train = j;
+            pairs.push_back(p);
+        }
+    return match_pairs_impl(b, pairs.data(), (int64_t)pairs.size(), ratio, cross_check, true, results);
+}
+
+extern "C" int esfm_match_pair(esfm_bank_t* b, int query_frame, int train_frame, double ratio, int cross_check,
+                               esfm_dmatch_t* out, int cap, int* n_matches) {
+    if (!n_matches) return fail(ESFM_ERR_INVALID, "n_matches is NULL");
+    *n_matches = 0;
+    esfm_pair_t p;
+    p.query = query_frame;
+    p.train = train_frame;
+    esfm_results* r = nullptr;
+    if (int rc = match_pairs_impl(b, &p, 1, ratio, cross_check, true, &r)) return rc;
+    const int n = r->counts[0];
+    if (n > cap || (n > 0 && !out)) {
+        delete r;
+        return fail(ESFM_ERR_CAPACITY, "output buffer holds %d matches, %d needed", cap, n);
+    }
+    if (n > 0) memcpy(out, r->matches.data() + r->offsets[0], (size_t)n * sizeof(esfm_dmatch_t));
+    *n_matches = n;
+    delete r;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_match_descriptors(esfm_ctx_t* ctx, esfm_kind kind, const void* query, int rows_q, size_t step_q,
+                                      const void* train, int rows_t, size_t step_t, int cols, double ratio, int cross_check,
+                                      esfm_dmatch_t* out, int cap, int* n_matches) {
+    if (!n_matches) return fail(ESFM_ERR_INVALID, "n_matches is NULL");
+    *n_matches = 0;
+    esfm_bank* b = nullptr;
+    if (int rc = esfm_bank_create(ctx, kind, 2, &b)) return rc;
+    int rc = esfm_bank_set_frame(b, 0, query, rows_q, cols, step_q);
+    if (!rc) rc = esfm_bank_set_frame(b, 1, train, rows_t, cols, step_t);
+    if (!rc) rc = esfm_bank_commit(b);
+    if (!rc) rc = esfm_match_pair(b, 0, 1, ratio, cross_check, out, cap, n_matches);
+    esfm_bank_destroy(b);
+    return rc;
+}
+
+extern "C" int esfm_knn2_pair(esfm_bank_t* b, int query_frame, int train_frame, int32_t* idx, float* dist) {
+    if (!b || !idx || !dist) return fail(ESFM_ERR_INVALID, "esfm_knn2_pair: NULL argument");
+    if (!b->committed) return fail(ESFM_ERR_STATE, "bank not committed");
+    if (query_frame < 0 || query_frame >= b->n_frames || train_frame < 0 || train_frame >= b->n_frames)
+        return fail(ESFM_ERR_INVALID, "frame index out of range");
+    esfm_ctx* ctx = b->ctx;
+    if (int rc = set_device(ctx)) return rc;
+    const int fq = b->rows[query_frame];
+    if (fq == 0) return ESFM_OK;
+    const ChunkPlan pl = plan_chunks(b, 1);
+    if (int rc = ensure_scratch(ctx, b, pl)) return rc;
+    int32_t* d_idx = nullptr;
+    float* d_dist = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_idx, (size_t)fq * 2 * sizeof(int32_t)));
+    cudaError_t e = cudaMalloc((void**)&d_dist, (size_t)fq * 2 * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(d_idx); return fail(ESFM_ERR_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    PairDesc pd;
+    pd.q_frame = query_frame;
+    pd.t_frame = train_frame;
+    int rc = ESFM_OK;
+    e = cudaMemcpyAsync(ctx->d_pairs, &pd, sizeof pd, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) rc = fail(ESFM_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+    if (!rc) rc = run_chunk(ctx, b, pl, 1, 0.0, 0, d_idx, d_dist);
+    if (!rc) {
+        e = cudaMemcpyAsync(idx, d_idx, (size_t)fq * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dist, d_dist, (size_t)fq * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ESFM_ERR_CUDA, "knn2 copy back failed: %s", cudaGetErrorString(e));
+        ctx->stats.d2h_bytes += (size_t)fq * 16;
+        ctx->stats.pairs += 1;
+        ctx->stats.comparisons += (uint64_t)fq * (uint64_t)b->rows[train_frame];
+    }
+    cudaFree(d_idx);
+    cudaFree(d_dist);
+    if (!rc) rc = collect_timing(ctx);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------------
+extern "C" int esfm_results_counts(esfm_results_t* r, int64_t* n_pairs, int64_t* n_matches) {
+    if (!r) return fail(ESFM_ERR_INVALID, "results is NULL");
+    if (n_pairs) *n_pairs = (int64_t)r->pairs.size();
+    if (n_matches) *n_matches = r->total_matches;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_results_pair_at(esfm_results_t* r, int64_t k, int* query_frame, int* train_frame,
+                                    const esfm_dmatch_t** matches, int* n_matches) {
+    if (!r) return fail(ESFM_ERR_INVALID, "results is NULL");
+    if (k < 0 || k >= (int64_t)r->pairs.size()) return fail(ESFM_ERR_INVALID, "pair index %lld out of range", (long long)k);
+    if (query_frame) *query_frame = r->pairs[(size_t)k].q_frame;
+    if (train_frame) *train_frame = r->pairs[(size_t)k].t_frame;
+    if (n_matches) *n_matches = r->counts[(size_t)k];
+    if (matches) {
+        if (!r->fetched) return fail(ESFM_ERR_STATE, "matches are device-resident; call esfm_results_fetch first");
+        *matches = r->counts[(size_t)k] > 0 ? r->matches.data() + r->offsets[(size_t)k] : nullptr;
+    }
+    return ESFM_OK;
+}
+
+extern "C" int esfm_results_pair(esfm_results_t* r, int query_frame, int train_frame, const esfm_dmatch_t** matches,
+                                 int* n_matches) {
+    if (!r) return fail(ESFM_ERR_INVALID, "results is NULL");
+    build_index(r);
+    const uint64_t key = ((uint64_t)(uint32_t)query_frame << 32) | (uint32_t)train_frame;
+    auto it = r->index.find(key);
+    if (it == r->index.end()) return fail(ESFM_ERR_INVALID, "pair (%d,%d) is not part of this batch", query_frame, train_frame);
+    return esfm_results_pair_at(r, it->second, nullptr, nullptr, matches, n_matches);
+}
+
+extern "C" int esfm_results_pair_counts(esfm_results_t* r, int32_t* counts) {
+    if (!r || !counts) return fail(ESFM_ERR_INVALID, "NULL argument");
+    if (!r->counts.empty()) memcpy(counts, r->counts.data(), r->counts.size() * sizeof(int32_t));
+    return ESFM_OK;
+}
+
+extern "C" int esfm_results_destroy(esfm_results_t* r) {
+    delete r;
+    return ESFM_OK;
+}

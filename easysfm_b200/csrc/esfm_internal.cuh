@@ -1,0 +1,173 @@
+// esfm_internal.cuh -- shared declarations of libesfm_match.so (sm_100a only).
+//
+// Data layout in HBM (see DESIGN.md "Data layout"):
+//   F32X64 bank : rows_f32  float[total_rows][64]        row-major, as uploaded (used by the direct-form refinement)
+//                 kmajor    float[n_tiles][64*128 + 128]  per 128-row tile: [k][row] then 128 half squared norms;
+//                                                         pad rows are zeros with half-norm = +inf (self-masking)
+//   B256 bank   : rows_b256 uint4[total_rows][2]          row-major 32 bytes per descriptor
+//   scratch     : per pair slot 4 arrays of `stride` u64 keys: row NN1, row NN2, col NN1, col NN2
+//                 key = (orderable distance bits << 32) | index ; unsigned order == (distance, lowest index)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cfloat>
+
+#include "../../include/esfm_match.h"
+
+namespace esfm {
+
+typedef unsigned long long u64;
+
+constexpr int kDim = 64;                             // SURF descriptor length (floats)
+constexpr int kTile = 128;                           // rows per k-major tile
+constexpr int kTileFloats = kDim * kTile + kTile;    // 8192 operand floats + 128 half norms
+constexpr int kTileBytes = kTileFloats * 4;          // 33280 B, one bulk copy
+constexpr int kQTiles = 2;                           // query block = 2 tiles = 256 rows
+constexpr int kConsumerThreads = 256;                // 8 consumer warps
+constexpr int kSweepThreads = kConsumerThreads + 128; // + 1 producer warpgroup (only its first lane works)
+constexpr u64 kKeyInit = ~0ull;
+constexpr uint32_t kFltMaxBits = 0x7f7fffffu;
+
+// ORB / Hamming sweep geometry
+constexpr int kHamTile = 256;                        // train rows per smem stage (8 KB)
+constexpr int kHamStages = 4;
+constexpr int kHamRQ = 4;                            // query rows held in registers per thread
+constexpr int kHamIdxBits = 20;                      // packed 32-bit key = dist << 20 | index  (rows per frame < 2^20)
+
+struct PairDesc {
+    int32_t q_frame, t_frame;
+};
+
+struct SweepParams {
+    // bank
+    const float* kmajor;        // F32X64
+    const uint4* rows_b256;     // B256
+    const int* frame_rows;      // [n_frames]
+    const int* frame_row_off;   // [n_frames + 1]
+    const int* frame_tile_off;  // [n_frames + 1]   (F32X64, in tiles)
+    // work
+    const PairDesc* pairs;      // device array of this chunk
+    int n_pairs;
+    int units_per_pair;         // query-range split factor S (>= 1)
+    // scratch
+    u64* keys;                  // [n_pairs][4][stride]
+    int stride;                 // keys per array (>= padded rows of the largest frame in the chunk)
+    int col_cap;                // smem column-threshold capacity in entries (>= padded rows of the largest train frame)
+};
+
+struct FinalizeParams {
+    int kind;
+    const float* rows_f32;
+    const uint4* rows_b256;
+    const int* frame_rows;
+    const int* frame_row_off;
+    const PairDesc* pairs;
+    int n_pairs;
+    u64* keys;
+    int stride;
+    double ratio;
+    int cross_check;
+    esfm_dmatch_t* arena;       // dense match arena
+    unsigned long long arena_cap;
+    unsigned long long* cursor; // arena allocation cursor (matches)
+    unsigned long long* pair_off;  // [n_pairs] offset of each pair's matches in the arena
+    int32_t* pair_cnt;          // [n_pairs]
+    int* overflow;              // set to 1 if the arena was too small
+    // optional raw knn output for one pair (esfm_knn2_pair)
+    int32_t* knn_idx;
+    float* knn_dist;
+};
+
+// ---- host-side launchers (defined in the .cu files) -------------------------------------------
+cudaError_t launch_pack_f32(const float* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
+                            int n_frames, int n_tiles_total, float* kmajor, cudaStream_t s);
+cudaError_t launch_sweep_l2(const SweepParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_sweep_hamming(const SweepParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t s);
+size_t sweep_l2_smem_bytes(int col_cap, int stages);
+size_t sweep_hamming_smem_bytes(int col_cap);
+int sweep_l2_max_rows();       // largest frame (rows) the L2 sweep supports
+int sweep_hamming_max_rows();
+
+// ---- device helpers ------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// Register rebalancing between warpgroups (setmaxnreg works on 4-warp groups): the 384-thread CTA is
+// launched at 168 regs/thread; the producer group drops to 40 and the two consumer groups grow to 232.
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+// named barrier over the consumer warps only (the producer warp never joins)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
+
+__device__ __forceinline__ u64 make_key(uint32_t hi, uint32_t idx) { return ((u64)hi << 32) | idx; }
+
+// Insert (value, idx) into the two-slot sorted candidate list {k1 <= k2} that many threads update
+// concurrently, then tighten the shared-memory threshold to the value of the new second-best.
+//   slot 1 = min over all keys; every key except the final minimum is offered to slot 2 exactly once
+//   (either the newcomer, if it lost, or the key it displaced), so slot 2 = second smallest.
+static __device__ __noinline__ void insert_candidate(u64* k1, u64* k2, uint32_t* thr_bits, float v, uint32_t idx) {
+    const uint32_t vb = __float_as_uint(fmaxf(v, 0.0f));  // clamp the -1e-7 rounding noise: bits of x >= 0 order as uint
+    const u64 key = make_key(vb, idx);
+    const u64 old1 = atomicMin(k1, key);
+    const u64 loser = old1 > key ? old1 : key;
+    u64 cur2 = *reinterpret_cast<volatile u64*>(k2);
+    if (loser < cur2) {
+        const u64 old2 = atomicMin(k2, loser);
+        cur2 = old2 < loser ? old2 : loser;
+    }
+    atomicMin(thr_bits, (uint32_t)(cur2 >> 32));
+}
+
+// Direct-form squared-difference distance with the summation order fixed in oracle/bf_oracle.c:
+// four partial sums over dims j = l (mod 4), fused multiply-add, (s0+s1)+(s2+s3), IEEE sqrt.
+__device__ __forceinline__ float l2_direct(const float* __restrict__ a, const float* __restrict__ b) {
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kDim / 4; ++j) {
+        const float4 x = __ldg(a4 + j), y = __ldg(b4 + j);
+        const float t0 = __fsub_rn(x.x, y.x), t1 = __fsub_rn(x.y, y.y), t2 = __fsub_rn(x.z, y.z), t3 = __fsub_rn(x.w, y.w);
+        s0 = __fmaf_rn(t0, t0, s0);
+        s1 = __fmaf_rn(t1, t1, s1);
+        s2 = __fmaf_rn(t2, t2, s2);
+        s3 = __fmaf_rn(t3, t3, s3);
+    }
+    return __fsqrt_rn(__fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3)));
+}
+#endif  // __CUDACC__
+
+}  // namespace esfm

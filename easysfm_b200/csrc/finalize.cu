@@ -1,0 +1,200 @@
+// finalize.cu -- per image pair: exact re-evaluation of the surviving candidates, Lowe ratio test,
+// mutual cross-check and stable compaction into the dense match arena.
+//
+// Replaces the reference's ratio loop  cpp_code/src/feature_matching.cpp:84-92 / :129-137
+//   if (nn[i][0].distance < ratio_thre * nn[i][1].distance) matches.push_back(nn[i][0]);
+// (float distances promoted to double, `double ratio_thre` from feature_matching.h:17-21) and the
+// crossCheck=True filter of python_code/feature_match.py:26-27.  Output order = ascending queryIdx,
+// imgIdx = 0, exactly what push_back inside `for i` over the queries produces.
+//
+// L2: the sweep ranks with the expansion 1/2|q|^2 + 1/2|t|^2 - q.t, whose fp32 cancellation error is too
+// large to REPORT.  Here the two row candidates -- and, for the cross-check, the two
+// column candidates of the chosen train row -- are recomputed in direct form sum (a-b)^2 with the
+// summation order fixed in oracle/bf_oracle.c and re-ordered by (distance, index).
+// Hamming: the sweep's integer distances are already exact.
+#include "esfm_internal.cuh"
+
+namespace esfm {
+
+namespace {
+
+constexpr int kFinThreads = 256;
+
+struct RowResult {
+    int t1;
+    float d1;
+    bool keep;
+};
+
+__device__ __forceinline__ void order2(float& da, int& ia, float& db, int& ib) {
+    // ascending by (distance, index)
+    if (db < da || (db == da && ib < ia)) {
+        const float td = da; da = db; db = td;
+        const int ti = ia; ia = ib; ib = ti;
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ RowResult eval_row(const FinalizeParams& p, const u64* rk1, const u64* rk2, const u64* ck1,
+                                              const u64* ck2, const float* qrows, const float* trows, int q, int fq,
+                                              int32_t* knn_idx, float* knn_dist) {
+    RowResult r;
+    r.keep = false;
+    r.t1 = -1;
+    r.d1 = 0.f;
+    const u64 k1 = rk1[q], k2 = rk2[q];
+    int i1 = -1, i2 = -1;
+    float d1 = __int_as_float(0x7f800000), d2 = d1;
+    if (k1 != kKeyInit) {
+        i1 = (int)(uint32_t)k1;
+        if (KIND == ESFM_KIND_F32X64) d1 = l2_direct(qrows + (size_t)q * kDim, trows + (size_t)i1 * kDim);
+        else d1 = (float)(uint32_t)(k1 >> 32);
+    }
+    if (k2 != kKeyInit) {
+        i2 = (int)(uint32_t)k2;
+        if (KIND == ESFM_KIND_F32X64) {
+            d2 = l2_direct(qrows + (size_t)q * kDim, trows + (size_t)i2 * kDim);
+            order2(d1, i1, d2, i2);
+        } else {
+            d2 = (float)(uint32_t)(k2 >> 32);
+        }
+    }
+    if (knn_idx) {
+        knn_idx[2 * q] = i1; knn_idx[2 * q + 1] = i2;
+        knn_dist[2 * q] = d1; knn_dist[2 * q + 1] = d2;
+    }
+    if (p.ratio == __longlong_as_double(0x7ff0000000000000LL)) {
+        // ratio = +inf: no ratio test (plain mutual-NN matching, python_code/feature_match.py:26-27)
+        if (i1 < 0) return r;
+    } else {
+        if (i2 < 0) return r;  // fewer than two neighbours: the reference has no defined behaviour, we emit nothing (F7)
+        if (!((double)d1 < p.ratio * (double)d2)) return r;
+    }
+    if (p.cross_check) {
+        // nearest query row of train row i1 (lowest index on ties) must be q
+        const u64 c1 = ck1[i1];
+        int best = (int)(uint32_t)c1;
+        if (KIND == ESFM_KIND_F32X64) {
+            const u64 c2 = ck2[i1];
+            if (c2 != kKeyInit) {
+                int a = best, b = (int)(uint32_t)c2;
+                float da = l2_direct(qrows + (size_t)a * kDim, trows + (size_t)i1 * kDim);
+                float db = l2_direct(qrows + (size_t)b * kDim, trows + (size_t)i1 * kDim);
+                order2(da, a, db, b);
+                best = a;
+            }
+        }
+        if (c1 == kKeyInit || best != q) return r;
+    }
+    r.keep = true;
+    r.t1 = i1;
+    r.d1 = d1;
+    (void)fq;
+    return r;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeParams p) {
+    const int pair = blockIdx.x;
+    const PairDesc pd = p.pairs[pair];
+    const int fq = p.frame_rows[pd.q_frame], ft = p.frame_rows[pd.t_frame];
+    u64* rk1 = p.keys + (size_t)pair * 4 * p.stride;
+    u64* rk2 = rk1 + p.stride;
+    const u64* ck1 = rk2 + p.stride;
+    const u64* ck2 = ck1 + p.stride;
+    const float* qrows = nullptr;
+    const float* trows = nullptr;
+    if (KIND == ESFM_KIND_F32X64) {
+        qrows = p.rows_f32 + (size_t)p.frame_row_off[pd.q_frame] * kDim;
+        trows = p.rows_f32 + (size_t)p.frame_row_off[pd.t_frame] * kDim;
+    }
+    __shared__ unsigned int s_warp[kFinThreads / 32];
+    __shared__ unsigned long long s_base;
+    __shared__ unsigned int s_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const bool no_ratio = p.ratio == __longlong_as_double(0x7ff0000000000000LL);
+    if (fq == 0 || ft < (no_ratio ? 1 : 2)) {  // F7: no second neighbour exists
+        if (p.knn_idx) {
+            for (int q = threadIdx.x; q < fq; q += kFinThreads) {
+                RowResult r = eval_row<KIND>(p, rk1, rk2, ck1, ck2, qrows, trows, q, fq, p.knn_idx, p.knn_dist);
+                (void)r;
+            }
+        }
+        if (threadIdx.x == 0) {
+            p.pair_cnt[pair] = 0;
+            p.pair_off[pair] = 0;
+        }
+        return;
+    }
+
+    // pass 1: evaluate every query row; stash the verdict in the row's first key slot
+    unsigned int mine = 0;
+    for (int q = threadIdx.x; q < fq; q += kFinThreads) {
+        const RowResult r = eval_row<KIND>(p, rk1, rk2, ck1, ck2, qrows, trows, q, fq, p.knn_idx, p.knn_dist);
+        rk1[q] = r.keep ? make_key(__float_as_uint(r.d1), (uint32_t)r.t1) : kKeyInit;
+        mine += r.keep ? 1u : 0u;
+    }
+    // block total -> one arena allocation per pair
+    unsigned int wsum = __reduce_add_sync(0xffffffffu, mine);
+    if (lane == 0) s_warp[warp] = wsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int tot = 0;
+        for (int w = 0; w < kFinThreads / 32; ++w) tot += s_warp[w];
+        s_total = tot;
+        unsigned long long base = 0;
+        if (tot > 0) {
+            base = atomicAdd(p.cursor, (unsigned long long)tot);
+            if (base + tot > p.arena_cap) {
+                *p.overflow = 1;
+                tot = 0;
+                s_total = 0;
+            }
+        }
+        s_base = base;
+        p.pair_cnt[pair] = (int32_t)tot;
+        p.pair_off[pair] = base;
+    }
+    __syncthreads();
+    if (s_total == 0) return;
+
+    // pass 2: stable compaction in ascending query index (rows were written by this block: visible after the barrier)
+    unsigned long long running = s_base;
+    for (int q0 = 0; q0 < fq; q0 += kFinThreads) {
+        const int q = q0 + threadIdx.x;
+        const u64 v = (q < fq) ? rk1[q] : kKeyInit;
+        const bool keep = v != kKeyInit;
+        const unsigned int bal = __ballot_sync(0xffffffffu, keep);
+        __syncthreads();  // s_warp reuse
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        unsigned int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kFinThreads / 32; ++w) {
+            const unsigned int c = s_warp[w];
+            before += (w < warp) ? c : 0u;
+            total += c;
+        }
+        if (keep) {
+            esfm_dmatch_t m;
+            m.queryIdx = q;
+            m.trainIdx = (int32_t)(uint32_t)v;
+            m.imgIdx = 0;
+            m.distance = __uint_as_float((uint32_t)(v >> 32));
+            p.arena[running + before + __popc(bal & ((1u << lane) - 1u))] = m;
+        }
+        running += total;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t s) {
+    if (p.n_pairs <= 0) return cudaSuccess;
+    if (p.kind == ESFM_KIND_F32X64) finalize_kernel<ESFM_KIND_F32X64><<<p.n_pairs, kFinThreads, 0, s>>>(p);
+    else finalize_kernel<ESFM_KIND_B256><<<p.n_pairs, kFinThreads, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace esfm

@@ -1,0 +1,173 @@
+/*
+ * esfm_match.h -- C ABI of libesfm_match.so: B200-native (sm_100a) all-pairs descriptor matching,
+ * the drop-in for EasySFM's matching hot path.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the EasySFM tree):
+ *   - p3dv::FeatureMatching::matchFeaturesORB   cpp_code/include/feature_matching.h:17-18,
+ *                                               cpp_code/src/feature_matching.cpp:71-113
+ *   - p3dv::FeatureMatching::matchFeaturesSURF  cpp_code/include/feature_matching.h:20-21,
+ *                                               cpp_code/src/feature_matching.cpp:115-158
+ *   - the all-pairs driver loop                 cpp_code/test/sfm.cpp:140-161  (query = frame i, train = frame j < i)
+ *   - frame_t::descriptors / frame_pair_t::matches   cpp_code/include/utility.h:31,62
+ *   - Python pairwise_match matcher calls       python_code/feature_match.py:24-39
+ *
+ * Semantics (identical to OpenCV BFMatcher as the reference calls it):
+ *   forward brute-force 2-NN (L2 on 64 x fp32, Hamming on 256 bits), lowest train index on ties;
+ *   keep NN1 iff (double)d1 < ratio * (double)d2  (feature_matching.cpp:88,133);
+ *   if cross_check: keep (q,t) only if q is the nearest query row of train row t (lowest index on ties)
+ *   (feature_match.py:26-27); output in ascending queryIdx with imgIdx = 0 (feature_matching.cpp:84-91).
+ *   A train frame with fewer than 2 rows yields zero matches (the reference reads out of bounds there).
+ *   ratio = +infinity disables the ratio test (no second neighbour needed): with cross_check = 1 that is
+ *   cv2.BFMatcher(norm, crossCheck=True).match of feature_match.py:26-27, in ascending queryIdx.
+ *   cross_check = 0 with ESFM_KIND_B256 reproduces matchFeaturesORB exactly.
+ *
+ * Error convention: every function returns 0 on success and a nonzero esfm_status otherwise; nothing
+ * throws across the boundary; esfm_last_error() returns a message for the calling thread's last failure.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with ESFM_ERR_CUDA.
+ *
+ * Threading: one host thread drives one context; calls on one context are not re-entrant.
+ */
+#ifndef ESFM_MATCH_H_
+#define ESFM_MATCH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESFM_ABI_VERSION 1
+
+typedef enum esfm_status {
+    ESFM_OK = 0,
+    ESFM_ERR_INVALID = 1,  /* bad argument (null pointer, wrong cols/kind, index out of range, ...) */
+    ESFM_ERR_CUDA = 2,     /* CUDA runtime / driver failure, or no usable device */
+    ESFM_ERR_STATE = 3,    /* call order violated (e.g. matching before esfm_bank_commit) */
+    ESFM_ERR_NOMEM = 4,    /* host or device allocation failed */
+    ESFM_ERR_CAPACITY = 5  /* caller-provided output buffer too small, or frame too large for the kernels */
+} esfm_status;
+
+/* Descriptor kinds: the two the reference produces (feature_matching.cpp:16-22 ORB 32 bytes, :45-52 SURF 64 floats). */
+typedef enum esfm_kind {
+    ESFM_KIND_F32X64 = 0, /* SURF: rows x 64 float32, L2 distance          (cv::Mat CV_32FC1) */
+    ESFM_KIND_B256 = 1    /* ORB : rows x 32 uint8 (256 bits), Hamming     (cv::Mat CV_8UC1)  */
+} esfm_kind;
+
+/* Layout-identical to cv::DMatch (16 bytes) so a C++ shim can insert() it straight into std::vector<cv::DMatch>. */
+typedef struct esfm_dmatch_t {
+    int32_t queryIdx;
+    int32_t trainIdx;
+    int32_t imgIdx; /* always 0, as in the reference */
+    float distance; /* L2: sqrt(sum (a-b)^2); Hamming: bit count as float */
+} esfm_dmatch_t;
+
+/* One unit of the pair schedule: match frame `query` (rows = queries) against frame `train`. */
+typedef struct esfm_pair_t {
+    int32_t query;
+    int32_t train;
+} esfm_pair_t;
+
+typedef struct esfm_ctx esfm_ctx_t;         /* one CUDA device + stream + scratch */
+typedef struct esfm_bank esfm_bank_t;       /* device-resident descriptor bank (all frames of one kind) */
+typedef struct esfm_results esfm_results_t; /* host-resident compacted matches of a batch of pairs */
+
+/* Counters a caller (bench.py) reads back; all cumulative since esfm_init. */
+typedef struct esfm_stats_t {
+    uint64_t kernel_launches;  /* CUDA kernels launched by this library */
+    uint64_t h2d_bytes;        /* host->device bytes copied */
+    uint64_t d2h_bytes;        /* device->host bytes copied */
+    uint64_t comparisons;      /* descriptor comparisons evaluated (rows_q * rows_t per pair, counted once) */
+    uint64_t pairs;            /* image pairs matched */
+    double last_sweep_ms;      /* device time of the most recent distance/top-2 sweep kernel (CUDA events) */
+    double last_finalize_ms;   /* device time of the most recent refine/ratio/cross-check/compaction kernel */
+    double sweep_ms_total;     /* sum of sweep kernel device times */
+    uint64_t sweep_launches;   /* number of sweep kernel launches */
+} esfm_stats_t;
+
+int esfm_abi_version(void);
+
+/* Message for the calling thread's most recent failing call ("" if none). Never NULL. */
+const char* esfm_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+/* Bind a context to CUDA device `device`.  `cuda_stream` is a cudaStream_t to launch on (so the caller
+ * can bracket work with its own CUDA events), or NULL to let the library create its own stream. */
+int esfm_init(int device, void* cuda_stream, esfm_ctx_t** ctx);
+int esfm_destroy(esfm_ctx_t* ctx);
+int esfm_synchronize(esfm_ctx_t* ctx);
+int esfm_get_stats(esfm_ctx_t* ctx, esfm_stats_t* out);
+/* Time the sweep/finalize kernels with CUDA events (default on; costs two event records per launch). */
+int esfm_set_profiling(esfm_ctx_t* ctx, int enabled);
+/* Number of SMs of the bound device (grid sizing is a multiple of this). */
+int esfm_device_sm_count(esfm_ctx_t* ctx, int* sms);
+
+/* ---- descriptor bank (replaces the per-call cv::Mat arguments; utility.h:31) ---------------- */
+
+int esfm_bank_create(esfm_ctx_t* ctx, esfm_kind kind, int n_frames, esfm_bank_t** bank);
+/* Copy one frame's descriptors (frame_t::descriptors: .data, .rows, .cols, .step).  cols must be 64
+ * (F32X64, elements are float) or 32 (B256, elements are uint8).  rows may be 0.  The host pointer
+ * need not outlive the call.  `frame_id` in [0, n_frames).  May be called again before commit. */
+int esfm_bank_set_frame(esfm_bank_t* bank, int frame_id, const void* data, int rows, int cols, size_t step_bytes);
+/* Declare a frame's row count without host data: for banks whose rows arrive on the device
+ * (esfm_bank_device_rows + an NCCL broadcast driven by the host process). */
+int esfm_bank_set_frame_rows(esfm_bank_t* bank, int frame_id, int rows);
+/* Pack -> one host->device copy -> derived device layouts (k-major tiles + half squared norms for
+ * F32X64).  After commit the bank is immutable and resident in HBM until destroyed. */
+int esfm_bank_commit(esfm_bank_t* bank);
+/* Allocate device storage from the declared row counts only (no host data, no copy). */
+int esfm_bank_alloc_device(esfm_bank_t* bank);
+/* Raw row-major device buffer of all frames back to back (frame f starts at row offset sum(rows[<f])):
+ * F32X64 -> float[total_rows][64], B256 -> uint8[total_rows][32].  Valid after commit/alloc_device. */
+int esfm_bank_device_rows(esfm_bank_t* bank, void** dev_ptr, size_t* bytes);
+/* Rebuild the derived layouts after the caller wrote the raw device buffer (e.g. by broadcast). */
+int esfm_bank_commit_device(esfm_bank_t* bank);
+int esfm_bank_n_frames(esfm_bank_t* bank, int* n_frames);
+int esfm_bank_frame_rows(esfm_bank_t* bank, int frame_id, int* rows);
+int esfm_bank_device_bytes(esfm_bank_t* bank, size_t* bytes);
+int esfm_bank_destroy(esfm_bank_t* bank);
+
+/* ---- matching ------------------------------------------------------------------------------ */
+
+/* All N(N-1)/2 pairs of the bank in the reference's loop order: for i in [0,N): for j in [0,i):
+ * query = i, train = j  (sfm.cpp:140-161). */
+int esfm_match_all_pairs(esfm_bank_t* bank, double ratio, int cross_check, esfm_results_t** results);
+/* An explicit batch of pairs (the unit a multi-GPU scheduler shards). */
+int esfm_match_pairs(esfm_bank_t* bank, const esfm_pair_t* pairs, int64_t n_pairs, double ratio, int cross_check,
+                     esfm_results_t** results);
+/* Same, but matches stay on the device (no device->host copy); only counts are returned to the host.
+ * Used to measure the device-resident throughput; results can still be fetched with esfm_results_fetch. */
+int esfm_match_pairs_device(esfm_bank_t* bank, const esfm_pair_t* pairs, int64_t n_pairs, double ratio,
+                            int cross_check, esfm_results_t** results);
+int esfm_results_fetch(esfm_results_t* results);
+/* One pair, caller-owned output (the unmodified per-call shape of matchFeaturesORB/SURF).
+ * `cap` = capacity of `out` in matches (rows of the query frame is always enough). */
+int esfm_match_pair(esfm_bank_t* bank, int query_frame, int train_frame, double ratio, int cross_check,
+                    esfm_dmatch_t* out, int cap, int* n_matches);
+/* Two host descriptor matrices in, matches out: literally the reference's call
+ * matchFeaturesX(frame_1 = query, frame_2 = train, matches, ratio).  Uploads both, matches, frees. */
+int esfm_match_descriptors(esfm_ctx_t* ctx, esfm_kind kind, const void* query, int rows_q, size_t step_q,
+                           const void* train, int rows_t, size_t step_t, int cols, double ratio, int cross_check,
+                           esfm_dmatch_t* out, int cap, int* n_matches);
+/* Raw 2-NN of one pair (knnMatch(k=2), feature_matching.cpp:80): idx[2*q+r], dist[2*q+r], r in {0,1};
+ * idx = -1 / dist = +inf where the train frame has fewer rows. */
+int esfm_knn2_pair(esfm_bank_t* bank, int query_frame, int train_frame, int32_t* idx, float* dist);
+
+/* ---- results (replaces frame_pair_t::matches, utility.h:62) -------------------------------- */
+
+int esfm_results_counts(esfm_results_t* results, int64_t* n_pairs, int64_t* n_matches);
+/* k-th pair of the batch in submission order. */
+int esfm_results_pair_at(esfm_results_t* results, int64_t k, int* query_frame, int* train_frame,
+                         const esfm_dmatch_t** matches, int* n_matches);
+/* Lookup by frame ids (first occurrence in the batch). */
+int esfm_results_pair(esfm_results_t* results, int query_frame, int train_frame, const esfm_dmatch_t** matches,
+                      int* n_matches);
+/* Per-pair match counts for the whole batch (n_pairs int32 values). */
+int esfm_results_pair_counts(esfm_results_t* results, int32_t* counts);
+int esfm_results_destroy(esfm_results_t* results);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESFM_MATCH_H_ */

@@ -1,0 +1,164 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same inputs.
+
+Oracles: oracle.match / oracle.knn2 (C restatement, oracle/bf_oracle.c) and oracle.cv2_oracle (the
+reference's own cv2.BFMatcher calls).  Hamming must be bit-exact; L2 within 1e-5 relative (util.REL_TOL).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import cv2_oracle
+from easysfm_b200 import synth
+from util import assert_matches_equal, check_knn_l2, dist64, justify_l2
+
+pytestmark = pytest.mark.gpu
+
+RATIOS = (0.5, 0.8)
+
+
+# --------------------------------------------------------------------------------------------------
+# ORB / Hamming: bit-exact
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nq,nt", [(1, 2), (2, 2), (37, 53), (256, 256), (257, 1025), (1500, 700), (2049, 3000)])
+def test_hamming_pair_bit_exact(ctx, nq, nt):
+    fr = synth.orb_like(2, [nq, nt], seed=nq * 7 + nt)
+    Q, T = fr
+    for ratio in RATIOS:
+        for cc in (False, True):
+            got = ctx.match_descriptors(Q, T, ratio, cc)
+            ref = oracle.match(Q, T, ratio, cc)
+            assert_matches_equal(got, ref)
+    ref_cv = cv2_oracle.match(Q, T, 0.8, True)
+    assert_matches_equal(ctx.match_descriptors(Q, T, 0.8, True), ref_cv)
+
+
+def test_hamming_knn2_ties_lowest_index(ctx):
+    rng = np.random.default_rng(5)
+    T = rng.integers(0, 256, (600, 32), dtype=np.uint8)
+    T[7] = T[3]; T[400] = T[3]; T[599] = T[3]          # exact duplicates: ranks 1,2 must be 3 then 7
+    Q = T[[3, 10, 20]].copy()
+    Q[1, 0] ^= 1
+    bank = ctx.bank_from_frames([Q, T])
+    idx, dist = bank.knn2_pair(0, 1)
+    ridx, rdist = oracle.knn2(Q, T)
+    np.testing.assert_array_equal(idx, ridx)
+    np.testing.assert_array_equal(dist, rdist)
+    assert idx[0].tolist() == [3, 7] and dist[0].tolist() == [0.0, 0.0]
+    cidx, cdist = cv2_oracle.knn2(Q, T)
+    np.testing.assert_array_equal(idx, cidx)
+    np.testing.assert_array_equal(dist, cdist)
+
+
+def test_hamming_all_pairs_ragged(ctx):
+    rows = [900, 0, 1, 2, 1300, 257, 1024]
+    fr = synth.orb_like(len(rows), rows, seed=11)
+    bank = ctx.bank_from_frames(fr)
+    for cc in (False, True):
+        res = bank.match_all_pairs(0.8, cc)
+        assert res.n_pairs == len(rows) * (len(rows) - 1) // 2
+        k = 0
+        for i in range(len(rows)):
+            for j in range(i):
+                q, t, m = res.pair_at(k)
+                assert (q, t) == (i, j)
+                assert_matches_equal(m, oracle.match(fr[i], fr[j], 0.8, cc))
+                assert_matches_equal(res.pair(i, j), m)
+                k += 1
+
+
+# --------------------------------------------------------------------------------------------------
+# SURF / L2
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nq,nt", [(1, 2), (3, 2), (100, 130), (256, 128), (257, 385), (1000, 2000), (2000, 777)])
+def test_l2_pair_vs_oracle(ctx, nq, nt):
+    Q, T = synth.surf_like(2, [nq, nt], seed=nq + 3 * nt)
+    D = dist64(Q, T)
+    bank = ctx.bank_from_frames([Q, T])
+    idx, dist = bank.knn2_pair(0, 1)
+    check_knn_l2(Q, T, idx, dist, D)
+    ridx, rdist = oracle.knn2(Q, T)
+    same = (idx == ridx).all(axis=1)
+    # where the candidates agree the refinement reproduces the oracle's arithmetic bit for bit
+    np.testing.assert_array_equal(dist[same], rdist[same])
+    assert same.mean() > 0.999
+    for ratio in RATIOS:
+        for cc in (False, True):
+            got = ctx.match_descriptors(Q, T, ratio, cc)
+            ref = oracle.match(Q, T, ratio, cc)
+            ndiff = justify_l2(Q, T, ratio, cc, got, ref, D)
+            assert ndiff <= max(1, len(ref) // 500)
+            ref_cv = cv2_oracle.match(Q, T, ratio, cc)
+            justify_l2(Q, T, ratio, cc, got, ref_cv, D)
+
+
+def test_l2_duplicates_and_zero_distance(ctx):
+    Q, T = synth.surf_like(2, [300, 500], seed=77)
+    T[40] = T[17]; T[300] = T[17]; T[499] = T[17]      # three identical train rows (A1 probe)
+    Q[5] = T[17]                                        # d = 0 to all of them
+    Q[6] = Q[5]                                         # duplicate queries: only the lower index survives cross-check
+    bank = ctx.bank_from_frames([Q, T])
+    idx, dist = bank.knn2_pair(0, 1)
+    assert idx[5].tolist() == [17, 40] and dist[5].tolist() == [0.0, 0.0]
+    ridx, rdist = oracle.knn2(Q, T)
+    np.testing.assert_array_equal(idx, ridx)
+    np.testing.assert_array_equal(dist, rdist)
+    cidx, _ = cv2_oracle.knn2(Q, T)
+    np.testing.assert_array_equal(idx, cidx)
+    for cc in (False, True):
+        got = ctx.match_descriptors(Q, T, 0.8, cc)
+        assert_matches_equal(got, oracle.match(Q, T, 0.8, cc))
+        ref_cv = cv2_oracle.match(Q, T, 0.8, cc)
+        assert_matches_equal(got, ref_cv, exact_distance=False)
+
+
+def test_l2_all_pairs_config2_subset(ctx):
+    """BASELINE configs[1] shape (25 x 2k SURF-like), reduced to 6 frames here; ratios 0.5 / 0.8, cross_check 0 / 1."""
+    fr = synth.surf_like(6, 2000, seed=2)
+    bank = ctx.bank_from_frames(fr)
+    for ratio in RATIOS:
+        for cc in (False, True):
+            res = bank.match_all_pairs(ratio, cc)
+            for k in range(res.n_pairs):
+                i, j, m = res.pair_at(k)
+                ref = oracle.match(fr[i], fr[j], ratio, cc)
+                if len(m) == len(ref) and (m["trainIdx"] == ref["trainIdx"]).all():
+                    np.testing.assert_array_equal(m["distance"], ref["distance"])
+                else:
+                    justify_l2(fr[i], fr[j], ratio, cc, m, ref)
+
+
+def test_mutual_nn_mode(ctx):
+    """ratio = +inf: plain mutual nearest neighbour == cv2.BFMatcher(crossCheck=True).match (feature_match.py:26-27)."""
+    Q, T = synth.surf_like(2, [400, 350], seed=9)
+    got = ctx.match_descriptors(Q, T, float("inf"), True)
+    assert_matches_equal(got, oracle.mutual_nn(Q, T))
+    assert_matches_equal(got, cv2_oracle.mutual_nn(Q, T), exact_distance=False)
+    Qb, Tb = synth.orb_like(2, [300, 1], seed=4)    # a single train row still has a nearest neighbour
+    got = ctx.match_descriptors(Qb, Tb, float("inf"), True)
+    assert_matches_equal(got, cv2_oracle.mutual_nn(Qb, Tb))
+
+
+def test_edge_cases(ctx):
+    Q, T = synth.surf_like(2, [50, 1], seed=1)
+    assert len(ctx.match_descriptors(Q, T, 0.8, False)) == 0          # train rows < 2 => no matches (F7)
+    assert len(ctx.match_descriptors(Q[:0], Q, 0.8, True)) == 0       # empty query
+    assert len(ctx.match_descriptors(Q, Q[:0], 0.8, True)) == 0       # empty train
+    Qb = synth.orb_like(1, 64, seed=2)[0]
+    assert len(ctx.match_descriptors(Qb, Qb[:1], 0.8, False)) == 0
+    m = ctx.match_descriptors(Qb, Qb, 0.8, True)                       # identical frames: every row matches itself at d = 0
+    assert (m["queryIdx"] == m["trainIdx"]).all() and (m["distance"] == 0).all()
+    assert_matches_equal(m, oracle.match(Qb, Qb, 0.8, True))
+
+
+def test_error_behaviour(ctx):
+    import easysfm_b200 as esfm
+    b = ctx.bank(esfm.KIND_F32X64, 2)
+    with pytest.raises(esfm.EsfmError):
+        b.set_frame(0, np.zeros((4, 32), np.float32))                  # wrong width
+    with pytest.raises(esfm.EsfmError):
+        b.set_frame(5, np.zeros((4, 64), np.float32))                  # frame id out of range
+    with pytest.raises(esfm.EsfmError):
+        b.match_all_pairs(0.8)                                         # not committed
+    b.set_frame(0, np.zeros((4, 64), np.float32))
+    with pytest.raises(esfm.EsfmError):
+        b.commit()                                                     # frame 1 never set
