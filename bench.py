@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the EasySFM matching hot path on B200 (contract: see task brief §4).
+
+Workload (BASELINE.json configs[3], the config the metric is quoted on): synthetic SURF-like descriptors,
+1000 images x 8000 features x 64 fp32, all-pairs 2-NN + ratio 0.8 + mutual cross-check.  The whole triangle
+is 499,500 image pairs = 3.2e13 comparisons (~1.5 min on one B200), so one *step* is a fixed slice of it:
+  value : `pairs_per_step` consecutive pairs of this rank's block-cyclic shard of the triangle, descriptor bank
+          already resident in HBM (device-resident throughput; only per-pair counts come back to the host);
+  e2e   : the public call a user makes -- esfm_bank_set_frame x M + esfm_bank_commit + esfm_match_all_pairs on M
+          host frames (M(M-1)/2 ~ pairs_per_step), host->device upload of the frames from pinned memory and
+          device->host copy of the compacted matches inside the timed region.
+Both are reported as descriptor comparisons/s (rows_q * rows_t per pair, counted once even with cross-check).
+`--impl reference` times the reference's own CPU path (cv2.BFMatcher knnMatch(k=2) + reverse knnMatch(k=1) as in
+python_code/feature_match.py:26-39) on a bounded sample of the same pairs with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_IMAGES = {"surf": 1000, "orb": 5000}
+N_FEAT = {"surf": 8000, "orb": 4000}
+RATIO = 0.8
+CROSS_CHECK = True
+SEED = {"surf": 4, "orb": 5}
+SM_LANES_FP32 = 128      # FFMA lanes per SM per clock (verified: profiles/pipes_r1.txt)
+POPC_LANES = 16          # POPC lanes per SM per clock (verified: profiles/pipes_r1.txt)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = [x for x in sm if x >= 0.5 * max(sm)]
+        return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_bank_device(kind, n_images, n_feat, seed, dev):
+    import torch
+    from easysfm_b200 import synth
+    if kind == "surf":
+        return synth.surf_like_torch(n_images, n_feat, seed, dev)
+    return synth.orb_like_torch(n_images, n_feat, seed, dev)
+
+
+def cpu_reference_sample(host_bank, pairs, budget_s, cross_check):
+    """Time the reference's cv2 calls on pairs from the same bank until ~budget_s of CPU work is done."""
+    import cv2
+    from oracle import cv2_oracle
+    t_total, n_done, comps = 0.0, 0, 0
+    for (i, j) in pairs:
+        Q, T = host_bank[i], host_bank[j]
+        t_total += cv2_oracle.time_pair(Q, T, cross_check, repeats=1)
+        n_done += 1
+        comps += Q.shape[0] * T.shape[0]
+        if t_total >= budget_s and n_done >= 4:
+            break
+    return comps / t_total, n_done, t_total, cv2.getNumThreads()
+
+
+def run_reference(args, kind):
+    """--impl reference: cv2.BFMatcher on the box's host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import cv2
+    from easysfm_b200 import synth
+    n_feat = N_FEAT[kind]
+    pairs_per_step = args.ref_pairs_per_step
+    n_frames = 2 * pairs_per_step * (args.steps + args.warmup) + 2
+    n_frames = min(n_frames, 64)
+    gen = synth.surf_like if kind == "surf" else synth.orb_like
+    frames = gen(n_frames, n_feat, seed=SEED[kind])
+    cv2.setNumThreads(0)
+    from oracle import cv2_oracle
+    rng = np.random.default_rng(0)
+    def step():
+        comps = 0
+        for _ in range(pairs_per_step):
+            i, j = rng.choice(n_frames, 2, replace=False)
+            cv2_oracle.time_pair(frames[i], frames[j], CROSS_CHECK, repeats=1)
+            comps += frames[i].shape[0] * frames[j].shape[0]
+        return comps
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    comps = 0
+    for _ in range(args.steps):
+        comps += step()
+    dt = time.perf_counter() - t0
+    value = comps / dt
+    sample = f"{pairs_per_step} image pairs of {n_feat}x{n_feat} per step, {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": "descriptor comparisons/sec, all-pairs 2-NN + ratio + cross-check", "value": value,
+        "unit": "comparisons/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if kind == "surf" else "u8", "data": "synthetic",
+        "config": workload_config(kind, pairs_per_step, None),
+        "cpu_baseline": {"value": value, "unit": "comparisons/s", "cores": cv2.getNumThreads(), "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "comparisons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "pairs_per_s": value / (n_feat * n_feat),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(kind, pairs_per_step, e2e_frames):
+    name = {"surf": "synthetic SURF 64-d fp32, 1000 images x 8k features, all-pairs 2-NN + ratio 0.8 + cross-check (BASELINE configs[3])",
+            "orb": "synthetic ORB 256-bit, 5000 images x 4k features, all-pairs Hamming 2-NN + ratio 0.8 + cross-check (BASELINE configs[4])"}[kind]
+    cfg = {"workload": name, "step": f"{pairs_per_step} image pairs per GPU per step (a slice of the pair triangle)",
+           "ratio": RATIO, "cross_check": CROSS_CHECK,
+           "l2_flush": "inputs larger than L2: every step touches new frames of a bank (2.0 GB SURF / 0.64 GB ORB) >> 126 MB L2"}
+    if e2e_frames:
+        cfg["e2e_step"] = f"esfm_match_all_pairs on {e2e_frames} host frames ({e2e_frames * (e2e_frames - 1) // 2} pairs)"
+    return cfg
+
+
+def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budget_s):
+    """Returns the result dict for one descriptor kind (device-resident value, e2e, roofline, cpu baseline)."""
+    import torch
+    from easysfm_b200 import scheduler
+    import easysfm_b200 as esfm
+
+    n_images, n_feat = N_IMAGES[kind], N_FEAT[kind]
+    if args.images:
+        n_images = args.images
+    sms = ctx.sm_count
+    pairs_per_step = args.pairs_per_step or sms * (16 if kind == "surf" else 64)
+    e2e_frames = int((1 + (1 + 8 * pairs_per_step) ** 0.5) / 2)  # M(M-1)/2 ~ pairs_per_step
+
+    # ---- setup (untimed): bank generated on rank 0's GPU, replicated with one NCCL broadcast -------------
+    t_setup = time.perf_counter()
+    kind_id = esfm.KIND_F32X64 if kind == "surf" else esfm.KIND_B256
+    bank = ctx.bank(kind_id, n_images)
+    for f in range(n_images):
+        bank.set_frame_rows(f, n_feat)
+    bank.alloc_device()
+    ptr, nbytes = bank.device_rows()
+    raw = scheduler._wrap_device_bytes(ptr, nbytes, ctx.device)
+    bcast_ms = None
+    if rank == 0:
+        data = make_bank_device(kind, n_images, n_feat, SEED[kind], dev)
+        raw.copy_(data.reshape(-1).view(torch.uint8))
+        del data
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.broadcast(raw, src=0)
+        e1.record()
+        torch.cuda.synchronize()
+        bcast_ms = e0.elapsed_time(e1)
+    torch.cuda.synchronize()
+    bank.commit_device()
+
+    # host copy (pinned) of the frames the e2e steps and the CPU baseline read
+    n_host = min(n_images, e2e_frames * (steps + warmup) + 2)
+    row_bytes = 256 if kind == "surf" else 32
+    host_raw = torch.empty((n_host * n_feat * row_bytes,), dtype=torch.uint8, pin_memory=True)
+    host_raw.copy_(raw[: host_raw.numel()])
+    torch.cuda.synchronize()
+    np_dtype, cols = (np.float32, 64) if kind == "surf" else (np.uint8, 32)
+    host_bank = host_raw.numpy().view(np_dtype).reshape(n_host, n_feat, cols)
+
+    pairs = scheduler.all_pairs(n_images)
+    mine = scheduler.shard_pairs(len(pairs), rank, world, block=64)
+    my_pairs = pairs[mine]
+    need = (steps + warmup) * pairs_per_step
+    if len(my_pairs) < need:
+        reps = (need + len(my_pairs) - 1) // len(my_pairs)
+        my_pairs = np.concatenate([my_pairs] * reps)
+    setup_s = time.perf_counter() - t_setup
+
+    def step_pairs(s):
+        return my_pairs[s * pairs_per_step:(s + 1) * pairs_per_step]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident arm ---------------------------------------------------------------------------
+    for s in range(warmup):
+        bank.match_pairs(step_pairs(s), RATIO, CROSS_CHECK, device_resident=True).close()
+    sampler = ClockSampler(ctx.device)
+    sync_all()
+    sampler.start()
+    st0 = ctx.stats()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    n_matches = 0
+    for s in range(warmup, warmup + steps):
+        r = bank.match_pairs(step_pairs(s), RATIO, CROSS_CHECK, device_resident=True)
+        n_matches += r.n_matches
+        r.close()
+    ev1.record()
+    sync_all()
+    clocks = sampler.stop()
+    st1 = ctx.stats()
+    ms = ev0.elapsed_time(ev1)
+    comps_local = st1["comparisons"] - st0["comparisons"]
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+        c = torch.tensor([float(comps_local)], dtype=torch.float64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        comps_all = float(c.item())
+    else:
+        ms_max, comps_all = ms, float(comps_local)
+    value = comps_all / (ms_max * 1e-3)
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+    sweep_ms = (st1["sweep_ms_total"] - st0["sweep_ms_total"]) / max(1, st1["sweep_launches"] - st0["sweep_launches"])
+    comps_per_launch = comps_local / max(1, st1["sweep_launches"] - st0["sweep_launches"])
+
+    # ---- end-to-end arm: host frames in, host matches out, through the public API ----------------------
+    def e2e_step(s):
+        f0 = (s * e2e_frames) % max(1, n_host - e2e_frames + 1)
+        b = ctx.bank(kind_id, e2e_frames)
+        for k in range(e2e_frames):
+            b.set_frame(k, host_bank[f0 + k])
+        b.commit()
+        res = b.match_all_pairs(RATIO, CROSS_CHECK)
+        nm = res.n_matches
+        res.close()
+        b.close()
+        return nm
+
+    for s in range(warmup):
+        e2e_step(s)
+    sync_all()
+    st2 = ctx.stats()
+    ev0.record()
+    for s in range(warmup, warmup + steps):
+        e2e_step(s)
+    ev1.record()
+    sync_all()
+    st3 = ctx.stats()
+    e2e_ms = ev0.elapsed_time(ev1)
+    e2e_comps_local = st3["comparisons"] - st2["comparisons"]
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        c = torch.tensor([float(e2e_comps_local)], dtype=torch.float64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        e2e_comps = float(c.item())
+    else:
+        e2e_comps = float(e2e_comps_local)
+    e2e = {"value": e2e_comps / (e2e_ms * 1e-3), "unit": "comparisons/s",
+           "h2d_bytes_per_step": int((st3["h2d_bytes"] - st2["h2d_bytes"]) / steps),
+           "d2h_bytes_per_step": int((st3["d2h_bytes"] - st2["d2h_bytes"]) / steps),
+           "ms_per_step": e2e_ms / steps}
+
+    # ---- roofline of the dominant kernel (the sweep) -----------------------------------------------------
+    peaks, peak_src = _peaks()
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    if kind == "surf":
+        unit_ops, unit = 128.0, "TFLOP/s"                      # 64 FFMA = 128 FLOP per comparison
+        peak = sms * SM_LANES_FP32 * 2 * sm_max * 1e6 / 1e12
+        bound = "fp32-fma-pipe"
+        kern = "sweep_l2_kernel"
+    else:
+        unit_ops, unit = 8.0, "TPOPC/s"                        # 8 x 32-bit POPC per comparison
+        peak = sms * POPC_LANES * sm_max * 1e6 / 1e12
+        bound = "popc-pipe"
+        kern = "sweep_hamming_kernel"
+    achieved = comps_per_launch * unit_ops / (sweep_ms * 1e-3) / 1e12
+    roofline = {"bound": bound, "kernel": kern, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                "peak_source": f"{sms} SMs x {'128 FFMA lanes x 2 FLOP' if kind == 'surf' else '16 POPC lanes'} x {sm_max:.0f} MHz "
+                               f"(sm_max_mhz {peak_src}; lanes/clk measured by csrc/microbench/pipes.cu, profiles/pipes_r1.txt)",
+                "kernel_ms": sweep_ms, "comparisons_per_launch": comps_per_launch,
+                "hbm_gbs_algorithmic": None, "traffic": None}
+    if clocks.get("sm_mhz"):
+        roofline["frac_at_sampled_clock"] = achieved / (peak * clocks["sm_mhz"] / sm_max)
+    # algorithmic HBM bytes: every pair reads both frames once + writes its matches
+    bytes_per_pair = 2 * n_feat * (260 if kind == "surf" else 32)
+    roofline["hbm_gbs_algorithmic"] = (comps_per_launch / (n_feat * n_feat)) * bytes_per_pair / (sweep_ms * 1e-3) / 1e9
+    roofline["hbm_peak_gbs"] = peaks.get("hbm_gbs")
+
+    # ---- CPU baseline (rank 0, N = 1 only): the reference's cv2 calls on a bounded sample ----------------
+    cpu = None
+    if rank == 0 and world == 1 and cpu_budget_s > 0:
+        sample_pairs = [(i + 1, i) for i in range(0, min(n_host - 1, 64))]
+        v, n_done, secs, cores = cpu_reference_sample(host_bank, sample_pairs, cpu_budget_s, CROSS_CHECK)
+        cpu = {"value": v, "unit": "comparisons/s", "cores": cores, "kind": "reference",
+               "sample": f"{n_done} image pairs of {n_feat}x{n_feat} ({secs:.1f} s of cv2.BFMatcher knnMatch(k=2) + reverse knnMatch(k=1))",
+               "extrapolated_all_pairs_hours": (n_images * (n_images - 1) / 2) * (n_feat * n_feat) / v / 3600.0}
+
+    out = {
+        "metric": "descriptor comparisons/sec, all-pairs 2-NN + ratio + cross-check", "value": value, "unit": "comparisons/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if kind == "surf" else "u8", "data": "synthetic",
+        "config": workload_config(kind, pairs_per_step, e2e_frames),
+        "pairs_per_s": value / (n_feat * n_feat), "matches_per_step": n_matches / steps,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "setup_s": setup_s, "bank_broadcast_ms": bcast_ms,
+        "full_job_estimate_s": (n_images * (n_images - 1) / 2) * (n_feat * n_feat) / value,
+    }
+    bank.close()
+    del host_bank, host_raw, raw
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kind", default="surf", choices=["surf", "orb"], help="headline descriptor kind")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the second descriptor kind")
+    ap.add_argument("--pairs-per-step", type=int, default=0)
+    ap.add_argument("--images", type=int, default=0, help="override the number of images (smoke runs)")
+    ap.add_argument("--cpu-budget-s", type=float, default=15.0)
+    ap.add_argument("--ref-pairs-per-step", type=int, default=4)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        return run_reference(args, args.kind)
+
+    import torch
+    import torch.distributed as dist
+    import easysfm_b200 as esfm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: easysfm_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    # the library launches on torch's current (non-default) stream so torch.cuda.Event brackets its kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = esfm.Context(local_rank, stream=stream.cuda_stream)
+
+    primary = bench_kind(args, args.kind, ctx, dev, rank, world, dist, args.steps, args.warmup, args.cpu_budget_s)
+    if not args.no_secondary:
+        other = "orb" if args.kind == "surf" else "surf"
+        sec = bench_kind(args, other, ctx, dev, rank, world, dist, max(3, args.steps // 2), args.warmup, args.cpu_budget_s / 2)
+        primary["secondary"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "dtype", "config", "pairs_per_s", "e2e",
+                                                    "roofline", "cpu_baseline", "gpu_launches", "clocks", "full_job_estimate_s")}
+    if rank == 0:
+        print(json.dumps(primary))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

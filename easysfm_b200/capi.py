@@ -83,7 +83,8 @@ _LIB = None
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "lib", "libesfm_match.so")
+    # ESFM_LIBRARY lets kernel experiments load an alternative build of the SAME C ABI (never a CPU path)
+    return os.environ.get("ESFM_LIBRARY") or os.path.join(_HERE, "lib", "libesfm_match.so")
 
 
 def load_library():

@@ -51,6 +51,7 @@ struct esfm_ctx {
     esfm_stats_t stats{};
     // device scratch, grown on demand
     u64* keys = nullptr;           size_t keys_bytes = 0;
+    uint32_t* col_thr = nullptr;   size_t col_thr_elems = 0;
     esfm_dmatch_t* arena = nullptr; size_t arena_cap = 0;   // in matches
     PairDesc* d_pairs = nullptr;   size_t pairs_cap = 0;
     unsigned long long* d_pair_off = nullptr;
@@ -171,7 +172,7 @@ extern "C" int esfm_destroy(esfm_ctx_t* ctx) {
     if (!ctx) return ESFM_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->keys); cudaFree(ctx->arena); cudaFree(ctx->d_pairs); cudaFree(ctx->d_pair_off);
+    cudaFree(ctx->keys); cudaFree(ctx->col_thr); cudaFree(ctx->arena); cudaFree(ctx->d_pairs); cudaFree(ctx->d_pair_off);
     cudaFree(ctx->d_pair_cnt); cudaFree(ctx->d_cursor);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -417,6 +418,8 @@ int ensure_scratch(esfm_ctx* ctx, const esfm_bank* b, const ChunkPlan& pl) {
     size_t cap = ctx->keys_bytes / sizeof(u64);
     if (int rc = grow(&ctx->keys, &cap, key_elems)) return rc;
     ctx->keys_bytes = cap * sizeof(u64);
+    if (b->kind == ESFM_KIND_F32X64)
+        if (int rc = grow(&ctx->col_thr, &ctx->col_thr_elems, pl.chunk_pairs * (size_t)pl.stride)) return rc;
     size_t arena_need = pl.chunk_pairs * (size_t)std::max(b->max_rows, 1);
     if (int rc = grow(&ctx->arena, &ctx->arena_cap, arena_need)) return rc;
     if (ctx->pairs_cap < pl.chunk_pairs) {
@@ -442,6 +445,8 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
               float* knn_dist) {
     CUDA_TRY(cudaMemsetAsync(ctx->keys, 0xFF, n * 4 * (size_t)pl.stride * sizeof(u64), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_cursor, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (b->kind == ESFM_KIND_F32X64)  // column thresholds start at 0x7f7f7f7f = 3.39e38f ("no bound yet")
+        CUDA_TRY(cudaMemsetAsync(ctx->col_thr, 0x7F, n * (size_t)pl.stride * sizeof(uint32_t), ctx->stream));
     SweepParams sp{};
     sp.kmajor = b->d_kmajor;
     sp.rows_b256 = (const uint4*)b->d_rows;
@@ -452,6 +457,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     sp.n_pairs = (int)n;
     sp.units_per_pair = units_per_pair(ctx, b, n);
     sp.keys = ctx->keys;
+    sp.col_thr = ctx->col_thr;
     sp.stride = pl.stride;
     sp.col_cap = pl.col_cap;
     if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));

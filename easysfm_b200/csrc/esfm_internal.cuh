@@ -51,8 +51,9 @@ struct SweepParams {
     int units_per_pair;         // query-range split factor S (>= 1)
     // scratch
     u64* keys;                  // [n_pairs][4][stride]
+    uint32_t* col_thr;          // [n_pairs][stride] running column thresholds (float bits), L2 sweep only
     int stride;                 // keys per array (>= padded rows of the largest frame in the chunk)
-    int col_cap;                // smem column-threshold capacity in entries (>= padded rows of the largest train frame)
+    int col_cap;                // Hamming sweep: smem column-minimum capacity in entries
 };
 
 struct FinalizeParams {
@@ -84,7 +85,7 @@ cudaError_t launch_pack_f32(const float* rows, const int* frame_rows, const int*
 cudaError_t launch_sweep_l2(const SweepParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_sweep_hamming(const SweepParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t s);
-size_t sweep_l2_smem_bytes(int col_cap, int stages);
+size_t sweep_l2_smem_bytes(int stages);
 size_t sweep_hamming_smem_bytes(int col_cap);
 int sweep_l2_max_rows();       // largest frame (rows) the L2 sweep supports
 int sweep_hamming_max_rows();
@@ -133,23 +134,6 @@ template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("set
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 
 __device__ __forceinline__ u64 make_key(uint32_t hi, uint32_t idx) { return ((u64)hi << 32) | idx; }
-
-// Insert (value, idx) into the two-slot sorted candidate list {k1 <= k2} that many threads update
-// concurrently, then tighten the shared-memory threshold to the value of the new second-best.
-//   slot 1 = min over all keys; every key except the final minimum is offered to slot 2 exactly once
-//   (either the newcomer, if it lost, or the key it displaced), so slot 2 = second smallest.
-static __device__ __noinline__ void insert_candidate(u64* k1, u64* k2, uint32_t* thr_bits, float v, uint32_t idx) {
-    const uint32_t vb = __float_as_uint(fmaxf(v, 0.0f));  // clamp the -1e-7 rounding noise: bits of x >= 0 order as uint
-    const u64 key = make_key(vb, idx);
-    const u64 old1 = atomicMin(k1, key);
-    const u64 loser = old1 > key ? old1 : key;
-    u64 cur2 = *reinterpret_cast<volatile u64*>(k2);
-    if (loser < cur2) {
-        const u64 old2 = atomicMin(k2, loser);
-        cur2 = old2 < loser ? old2 : loser;
-    }
-    atomicMin(thr_bits, (uint32_t)(cur2 >> 32));
-}
 
 // Direct-form squared-difference distance with the summation order fixed in oracle/bf_oracle.c:
 // four partial sums over dims j = l (mod 4), fused multiply-add, (s0+s1)+(s2+s3), IEEE sqrt.

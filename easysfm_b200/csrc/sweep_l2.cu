@@ -27,6 +27,12 @@ namespace {
 
 __device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+__device__ __forceinline__ uint4 ldcg_u4(const uint32_t* p) {   // L2-coherent 128-bit load (other CTAs update these)
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ uint4 lds128_volatile_u32(const uint32_t* p) {
     uint4 v;
     asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
@@ -57,6 +63,19 @@ __device__ __forceinline__ UnitInfo decode_unit(const SweepParams& p, int unit) 
 
 }  // namespace
 
+// Packed queue entry: v = candidate value (1/2 d^2), w = type << 30 | row << 15 | col  (rows per frame < 2^15)
+constexpr int kQueueCap = 256;          // per consumer warp
+constexpr int kScratchStride = 20;      // floats per lane (16 used; 80-byte stride keeps STS.128/LDS conflict-free)
+constexpr uint32_t kThrInit = 0x7f7f7f7fu;  // 3.39e38f: what a byte-wise memset(0x7f) of the threshold arrays produces
+
+// Two smallest of a value replicated over a lane group by xor-shuffles: (lo, hi) <- merge with partner's (lo, hi).
+__device__ __forceinline__ void merge_lo_hi(float& lo, float& hi, int xor_mask) {
+    const float plo = __shfl_xor_sync(0xffffffffu, lo, xor_mask);
+    const float phi = __shfl_xor_sync(0xffffffffu, hi, xor_mask);
+    hi = fminf(fmaxf(lo, plo), fminf(hi, phi));
+    lo = fminf(lo, plo);
+}
+
 template <int STAGES>
 __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -68,7 +87,8 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
     uint64_t* emptyQ = bars + 1;
     uint64_t* fullT = bars + 2;
     uint64_t* emptyT = bars + 2 + STAGES;
-    uint32_t* tauc = reinterpret_cast<uint32_t*>(bars + 2 + 2 * STAGES);  // col thresholds, col_cap entries
+    uint2* queues = reinterpret_cast<uint2*>(bars + 2 + 2 * STAGES);      // 8 warps x kQueueCap entries
+    float* scratch = reinterpret_cast<float*>(queues + (kConsumerThreads / 32) * kQueueCap);  // 256 lanes x kScratchStride
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_units = p.n_pairs * p.units_per_pair;
@@ -118,25 +138,27 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
     const int tx = lane & 7;                           // 0..7  : column group
     // rows of this thread inside the tile: r(i) = (i>>2)*64 + ty*4 + (i&3), i < 8
     // cols of this thread inside the tile: c(j) = (j>>2)*32 + tx*4 + (j&3), j < 16
+    uint2* queue = queues + warp * kQueueCap;
+    float* myscr = scratch + threadIdx.x * kScratchStride;
+    const uint32_t lanemask_lt = (1u << lane) - 1u;
     uint32_t g = 0, qseq = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const UnitInfo u = decode_unit(p, unit);
-        consumer_sync();  // everyone is done with the previous unit's column thresholds
-        for (int x = threadIdx.x; x < u.ntt * kTile; x += kConsumerThreads) tauc[x] = kFltMaxBits;
-        consumer_sync();
         u64* rk1 = p.keys + (size_t)u.pair * 4 * p.stride;
         u64* rk2 = rk1 + p.stride;
         u64* ck1 = rk2 + p.stride;
         u64* ck2 = ck1 + p.stride;
+        uint32_t* tauc = p.col_thr + (size_t)u.pair * p.stride;   // column thresholds of this pair (global, shared by all CTAs)
 
         for (int qb = u.qb0; qb < u.qb1; ++qb) {
             const int ntq = min(kQTiles, u.nqt - qb * kQTiles);
             const bool active = qt < ntq;
+            const bool cold_col = qb == u.qb0;   // first query block of the unit: this CTA has no column bound yet
             mbar_wait(fullQ, qseq & 1);
             ++qseq;
             {   // reset the thresholds of the 32 rows this warp owns
                 const int r = (lane < 16) ? (((warp & 3) << 4) + lane) : (64 + ((warp & 3) << 4) + (lane - 16));
-                taur[qt * kTile + r] = kFltMaxBits;
+                taur[qt * kTile + r] = kThrInit;
             }
             __syncwarp();
             const float* Qt = Qs + qt * kTileFloats;
@@ -150,11 +172,17 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
 
             for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                 const uint32_t st = g % STAGES, ph = (g / STAGES) & 1;
+                // column thresholds of this tile: issued now, consumed after the k-loop (L2 latency hidden)
+                uint4 tcq[4];
+                if (active) {
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) tcq[m] = ldcg_u4(tauc + tt * kTile + m * 32 + tx * 4);
+                }
                 mbar_wait(&fullT[st], ph);
                 if (active) {
                     const float* Tt = Ts + (size_t)st * kTileFloats;
                     float2 acc[8][8];
-                    {   // acc = hq_i + ht_j   (one packed FMA per pair: hq * 1 + ht)
+                    {   // acc = hq_i + ht_j   (one packed op per pair)
                         float ht[16];
 #pragma unroll
                         for (int m = 0; m < 4; ++m) {
@@ -187,85 +215,153 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                         }
                     }
 
-                    // ---------------- epilogue: threshold compares (fast path) ----------------
-                    uint32_t rowmask = 0, colmask = 0;
-                    {   // row minima (3-input FMNMX trees) against the 8 row thresholds
+                    // ---------------- epilogue, fast path: minima (3-input FMNMX trees) vs thresholds ----------------
+                    float tr[8], tc[16], rm[8], cm[16];
+                    {
                         const uint4 t0 = lds128_volatile_u32(taur + qt * kTile + ty * 4);
                         const uint4 t1 = lds128_volatile_u32(taur + qt * kTile + 64 + ty * 4);
-                        const float tr[8] = {__uint_as_float(t0.x), __uint_as_float(t0.y), __uint_as_float(t0.z), __uint_as_float(t0.w),
-                                             __uint_as_float(t1.x), __uint_as_float(t1.y), __uint_as_float(t1.z), __uint_as_float(t1.w)};
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float m = fminf(acc[i][0].x, acc[i][0].y);
-#pragma unroll
-                            for (int jp = 1; jp < 8; ++jp) m = fminf(fminf(m, acc[i][jp].x), acc[i][jp].y);
-                            if (m <= tr[i]) rowmask |= 1u << i;
-                        }
-                    }
-                    {   // column minima against the 16 column thresholds
-                        float tc[16];
+                        tr[0] = __uint_as_float(t0.x); tr[1] = __uint_as_float(t0.y); tr[2] = __uint_as_float(t0.z); tr[3] = __uint_as_float(t0.w);
+                        tr[4] = __uint_as_float(t1.x); tr[5] = __uint_as_float(t1.y); tr[6] = __uint_as_float(t1.z); tr[7] = __uint_as_float(t1.w);
 #pragma unroll
                         for (int m = 0; m < 4; ++m) {
-                            const uint4 t = lds128_volatile_u32(tauc + tt * kTile + m * 32 + tx * 4);
-                            tc[m * 4 + 0] = __uint_as_float(t.x); tc[m * 4 + 1] = __uint_as_float(t.y);
-                            tc[m * 4 + 2] = __uint_as_float(t.z); tc[m * 4 + 3] = __uint_as_float(t.w);
-                        }
-#pragma unroll
-                        for (int jp = 0; jp < 8; ++jp) {
-                            float mx = fminf(acc[0][jp].x, acc[1][jp].x), my = fminf(acc[0][jp].y, acc[1][jp].y);
-#pragma unroll
-                            for (int i = 2; i < 8; i += 2) {
-                                mx = fminf(fminf(mx, acc[i][jp].x), acc[i + 1][jp].x);
-                                my = fminf(fminf(my, acc[i][jp].y), acc[i + 1][jp].y);
-                            }
-                            if (mx <= tc[2 * jp]) colmask |= 1u << (2 * jp);
-                            if (my <= tc[2 * jp + 1]) colmask |= 2u << (2 * jp);
+                            tc[m * 4 + 0] = __uint_as_float(tcq[m].x); tc[m * 4 + 1] = __uint_as_float(tcq[m].y);
+                            tc[m * 4 + 2] = __uint_as_float(tcq[m].z); tc[m * 4 + 3] = __uint_as_float(tcq[m].w);
                         }
                     }
-
-                    // ---------------- slow path: rare candidate inserts ----------------
-                    if (rowmask | colmask) {
-                        float vals[128];  // dynamic indexing below => local memory (L1); only touched on a hit
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
+                    for (int i = 0; i < 8; ++i) {
+                        float m = fminf(acc[i][0].x, acc[i][0].y);
 #pragma unroll
-                            for (int jp = 0; jp < 8; ++jp) {
-                                vals[i * 16 + 2 * jp] = acc[i][jp].x;
-                                vals[i * 16 + 2 * jp + 1] = acc[i][jp].y;
-                            }
-                        const int col0 = tt * kTile + tx * 4;
-                        const int row0 = qrow0 + ty * 4;
-#pragma unroll 1
+                        for (int jp = 1; jp < 8; ++jp) m = fminf(fminf(m, acc[i][jp].x), acc[i][jp].y);
+                        rm[i] = m;
+                    }
+#pragma unroll
+                    for (int jp = 0; jp < 8; ++jp) {
+                        float mx = fminf(acc[0][jp].x, acc[1][jp].x), my = fminf(acc[0][jp].y, acc[1][jp].y);
+#pragma unroll
+                        for (int i = 2; i < 8; i += 2) {
+                            mx = fminf(fminf(mx, acc[i][jp].x), acc[i + 1][jp].x);
+                            my = fminf(fminf(my, acc[i][jp].y), acc[i + 1][jp].y);
+                        }
+                        cm[2 * jp] = mx;
+                        cm[2 * jp + 1] = my;
+                    }
+                    const int col0 = tt * kTile + tx * 4;
+                    const int row0 = qrow0 + ty * 4;
+                    // Cold tiles have no bound yet.  Seed one from the tile itself so that only O(2) elements per
+                    // row / column go down the slow path: the second smallest of the lane minima is >= the true
+                    // second smallest, hence a valid (conservative) threshold.
+                    if (tt == 0) {
+#pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            if (!((rowmask >> i) & 1)) continue;
-                            const int rl = (i >> 2) * 64 + (i & 3);           // tile-local row minus ty*4
-                            uint32_t* thp = taur + qt * kTile + ty * 4 + rl;
-                            const int grow = row0 + rl;
-                            float th = __uint_as_float(*reinterpret_cast<volatile uint32_t*>(thp));
-#pragma unroll 1
-                            for (int j = 0; j < 16; ++j) {
-                                const float v = vals[i * 16 + j];
-                                if (v <= th) {
-                                    insert_candidate(rk1 + grow, rk2 + grow, thp, v, (uint32_t)(col0 + (j >> 2) * 32 + (j & 3)));
-                                    th = __uint_as_float(*reinterpret_cast<volatile uint32_t*>(thp));
-                                }
-                            }
+                            float lo = rm[i], hi = __uint_as_float(kThrInit);
+                            merge_lo_hi(lo, hi, 1); merge_lo_hi(lo, hi, 2); merge_lo_hi(lo, hi, 4);
+                            tr[i] = fminf(tr[i], hi);
+                            if (tx == 0) taur[qt * kTile + ty * 4 + (i >> 2) * 64 + (i & 3)] = __float_as_uint(tr[i]);
                         }
-#pragma unroll 1
+                    }
+                    if (cold_col) {
+#pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            if (!((colmask >> j) & 1)) continue;
-                            const int gcol = col0 + (j >> 2) * 32 + (j & 3);
-                            uint32_t* thp = tauc + gcol;
-                            float th = __uint_as_float(*reinterpret_cast<volatile uint32_t*>(thp));
+                            float lo = cm[j], hi = __uint_as_float(kThrInit);
+                            merge_lo_hi(lo, hi, 8); merge_lo_hi(lo, hi, 16);
+                            tc[j] = fminf(tc[j], hi);
+                            if ((lane >> 3) == 0 && hi < __uint_as_float(kThrInit))
+                                atomicMin(tauc + col0 + (j >> 2) * 32 + (j & 3), __float_as_uint(fmaxf(hi, 0.f)));
+                        }
+                    }
+                    uint32_t mymask = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) mymask |= (rm[i] <= tr[i]) ? (1u << i) : 0u;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) mymask |= (cm[j] <= tc[j]) ? (256u << j) : 0u;
+                    const uint32_t wmask = __reduce_or_sync(0xffffffffu, mymask);
+
+                    // ---------------- slow path: ~2 ln F hits per row / column over a whole sweep ----------------
+                    if (wmask) {
+                        int count = 0;   // warp-uniform number of queued candidates
+                        auto drain = [&]() {
+                            __syncwarp();
+                            for (int e = lane; e < count; e += 32) {
+                                const uint2 ent = queue[e];
+                                const bool is_col = (ent.y >> 30) != 0;
+                                const uint32_t row = (ent.y >> 15) & 0x7fffu, col = ent.y & 0x7fffu;
+                                u64* k1 = is_col ? ck1 + col : rk1 + row;
+                                u64* k2 = is_col ? ck2 + col : rk2 + row;
+                                const u64 key = make_key(ent.x, is_col ? row : col);
+                                const u64 old1 = atomicMin(k1, key);
+                                if (old1 != key) {   // idempotent: re-offering the current best changes nothing
+                                    const u64 loser = old1 > key ? old1 : key;
+                                    u64 cur2 = *reinterpret_cast<volatile u64*>(k2);
+                                    if (loser < cur2) {
+                                        const u64 old2 = atomicMin(k2, loser);
+                                        cur2 = old2 < loser ? old2 : loser;
+                                    }
+                                    const uint32_t nb = (uint32_t)(cur2 >> 32);   // value of the new second best
+                                    if (is_col) atomicMin(tauc + col, nb);
+                                    else atomicMin(taur + (row - (uint32_t)(qb * (kQTiles * kTile))), nb);
+                                }
+                            }
+                            __syncwarp();
+                            count = 0;
+                        };
 #pragma unroll 1
-                            for (int i = 0; i < 8; ++i) {
-                                const float v = vals[i * 16 + j];
-                                if (v <= th) {
-                                    insert_candidate(ck1 + gcol, ck2 + gcol, thp, v, (uint32_t)(row0 + (i >> 2) * 64 + (i & 3)));
-                                    th = __uint_as_float(*reinterpret_cast<volatile uint32_t*>(thp));
+                        for (int b = 0; b < 24; ++b) {
+                            if (!((wmask >> b) & 1)) continue;
+                            const bool flagged = (mymask >> b) & 1;
+                            float thr = 0.f;
+                            // stage this lane's 16 (row body) or 8 (column body) values in its private scratch line
+                            switch (b) {
+#define ROW_CASE(i)                                                                                                     \
+    case i:                                                                                                             \
+        thr = tr[i];                                                                                                    \
+        if (flagged) {                                                                                                  \
+            _Pragma("unroll") for (int m = 0; m < 4; ++m)                                                               \
+                *reinterpret_cast<float4*>(myscr + 4 * m) = make_float4(acc[i][2 * m].x, acc[i][2 * m].y, acc[i][2 * m + 1].x, acc[i][2 * m + 1].y); \
+        }                                                                                                               \
+        break;
+                                ROW_CASE(0) ROW_CASE(1) ROW_CASE(2) ROW_CASE(3) ROW_CASE(4) ROW_CASE(5) ROW_CASE(6) ROW_CASE(7)
+#undef ROW_CASE
+#define COL_CASE(j)                                                                                                     \
+    case 8 + j:                                                                                                         \
+        thr = tc[j];                                                                                                    \
+        if (flagged) {                                                                                                  \
+            *reinterpret_cast<float4*>(myscr) = (j & 1) ? make_float4(acc[0][j >> 1].y, acc[1][j >> 1].y, acc[2][j >> 1].y, acc[3][j >> 1].y)      \
+                                                          : make_float4(acc[0][j >> 1].x, acc[1][j >> 1].x, acc[2][j >> 1].x, acc[3][j >> 1].x);     \
+            *reinterpret_cast<float4*>(myscr + 4) = (j & 1) ? make_float4(acc[4][j >> 1].y, acc[5][j >> 1].y, acc[6][j >> 1].y, acc[7][j >> 1].y)  \
+                                                              : make_float4(acc[4][j >> 1].x, acc[5][j >> 1].x, acc[6][j >> 1].x, acc[7][j >> 1].x); \
+        }                                                                                                               \
+        break;
+                                COL_CASE(0) COL_CASE(1) COL_CASE(2) COL_CASE(3) COL_CASE(4) COL_CASE(5) COL_CASE(6) COL_CASE(7)
+                                COL_CASE(8) COL_CASE(9) COL_CASE(10) COL_CASE(11) COL_CASE(12) COL_CASE(13) COL_CASE(14) COL_CASE(15)
+#undef COL_CASE
+                                default: break;
+                            }
+                            const bool is_col = b >= 8;
+                            const int n = is_col ? 8 : 16;
+                            // fixed coordinate of the body, and stride pattern of the scanned one
+                            const int jj = b - 8;
+                            const uint32_t fixed = is_col ? (uint32_t)(col0 + (jj >> 2) * 32 + (jj & 3))
+                                                          : (uint32_t)(row0 + (b >> 2) * 64 + (b & 3));
+#pragma unroll 1
+                            for (int k = 0; k < n; ++k) {
+                                const float v = myscr[k];   // lane-private line: no cross-lane hazard
+                                const bool hit = flagged && (v <= thr);
+                                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                                if (bal) {
+                                    if (count + 32 > kQueueCap) drain();
+                                    if (hit) {
+                                        const uint32_t other = is_col ? (uint32_t)(row0 + (k >> 2) * 64 + (k & 3))
+                                                                      : (uint32_t)(col0 + (k >> 2) * 32 + (k & 3));
+                                        const uint32_t row = is_col ? other : fixed, col = is_col ? fixed : other;
+                                        queue[count + __popc(bal & lanemask_lt)] =
+                                            make_uint2(__float_as_uint(fmaxf(v, 0.f)), ((is_col ? 1u : 0u) << 30) | (row << 15) | col);
+                                    }
+                                    count += __popc(bal);
                                 }
                             }
                         }
+                        drain();
                     }
                 }
                 __syncwarp();
@@ -277,38 +373,23 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
     }
 }
 
-size_t sweep_l2_smem_bytes(int col_cap, int stages) {
-    return (size_t)(kQTiles + stages) * kTileBytes + kQTiles * kTile * 4 + (2 + 2 * stages) * 8 + (size_t)col_cap * 4;
+size_t sweep_l2_smem_bytes(int stages) {
+    return (size_t)(kQTiles + stages) * kTileBytes + kQTiles * kTile * 4 + (2 + 2 * stages) * 8 +
+           (size_t)(kConsumerThreads / 32) * kQueueCap * sizeof(uint2) + (size_t)kConsumerThreads * kScratchStride * 4;
 }
 
-int sweep_l2_max_rows() {
-    // column thresholds must fit next to the 2-stage ring inside 227 KB of shared memory
-    const size_t fixed = sweep_l2_smem_bytes(0, 2);
-    const size_t cap = (232448 - fixed) / 4;
-    return (int)(cap / kTile) * kTile;
-}
+int sweep_l2_max_rows() { return 32767 / kTile * kTile; }  // queue entries pack row and column in 15 bits each
 
 cudaError_t launch_sweep_l2(const SweepParams& p, int sm_count, cudaStream_t s) {
     const int n_units = p.n_pairs * p.units_per_pair;
     if (n_units <= 0) return cudaSuccess;
     const int grid = n_units < sm_count ? n_units : sm_count;
-    int stages = 3;
-    size_t smem = sweep_l2_smem_bytes(p.col_cap, 3);
-    if (smem > 232448) {
-        stages = 2;
-        smem = sweep_l2_smem_bytes(p.col_cap, 2);
-    }
-    if (smem > 232448) return cudaErrorInvalidValue;
-    cudaError_t e;
-    if (stages == 3) {
-        e = cudaFuncSetAttribute(sweep_l2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        sweep_l2_kernel<3><<<grid, kSweepThreads, smem, s>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(sweep_l2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        sweep_l2_kernel<2><<<grid, kSweepThreads, smem, s>>>(p);
-    }
+    constexpr int kStages = 3;
+    const size_t smem = sweep_l2_smem_bytes(kStages);
+    static_assert(true, "");
+    cudaError_t e = cudaFuncSetAttribute(sweep_l2_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    sweep_l2_kernel<kStages><<<grid, kSweepThreads, smem, s>>>(p);
     return cudaGetLastError();
 }
 
