@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kHamThreads, 1) sweep_hamming_kernel(const Swe
                     for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                         const uint32_t st = g % kHamStages, ph = (g / kHamStages) & 1;
                         const int n = min(kHamTile, u.ft - tt * kHamTile);
-                        mbar_wait(&emptyT[st], ph ^ 1);
+                        mbar_wait_backoff(&emptyT[st], ph ^ 1);
                         mbar_arrive_expect_tx(&fullT[st], (uint32_t)n * 32u);
                         bulk_g2s(Ts + (size_t)st * kHamTile * 2, tbase + (size_t)tt * kHamTile * 2, (uint32_t)n * 32u, &fullT[st]);
                     }

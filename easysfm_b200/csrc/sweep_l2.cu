@@ -115,13 +115,13 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                 const float* tbase = p.kmajor + (size_t)p.frame_tile_off[u.t_frame] * kTileFloats;
                 for (int qb = u.qb0; qb < u.qb1; ++qb) {
                     const int ntq = min(kQTiles, u.nqt - qb * kQTiles);
-                    mbar_wait(emptyQ, (qseq & 1) ^ 1);
+                    mbar_wait_backoff(emptyQ, (qseq & 1) ^ 1);
                     mbar_arrive_expect_tx(fullQ, (uint32_t)ntq * kTileBytes);
                     bulk_g2s(Qs, qbase + (size_t)qb * kQTiles * kTileFloats, (uint32_t)ntq * kTileBytes, fullQ);
                     ++qseq;
                     for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                         const uint32_t st = g % STAGES, ph = (g / STAGES) & 1;
-                        mbar_wait(&emptyT[st], ph ^ 1);
+                        mbar_wait_backoff(&emptyT[st], ph ^ 1);
                         mbar_arrive_expect_tx(&fullT[st], kTileBytes);
                         bulk_g2s(Ts + (size_t)st * kTileFloats, tbase + (size_t)tt * kTileFloats, kTileBytes, &fullT[st]);
                     }
@@ -305,31 +305,47 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                             __syncwarp();
                             count = 0;
                         };
+                        // Visit only the bodies (8 rows, 16 columns of the register tile) some lane flagged.  The switch
+                        // holds the static-register part: a 16- or 8-bit hit mask of this lane's elements <= threshold,
+                        // and (only when a lane has more than one hit, which is rare) a copy of the values in the
+                        // lane's private scratch line.  Everything after the switch is shared, generic code.
+                        uint32_t todo = wmask;
 #pragma unroll 1
-                        for (int b = 0; b < 24; ++b) {
-                            if (!((wmask >> b) & 1)) continue;
+                        while (todo) {
+                            const int b = __ffs(todo) - 1;
+                            todo &= todo - 1;
                             const bool flagged = (mymask >> b) & 1;
-                            float thr = 0.f;
-                            // stage this lane's 16 (row body) or 8 (column body) values in its private scratch line
+                            uint32_t hm = 0;      // hit mask of this lane inside the body
+                            float vmin = 0.f;     // the lane minimum: the value of the hit when there is exactly one
                             switch (b) {
 #define ROW_CASE(i)                                                                                                     \
     case i:                                                                                                             \
-        thr = tr[i];                                                                                                    \
         if (flagged) {                                                                                                  \
-            _Pragma("unroll") for (int m = 0; m < 4; ++m)                                                               \
-                *reinterpret_cast<float4*>(myscr + 4 * m) = make_float4(acc[i][2 * m].x, acc[i][2 * m].y, acc[i][2 * m + 1].x, acc[i][2 * m + 1].y); \
+            vmin = rm[i];                                                                                               \
+            _Pragma("unroll") for (int jp = 0; jp < 8; ++jp) {                                                          \
+                hm |= (acc[i][jp].x <= tr[i]) ? (1u << (2 * jp)) : 0u;                                                  \
+                hm |= (acc[i][jp].y <= tr[i]) ? (2u << (2 * jp)) : 0u;                                                  \
+            }                                                                                                           \
+            if (hm & (hm - 1)) {                                                                                        \
+                _Pragma("unroll") for (int m = 0; m < 4; ++m)                                                           \
+                    *reinterpret_cast<float4*>(myscr + 4 * m) = make_float4(acc[i][2 * m].x, acc[i][2 * m].y, acc[i][2 * m + 1].x, acc[i][2 * m + 1].y); \
+            }                                                                                                           \
         }                                                                                                               \
         break;
                                 ROW_CASE(0) ROW_CASE(1) ROW_CASE(2) ROW_CASE(3) ROW_CASE(4) ROW_CASE(5) ROW_CASE(6) ROW_CASE(7)
 #undef ROW_CASE
 #define COL_CASE(j)                                                                                                     \
     case 8 + j:                                                                                                         \
-        thr = tc[j];                                                                                                    \
         if (flagged) {                                                                                                  \
-            *reinterpret_cast<float4*>(myscr) = (j & 1) ? make_float4(acc[0][j >> 1].y, acc[1][j >> 1].y, acc[2][j >> 1].y, acc[3][j >> 1].y)      \
-                                                          : make_float4(acc[0][j >> 1].x, acc[1][j >> 1].x, acc[2][j >> 1].x, acc[3][j >> 1].x);     \
-            *reinterpret_cast<float4*>(myscr + 4) = (j & 1) ? make_float4(acc[4][j >> 1].y, acc[5][j >> 1].y, acc[6][j >> 1].y, acc[7][j >> 1].y)  \
-                                                              : make_float4(acc[4][j >> 1].x, acc[5][j >> 1].x, acc[6][j >> 1].x, acc[7][j >> 1].x); \
+            vmin = cm[j];                                                                                               \
+            _Pragma("unroll") for (int i = 0; i < 8; ++i)                                                               \
+                hm |= (((j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x) <= tc[j]) ? (1u << i) : 0u;                      \
+            if (hm & (hm - 1)) {                                                                                        \
+                *reinterpret_cast<float4*>(myscr) = (j & 1) ? make_float4(acc[0][j >> 1].y, acc[1][j >> 1].y, acc[2][j >> 1].y, acc[3][j >> 1].y)      \
+                                                              : make_float4(acc[0][j >> 1].x, acc[1][j >> 1].x, acc[2][j >> 1].x, acc[3][j >> 1].x);     \
+                *reinterpret_cast<float4*>(myscr + 4) = (j & 1) ? make_float4(acc[4][j >> 1].y, acc[5][j >> 1].y, acc[6][j >> 1].y, acc[7][j >> 1].y)  \
+                                                                  : make_float4(acc[4][j >> 1].x, acc[5][j >> 1].x, acc[6][j >> 1].x, acc[7][j >> 1].x); \
+            }                                                                                                           \
         }                                                                                                               \
         break;
                                 COL_CASE(0) COL_CASE(1) COL_CASE(2) COL_CASE(3) COL_CASE(4) COL_CASE(5) COL_CASE(6) COL_CASE(7)
@@ -338,27 +354,27 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                                 default: break;
                             }
                             const bool is_col = b >= 8;
-                            const int n = is_col ? 8 : 16;
-                            // fixed coordinate of the body, and stride pattern of the scanned one
                             const int jj = b - 8;
                             const uint32_t fixed = is_col ? (uint32_t)(col0 + (jj >> 2) * 32 + (jj & 3))
                                                           : (uint32_t)(row0 + (b >> 2) * 64 + (b & 3));
+                            const bool single = (hm & (hm - 1)) == 0;
 #pragma unroll 1
-                            for (int k = 0; k < n; ++k) {
-                                const float v = myscr[k];   // lane-private line: no cross-lane hazard
-                                const bool hit = flagged && (v <= thr);
+                            while (true) {
+                                const bool hit = hm != 0;
                                 const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-                                if (bal) {
-                                    if (count + 32 > kQueueCap) drain();
-                                    if (hit) {
-                                        const uint32_t other = is_col ? (uint32_t)(row0 + (k >> 2) * 64 + (k & 3))
-                                                                      : (uint32_t)(col0 + (k >> 2) * 32 + (k & 3));
-                                        const uint32_t row = is_col ? other : fixed, col = is_col ? fixed : other;
-                                        queue[count + __popc(bal & lanemask_lt)] =
-                                            make_uint2(__float_as_uint(fmaxf(v, 0.f)), ((is_col ? 1u : 0u) << 30) | (row << 15) | col);
-                                    }
-                                    count += __popc(bal);
+                                if (!bal) break;
+                                if (count + 32 > kQueueCap) drain();
+                                if (hit) {
+                                    const int k = __ffs(hm) - 1;
+                                    hm &= hm - 1;
+                                    const float v = single ? vmin : myscr[k];
+                                    const uint32_t other = is_col ? (uint32_t)(row0 + (k >> 2) * 64 + (k & 3))
+                                                                  : (uint32_t)(col0 + (k >> 2) * 32 + (k & 3));
+                                    const uint32_t row = is_col ? other : fixed, col = is_col ? fixed : other;
+                                    queue[count + __popc(bal & lanemask_lt)] =
+                                        make_uint2(__float_as_uint(fmaxf(v, 0.f)), ((is_col ? 1u : 0u) << 30) | (row << 15) | col);
                                 }
+                                count += __popc(bal);
                             }
                         }
                         drain();
