@@ -122,7 +122,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Producer-side wait: the ring has slack, so sleep between polls instead of burning issue slots of the
 // SM sub-partition the producer warp shares with two consumer warps.
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(200);
+    uint32_t ok = 0;
+    while (true) {
+        // try_wait with a suspend-time hint: the hardware may park the thread until the phase completes
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+            : "memory");
+        if (ok) break;
+        __nanosleep(2000);
+    }
 }
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {

@@ -73,18 +73,15 @@ __device__ __forceinline__ RowResult eval_row(const FinalizeParams& p, const u64
     if (p.cross_check) {
         // nearest query row of train row i1 (lowest index on ties) must be q
         const u64 c1 = ck1[i1];
-        int best = (int)(uint32_t)c1;
-        if (KIND == ESFM_KIND_F32X64) {
-            const u64 c2 = ck2[i1];
-            if (c2 != kKeyInit) {
-                int a = best, b = (int)(uint32_t)c2;
-                float da = l2_direct(qrows + (size_t)a * kDim, trows + (size_t)i1 * kDim);
-                float db = l2_direct(qrows + (size_t)b * kDim, trows + (size_t)i1 * kDim);
-                order2(da, a, db, b);
-                best = a;
-            }
+        if (c1 == kKeyInit) return r;
+        const int best = (int)(uint32_t)c1;
+        if (best != q) {
+            if (KIND != ESFM_KIND_F32X64) return r;
+            // The sweep ranked the column in expansion form; q may still be the true nearest row if the two are
+            // within its rounding noise.  Decide in direct form, (distance, index) order.
+            const float db = l2_direct(qrows + (size_t)best * kDim, trows + (size_t)i1 * kDim);
+            if (!(d1 < db || (d1 == db && q < best))) return r;
         }
-        if (c1 == kKeyInit || best != q) return r;
     }
     r.keep = true;
     r.t1 = i1;

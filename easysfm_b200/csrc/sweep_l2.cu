@@ -63,10 +63,10 @@ __device__ __forceinline__ UnitInfo decode_unit(const SweepParams& p, int unit) 
 
 }  // namespace
 
-// Packed queue entry: v = candidate value (1/2 d^2), w = type << 30 | row << 15 | col  (rows per frame < 2^15)
-constexpr int kQueueCap = 256;          // per consumer warp
-constexpr int kScratchStride = 20;      // floats per lane (16 used; 80-byte stride keeps STS.128/LDS conflict-free)
+constexpr int kScratchStride = 20;          // floats per lane (16 used; 80-byte stride keeps STS.128 conflict-free)
 constexpr uint32_t kThrInit = 0x7f7f7f7fu;  // 3.39e38f: what a byte-wise memset(0x7f) of the threshold arrays produces
+constexpr int kStageFloats = kTileFloats + kTile;   // tile + the 128 column thresholds that travel with it
+constexpr int kStageBytes = kStageFloats * 4;
 
 // Two smallest of a value replicated over a lane group by xor-shuffles: (lo, hi) <- merge with partner's (lo, hi).
 __device__ __forceinline__ void merge_lo_hi(float& lo, float& hi, int xor_mask) {
@@ -76,19 +76,50 @@ __device__ __forceinline__ void merge_lo_hi(float& lo, float& hi, int xor_mask) 
     lo = fminf(lo, plo);
 }
 
+// Lane-private sorted pair of row candidates, ordered by (value, index).  Within a lane the columns of a row
+// arrive in ascending index order, so a strict '<' on the value keeps the lowest index among equal values.
+struct RowTop2 {
+    float v1, v2;
+    uint32_t i1, i2;
+};
+__device__ __forceinline__ void row_insert(RowTop2& r, float v, uint32_t idx) {
+    if (v < r.v2) {
+        if (v < r.v1) {
+            r.v2 = r.v1; r.i2 = r.i1;
+            r.v1 = v;    r.i1 = idx;
+        } else {
+            r.v2 = v;    r.i2 = idx;
+        }
+    }
+}
+// Merge with the partner lane's pair (lexicographic on (value, index): lanes hold disjoint column sets).
+__device__ __forceinline__ bool key_less(float va, uint32_t ia, float vb, uint32_t ib) { return va < vb || (va == vb && ia < ib); }
+__device__ __forceinline__ void row_merge_xor(RowTop2& r, int xor_mask) {
+    const float pv1 = __shfl_xor_sync(0xffffffffu, r.v1, xor_mask), pv2 = __shfl_xor_sync(0xffffffffu, r.v2, xor_mask);
+    const uint32_t pi1 = __shfl_xor_sync(0xffffffffu, r.i1, xor_mask), pi2 = __shfl_xor_sync(0xffffffffu, r.i2, xor_mask);
+    RowTop2 o;
+    if (key_less(pv1, pi1, r.v1, r.i1)) {       // partner's best wins
+        o.v1 = pv1; o.i1 = pi1;
+        if (key_less(pv2, pi2, r.v1, r.i1)) { o.v2 = pv2; o.i2 = pi2; } else { o.v2 = r.v1; o.i2 = r.i1; }
+    } else {
+        o.v1 = r.v1; o.i1 = r.i1;
+        if (key_less(pv1, pi1, r.v2, r.i2)) { o.v2 = pv1; o.i2 = pi1; } else { o.v2 = r.v2; o.i2 = r.i2; }
+    }
+    r = o;
+}
+
 template <int STAGES>
 __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* Qs = reinterpret_cast<float*>(smem_raw);                       // kQTiles tiles
-    float* Ts = Qs + kQTiles * kTileFloats;                               // STAGES tiles
-    uint32_t* taur = reinterpret_cast<uint32_t*>(Ts + STAGES * kTileFloats);  // 256 row thresholds (float bits)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(taur + kQTiles * kTile);
+    float* Ts = Qs + kQTiles * kTileFloats;                               // STAGES x (tile + 128 column thresholds)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Ts + STAGES * kStageFloats);
     uint64_t* fullQ = bars;
     uint64_t* emptyQ = bars + 1;
     uint64_t* fullT = bars + 2;
     uint64_t* emptyT = bars + 2 + STAGES;
-    uint2* queues = reinterpret_cast<uint2*>(bars + 2 + 2 * STAGES);      // 8 warps x kQueueCap entries
-    float* scratch = reinterpret_cast<float*>(queues + (kConsumerThreads / 32) * kQueueCap);  // 256 lanes x kScratchStride
+    float* scratch = reinterpret_cast<float*>(bars + 2 + 2 * STAGES);     // 256 lanes x kScratchStride
+    float4* rowstate = reinterpret_cast<float4*>(scratch + kConsumerThreads * kScratchStride);  // [8 rows][256 lanes] (v1, v2, i1, i2)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_units = p.n_pairs * p.units_per_pair;
@@ -113,6 +144,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                 const UnitInfo u = decode_unit(p, unit);
                 const float* qbase = p.kmajor + (size_t)p.frame_tile_off[u.q_frame] * kTileFloats;
                 const float* tbase = p.kmajor + (size_t)p.frame_tile_off[u.t_frame] * kTileFloats;
+                const uint32_t* tauc = p.col_thr + (size_t)u.pair * p.stride;
                 for (int qb = u.qb0; qb < u.qb1; ++qb) {
                     const int ntq = min(kQTiles, u.nqt - qb * kQTiles);
                     mbar_wait_backoff(emptyQ, (qseq & 1) ^ 1);
@@ -122,8 +154,12 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                     for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                         const uint32_t st = g % STAGES, ph = (g / STAGES) & 1;
                         mbar_wait_backoff(&emptyT[st], ph ^ 1);
-                        mbar_arrive_expect_tx(&fullT[st], kTileBytes);
-                        bulk_g2s(Ts + (size_t)st * kTileFloats, tbase + (size_t)tt * kTileFloats, kTileBytes, &fullT[st]);
+                        mbar_arrive_expect_tx(&fullT[st], kStageBytes);
+                        float* dst = Ts + (size_t)st * kStageFloats;
+                        bulk_g2s(dst, tbase + (size_t)tt * kTileFloats, kTileBytes, &fullT[st]);
+                        // the running column thresholds of this tile ride along (a snapshot a few tiles old is fine:
+                        // a stale threshold is only looser, never wrong)
+                        bulk_g2s(dst + kTileFloats, tauc + (size_t)tt * kTile, kTile * 4, &fullT[st]);
                     }
                 }
             }
@@ -138,51 +174,45 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
     const int tx = lane & 7;                           // 0..7  : column group
     // rows of this thread inside the tile: r(i) = (i>>2)*64 + ty*4 + (i&3), i < 8
     // cols of this thread inside the tile: c(j) = (j>>2)*32 + tx*4 + (j&3), j < 16
-    uint2* queue = queues + warp * kQueueCap;
     float* myscr = scratch + threadIdx.x * kScratchStride;
-    const uint32_t lanemask_lt = (1u << lane) - 1u;
+    float4* mystate = rowstate + threadIdx.x;   // row i of this lane lives at mystate[i * 256]: conflict-free 16-byte accesses
     uint32_t g = 0, qseq = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const UnitInfo u = decode_unit(p, unit);
         u64* rk1 = p.keys + (size_t)u.pair * 4 * p.stride;
         u64* rk2 = rk1 + p.stride;
         u64* ck1 = rk2 + p.stride;
-        u64* ck2 = ck1 + p.stride;
         uint32_t* tauc = p.col_thr + (size_t)u.pair * p.stride;   // column thresholds of this pair (global, shared by all CTAs)
 
         for (int qb = u.qb0; qb < u.qb1; ++qb) {
             const int ntq = min(kQTiles, u.nqt - qb * kQTiles);
             const bool active = qt < ntq;
-            const bool cold_col = qb == u.qb0;   // first query block of the unit: this CTA has no column bound yet
             mbar_wait(fullQ, qseq & 1);
             ++qseq;
-            {   // reset the thresholds of the 32 rows this warp owns
-                const int r = (lane < 16) ? (((warp & 3) << 4) + lane) : (64 + ((warp & 3) << 4) + (lane - 16));
-                taur[qt * kTile + r] = kThrInit;
-            }
-            __syncwarp();
             const float* Qt = Qs + qt * kTileFloats;
-            float hq[8];
-            if (active) {
-                const float4 h0 = lds128(Qt + kDim * kTile + ty * 4), h1 = lds128(Qt + kDim * kTile + 64 + ty * 4);
-                hq[0] = h0.x; hq[1] = h0.y; hq[2] = h0.z; hq[3] = h0.w;
-                hq[4] = h1.x; hq[5] = h1.y; hq[6] = h1.z; hq[7] = h1.w;
+            float tr[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                tr[i] = __uint_as_float(kThrInit);     // shared (8 lanes of the row) running bound on the row's 2nd best
+                mystate[i * kConsumerThreads] = make_float4(__int_as_float(0x7f800000), __int_as_float(0x7f800000),
+                                                            __int_as_float(-1), __int_as_float(-1));
             }
             const int qrow0 = qb * (kQTiles * kTile) + qt * kTile;  // frame row of this warp's tile row 0
+            const int row0 = qrow0 + ty * 4;
 
             for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                 const uint32_t st = g % STAGES, ph = (g / STAGES) & 1;
-                // column thresholds of this tile: issued now, consumed after the k-loop (L2 latency hidden)
-                uint4 tcq[4];
-                if (active) {
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) tcq[m] = ldcg_u4(tauc + tt * kTile + m * 32 + tx * 4);
-                }
                 mbar_wait(&fullT[st], ph);
                 if (active) {
-                    const float* Tt = Ts + (size_t)st * kTileFloats;
+                    const float* Tt = Ts + (size_t)st * kStageFloats;
                     float2 acc[8][8];
                     {   // acc = hq_i + ht_j   (one packed op per pair)
+                        float hq[8];
+                        {
+                            const float4 h0 = lds128(Qt + kDim * kTile + ty * 4), h1 = lds128(Qt + kDim * kTile + 64 + ty * 4);
+                            hq[0] = h0.x; hq[1] = h0.y; hq[2] = h0.z; hq[3] = h0.w;
+                            hq[4] = h1.x; hq[5] = h1.y; hq[6] = h1.z; hq[7] = h1.w;
+                        }
                         float ht[16];
 #pragma unroll
                         for (int m = 0; m < 4; ++m) {
@@ -216,17 +246,11 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                     }
 
                     // ---------------- epilogue, fast path: minima (3-input FMNMX trees) vs thresholds ----------------
-                    float tr[8], tc[16], rm[8], cm[16];
-                    {
-                        const uint4 t0 = lds128_volatile_u32(taur + qt * kTile + ty * 4);
-                        const uint4 t1 = lds128_volatile_u32(taur + qt * kTile + 64 + ty * 4);
-                        tr[0] = __uint_as_float(t0.x); tr[1] = __uint_as_float(t0.y); tr[2] = __uint_as_float(t0.z); tr[3] = __uint_as_float(t0.w);
-                        tr[4] = __uint_as_float(t1.x); tr[5] = __uint_as_float(t1.y); tr[6] = __uint_as_float(t1.z); tr[7] = __uint_as_float(t1.w);
+                    float tc[16], rm[8], cm[16];
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            tc[m * 4 + 0] = __uint_as_float(tcq[m].x); tc[m * 4 + 1] = __uint_as_float(tcq[m].y);
-                            tc[m * 4 + 2] = __uint_as_float(tcq[m].z); tc[m * 4 + 3] = __uint_as_float(tcq[m].w);
-                        }
+                    for (int m = 0; m < 4; ++m) {
+                        const float4 t = lds128(Tt + kTileFloats + m * 32 + tx * 4);
+                        tc[m * 4 + 0] = t.x; tc[m * 4 + 1] = t.y; tc[m * 4 + 2] = t.z; tc[m * 4 + 3] = t.w;
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -247,27 +271,15 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                         cm[2 * jp + 1] = my;
                     }
                     const int col0 = tt * kTile + tx * 4;
-                    const int row0 = qrow0 + ty * 4;
-                    // Cold tiles have no bound yet.  Seed one from the tile itself so that only O(2) elements per
-                    // row / column go down the slow path: the second smallest of the lane minima is >= the true
-                    // second smallest, hence a valid (conservative) threshold.
+                    // The first tile of a query block has no row bound yet.  Seed one from the tile itself so that only
+                    // O(2) elements per row go down the slow path: the second smallest of the 8 lane minima is >= the
+                    // row's true second smallest, hence a valid (conservative) bound.
                     if (tt == 0) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             float lo = rm[i], hi = __uint_as_float(kThrInit);
                             merge_lo_hi(lo, hi, 1); merge_lo_hi(lo, hi, 2); merge_lo_hi(lo, hi, 4);
-                            tr[i] = fminf(tr[i], hi);
-                            if (tx == 0) taur[qt * kTile + ty * 4 + (i >> 2) * 64 + (i & 3)] = __float_as_uint(tr[i]);
-                        }
-                    }
-                    if (cold_col) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float lo = cm[j], hi = __uint_as_float(kThrInit);
-                            merge_lo_hi(lo, hi, 8); merge_lo_hi(lo, hi, 16);
-                            tc[j] = fminf(tc[j], hi);
-                            if ((lane >> 3) == 0 && hi < __uint_as_float(kThrInit))
-                                atomicMin(tauc + col0 + (j >> 2) * 32 + (j & 3), __float_as_uint(fmaxf(hi, 0.f)));
+                            tr[i] = hi;
                         }
                     }
                     uint32_t mymask = 0;
@@ -275,52 +287,26 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                     for (int i = 0; i < 8; ++i) mymask |= (rm[i] <= tr[i]) ? (1u << i) : 0u;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) mymask |= (cm[j] <= tc[j]) ? (256u << j) : 0u;
-                    const uint32_t wmask = __reduce_or_sync(0xffffffffu, mymask);
+                    uint32_t todo = __reduce_or_sync(0xffffffffu, mymask);
 
-                    // ---------------- slow path: ~2 ln F hits per row / column over a whole sweep ----------------
-                    if (wmask) {
-                        int count = 0;   // warp-uniform number of queued candidates
-                        auto drain = [&]() {
-                            __syncwarp();
-                            for (int e = lane; e < count; e += 32) {
-                                const uint2 ent = queue[e];
-                                const bool is_col = (ent.y >> 30) != 0;
-                                const uint32_t row = (ent.y >> 15) & 0x7fffu, col = ent.y & 0x7fffu;
-                                u64* k1 = is_col ? ck1 + col : rk1 + row;
-                                u64* k2 = is_col ? ck2 + col : rk2 + row;
-                                const u64 key = make_key(ent.x, is_col ? row : col);
-                                const u64 old1 = atomicMin(k1, key);
-                                if (old1 != key) {   // idempotent: re-offering the current best changes nothing
-                                    const u64 loser = old1 > key ? old1 : key;
-                                    u64 cur2 = *reinterpret_cast<volatile u64*>(k2);
-                                    if (loser < cur2) {
-                                        const u64 old2 = atomicMin(k2, loser);
-                                        cur2 = old2 < loser ? old2 : loser;
-                                    }
-                                    const uint32_t nb = (uint32_t)(cur2 >> 32);   // value of the new second best
-                                    if (is_col) atomicMin(tauc + col, nb);
-                                    else atomicMin(taur + (row - (uint32_t)(qb * (kQTiles * kTile))), nb);
-                                }
-                            }
-                            __syncwarp();
-                            count = 0;
-                        };
-                        // Visit only the bodies (8 rows, 16 columns of the register tile) some lane flagged.  The switch
-                        // holds the static-register part: a 16- or 8-bit hit mask of this lane's elements <= threshold,
-                        // and (only when a lane has more than one hit, which is rare) a copy of the values in the
-                        // lane's private scratch line.  Everything after the switch is shared, generic code.
-                        uint32_t todo = wmask;
+                    // ---------------- slow path: ~2 ln F hits per row, ~ln F per column over a whole sweep ----------------
+                    // Visit only the bodies (8 rows, 16 columns of the register tile) some lane flagged.  The switch holds
+                    // the static-register part: a hit mask of this lane's elements <= bound and, only when a lane has
+                    // more than one hit (rare), a copy of the values in the lane's private scratch line.
 #pragma unroll 1
-                        while (todo) {
-                            const int b = __ffs(todo) - 1;
-                            todo &= todo - 1;
-                            const bool flagged = (mymask >> b) & 1;
-                            uint32_t hm = 0;      // hit mask of this lane inside the body
-                            float vmin = 0.f;     // the lane minimum: the value of the hit when there is exactly one
-                            switch (b) {
+                    while (todo) {
+                        const int b = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const bool flagged = (mymask >> b) & 1;
+                        uint32_t hm = 0;      // hit mask of this lane inside the body
+                        float vmin = 0.f;     // the lane minimum: the value of the hit when there is exactly one
+                        switch (b) {
 #define ROW_CASE(i)                                                                                                     \
-    case i:                                                                                                             \
+    case i: {                                                                                                           \
+        float4 st4 = mystate[i * kConsumerThreads];                                                                     \
         if (flagged) {                                                                                                  \
+            RowTop2 t;                                                                                                  \
+            t.v1 = st4.x; t.v2 = st4.y; t.i1 = __float_as_uint(st4.z); t.i2 = __float_as_uint(st4.w);                   \
             vmin = rm[i];                                                                                               \
             _Pragma("unroll") for (int jp = 0; jp < 8; ++jp) {                                                          \
                 hm |= (acc[i][jp].x <= tr[i]) ? (1u << (2 * jp)) : 0u;                                                  \
@@ -330,9 +316,22 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                 _Pragma("unroll") for (int m = 0; m < 4; ++m)                                                           \
                     *reinterpret_cast<float4*>(myscr + 4 * m) = make_float4(acc[i][2 * m].x, acc[i][2 * m].y, acc[i][2 * m + 1].x, acc[i][2 * m + 1].y); \
             }                                                                                                           \
+            const bool single = (hm & (hm - 1)) == 0;                                                                   \
+            while (hm) {                                                                                                \
+                const int k = __ffs(hm) - 1;                                                                            \
+                hm &= hm - 1;                                                                                           \
+                row_insert(t, single ? vmin : myscr[k], (uint32_t)(col0 + (k >> 2) * 32 + (k & 3)));                   \
+            }                                                                                                           \
+            st4 = make_float4(t.v1, t.v2, __uint_as_float(t.i1), __uint_as_float(t.i2));                                \
+            mystate[i * kConsumerThreads] = st4;                                                                        \
         }                                                                                                               \
-        break;
-                                ROW_CASE(0) ROW_CASE(1) ROW_CASE(2) ROW_CASE(3) ROW_CASE(4) ROW_CASE(5) ROW_CASE(6) ROW_CASE(7)
+        {   /* new shared bound of the row: the exact second best over its 8 lanes' candidate pairs */                  \
+            float lo = st4.x, hi = st4.y;                                                                               \
+            merge_lo_hi(lo, hi, 1); merge_lo_hi(lo, hi, 2); merge_lo_hi(lo, hi, 4);                                     \
+            tr[i] = fminf(tr[i], hi);                                                                                   \
+        }                                                                                                               \
+    } break;
+                            ROW_CASE(0) ROW_CASE(1) ROW_CASE(2) ROW_CASE(3) ROW_CASE(4) ROW_CASE(5) ROW_CASE(6) ROW_CASE(7)
 #undef ROW_CASE
 #define COL_CASE(j)                                                                                                     \
     case 8 + j:                                                                                                         \
@@ -348,40 +347,46 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
             }                                                                                                           \
         }                                                                                                               \
         break;
-                                COL_CASE(0) COL_CASE(1) COL_CASE(2) COL_CASE(3) COL_CASE(4) COL_CASE(5) COL_CASE(6) COL_CASE(7)
-                                COL_CASE(8) COL_CASE(9) COL_CASE(10) COL_CASE(11) COL_CASE(12) COL_CASE(13) COL_CASE(14) COL_CASE(15)
+                            COL_CASE(0) COL_CASE(1) COL_CASE(2) COL_CASE(3) COL_CASE(4) COL_CASE(5) COL_CASE(6) COL_CASE(7)
+                            COL_CASE(8) COL_CASE(9) COL_CASE(10) COL_CASE(11) COL_CASE(12) COL_CASE(13) COL_CASE(14) COL_CASE(15)
 #undef COL_CASE
-                                default: break;
-                            }
-                            const bool is_col = b >= 8;
-                            const int jj = b - 8;
-                            const uint32_t fixed = is_col ? (uint32_t)(col0 + (jj >> 2) * 32 + (jj & 3))
-                                                          : (uint32_t)(row0 + (b >> 2) * 64 + (b & 3));
-                            const bool single = (hm & (hm - 1)) == 0;
-#pragma unroll 1
-                            while (true) {
-                                const bool hit = hm != 0;
-                                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-                                if (!bal) break;
-                                if (count + 32 > kQueueCap) drain();
-                                if (hit) {
-                                    const int k = __ffs(hm) - 1;
-                                    hm &= hm - 1;
-                                    const float v = single ? vmin : myscr[k];
-                                    const uint32_t other = is_col ? (uint32_t)(row0 + (k >> 2) * 64 + (k & 3))
-                                                                  : (uint32_t)(col0 + (k >> 2) * 32 + (k & 3));
-                                    const uint32_t row = is_col ? other : fixed, col = is_col ? fixed : other;
-                                    queue[count + __popc(bal & lanemask_lt)] =
-                                        make_uint2(__float_as_uint(fmaxf(v, 0.f)), ((is_col ? 1u : 0u) << 30) | (row << 15) | col);
-                                }
-                                count += __popc(bal);
-                            }
+                            default: break;
                         }
-                        drain();
+                        if (b >= 8 && hm) {
+                            // column candidates: fire-and-forget 64-bit min on the packed key (value bits << 32 | query row) and a
+                            // 32-bit min on the running threshold -- no return value, so nothing waits on L2
+                            const int jj = b - 8;
+                            const uint32_t gcol = (uint32_t)(col0 + (jj >> 2) * 32 + (jj & 3));
+                            const bool single = (hm & (hm - 1)) == 0;
+                            float best = __uint_as_float(kThrInit);
+                            while (hm) {
+                                const int k = __ffs(hm) - 1;
+                                hm &= hm - 1;
+                                const float v = fmaxf(single ? vmin : myscr[k], 0.f);
+                                atomicMin(ck1 + gcol, make_key(__float_as_uint(v), (uint32_t)(row0 + (k >> 2) * 64 + (k & 3))));
+                                best = fminf(best, v);
+                            }
+                            atomicMin(tauc + gcol, __float_as_uint(best));
+                        }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&emptyT[st]);
+            }
+            // ---- end of the sweep for this query block: merge the 8 lanes of every row and publish its two candidates ----
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 st4 = mystate[i * kConsumerThreads];
+                    RowTop2 t;
+                    t.v1 = st4.x; t.v2 = st4.y; t.i1 = __float_as_uint(st4.z); t.i2 = __float_as_uint(st4.w);
+                    row_merge_xor(t, 1); row_merge_xor(t, 2); row_merge_xor(t, 4);
+                    if (tx == 0) {
+                        const int grow = row0 + (i >> 2) * 64 + (i & 3);
+                        rk1[grow] = t.i1 == 0xffffffffu ? kKeyInit : make_key(__float_as_uint(fmaxf(t.v1, 0.f)), t.i1);
+                        rk2[grow] = t.i2 == 0xffffffffu ? kKeyInit : make_key(__float_as_uint(fmaxf(t.v2, 0.f)), t.i2);
+                    }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(emptyQ);
@@ -390,11 +395,11 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
 }
 
 size_t sweep_l2_smem_bytes(int stages) {
-    return (size_t)(kQTiles + stages) * kTileBytes + kQTiles * kTile * 4 + (2 + 2 * stages) * 8 +
-           (size_t)(kConsumerThreads / 32) * kQueueCap * sizeof(uint2) + (size_t)kConsumerThreads * kScratchStride * 4;
+    return (size_t)kQTiles * kTileBytes + (size_t)stages * kStageBytes + (2 + 2 * stages) * 8 +
+           (size_t)kConsumerThreads * kScratchStride * 4 + (size_t)8 * kConsumerThreads * sizeof(float4);
 }
 
-int sweep_l2_max_rows() { return 32767 / kTile * kTile; }  // queue entries pack row and column in 15 bits each
+int sweep_l2_max_rows() { return (1 << 20) / kTile * kTile; }
 
 cudaError_t launch_sweep_l2(const SweepParams& p, int sm_count, cudaStream_t s) {
     const int n_units = p.n_pairs * p.units_per_pair;
@@ -402,7 +407,6 @@ cudaError_t launch_sweep_l2(const SweepParams& p, int sm_count, cudaStream_t s) 
     const int grid = n_units < sm_count ? n_units : sm_count;
     constexpr int kStages = 3;
     const size_t smem = sweep_l2_smem_bytes(kStages);
-    static_assert(true, "");
     cudaError_t e = cudaFuncSetAttribute(sweep_l2_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     sweep_l2_kernel<kStages><<<grid, kSweepThreads, smem, s>>>(p);
