@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                     }
                     const float* qp = Qt + ty * 4;
                     const float* tp = Tt + tx * 4;
-#pragma unroll 4
+#pragma unroll 16
                     for (int k = 0; k < kDim; ++k) {
                         const float4 a0 = lds128(qp + k * kTile), a1 = lds128(qp + k * kTile + 64);
                         const float4 b0 = lds128(tp + k * kTile), b1 = lds128(tp + k * kTile + 32);
@@ -287,87 +287,90 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                     for (int i = 0; i < 8; ++i) mymask |= (rm[i] <= tr[i]) ? (1u << i) : 0u;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) mymask |= (cm[j] <= tc[j]) ? (256u << j) : 0u;
-                    uint32_t todo = __reduce_or_sync(0xffffffffu, mymask);
+                    const uint32_t wmask = __reduce_or_sync(0xffffffffu, mymask);
 
                     // ---------------- slow path: ~2 ln F hits per row, ~ln F per column over a whole sweep ----------------
-                    // Visit only the bodies (8 rows, 16 columns of the register tile) some lane flagged.  The switch holds
-                    // the static-register part: a hit mask of this lane's elements <= bound and, only when a lane has
-                    // more than one hit (rare), a copy of the values in the lane's private scratch line.
-#pragma unroll 1
-                    while (todo) {
-                        const int b = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const bool flagged = (mymask >> b) & 1;
-                        uint32_t hm = 0;      // hit mask of this lane inside the body
-                        float vmin = 0.f;     // the lane minimum: the value of the hit when there is exactly one
-                        switch (b) {
-#define ROW_CASE(i)                                                                                                     \
-    case i: {                                                                                                           \
-        float4 st4 = mystate[i * kConsumerThreads];                                                                     \
-        if (flagged) {                                                                                                  \
+                    // Straight-line code, one warp-uniform branch per body (8 rows, 16 columns of the register tile): a body
+                    // runs only if some lane flagged it.  Per flagged lane: a hit mask of its elements <= bound; the value of
+                    // a single hit is the lane minimum already in a register, several hits (rare) go through the lane's
+                    // private scratch line.
+                    if (wmask) {
+#define ROW_BODY(i)                                                                                                     \
+    if (wmask & (1u << i)) {                                                                                            \
+        if (mymask & (1u << i)) {                                                                                       \
+            const float4 st4 = mystate[i * kConsumerThreads];                                                           \
             RowTop2 t;                                                                                                  \
             t.v1 = st4.x; t.v2 = st4.y; t.i1 = __float_as_uint(st4.z); t.i2 = __float_as_uint(st4.w);                   \
-            vmin = rm[i];                                                                                               \
+            uint32_t hm = 0;                                                                                            \
             _Pragma("unroll") for (int jp = 0; jp < 8; ++jp) {                                                          \
                 hm |= (acc[i][jp].x <= tr[i]) ? (1u << (2 * jp)) : 0u;                                                  \
                 hm |= (acc[i][jp].y <= tr[i]) ? (2u << (2 * jp)) : 0u;                                                  \
             }                                                                                                           \
-            if (hm & (hm - 1)) {                                                                                        \
+            if ((hm & (hm - 1)) == 0) {                                                                                 \
+                const int k = __ffs(hm) - 1;                                                                            \
+                row_insert(t, rm[i], (uint32_t)(col0 + (k >> 2) * 32 + (k & 3)));                                       \
+            } else {                                                                                                    \
                 _Pragma("unroll") for (int m = 0; m < 4; ++m)                                                           \
                     *reinterpret_cast<float4*>(myscr + 4 * m) = make_float4(acc[i][2 * m].x, acc[i][2 * m].y, acc[i][2 * m + 1].x, acc[i][2 * m + 1].y); \
+                while (hm) {                                                                                            \
+                    const int k = __ffs(hm) - 1;                                                                        \
+                    hm &= hm - 1;                                                                                       \
+                    row_insert(t, myscr[k], (uint32_t)(col0 + (k >> 2) * 32 + (k & 3)));                                \
+                }                                                                                                       \
             }                                                                                                           \
-            const bool single = (hm & (hm - 1)) == 0;                                                                   \
-            while (hm) {                                                                                                \
-                const int k = __ffs(hm) - 1;                                                                            \
-                hm &= hm - 1;                                                                                           \
-                row_insert(t, single ? vmin : myscr[k], (uint32_t)(col0 + (k >> 2) * 32 + (k & 3)));                   \
-            }                                                                                                           \
-            st4 = make_float4(t.v1, t.v2, __uint_as_float(t.i1), __uint_as_float(t.i2));                                \
-            mystate[i * kConsumerThreads] = st4;                                                                        \
+            mystate[i * kConsumerThreads] = make_float4(t.v1, t.v2, __uint_as_float(t.i1), __uint_as_float(t.i2));      \
         }                                                                                                               \
-        {   /* new shared bound of the row: the exact second best over its 8 lanes' candidate pairs */                  \
-            float lo = st4.x, hi = st4.y;                                                                               \
-            merge_lo_hi(lo, hi, 1); merge_lo_hi(lo, hi, 2); merge_lo_hi(lo, hi, 4);                                     \
-            tr[i] = fminf(tr[i], hi);                                                                                   \
-        }                                                                                                               \
-    } break;
-                            ROW_CASE(0) ROW_CASE(1) ROW_CASE(2) ROW_CASE(3) ROW_CASE(4) ROW_CASE(5) ROW_CASE(6) ROW_CASE(7)
-#undef ROW_CASE
-#define COL_CASE(j)                                                                                                     \
-    case 8 + j:                                                                                                         \
-        if (flagged) {                                                                                                  \
-            vmin = cm[j];                                                                                               \
+    }
+                        ROW_BODY(0) ROW_BODY(1) ROW_BODY(2) ROW_BODY(3) ROW_BODY(4) ROW_BODY(5) ROW_BODY(6) ROW_BODY(7)
+#undef ROW_BODY
+                        if (wmask & 0xffu) {
+                            // refresh the shared bound of every row: exact second best over its 8 lanes' candidate pairs
+                            // (8 independent shuffle chains, so their latencies overlap)
+                            __syncwarp();
+                            float lo[8], hi[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float2 s2 = *reinterpret_cast<const float2*>(&mystate[i * kConsumerThreads]);
+                                lo[i] = s2.x; hi[i] = s2.y;
+                            }
+#pragma unroll
+                            for (int x = 1; x <= 4; x <<= 1)
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) merge_lo_hi(lo[i], hi[i], x);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) tr[i] = fminf(tr[i], hi[i]);
+                        }
+#define COL_BODY(j)                                                                                                     \
+    if (wmask & (256u << j)) {                                                                                          \
+        if (mymask & (256u << j)) {                                                                                     \
+            uint32_t hm = 0;                                                                                            \
             _Pragma("unroll") for (int i = 0; i < 8; ++i)                                                               \
                 hm |= (((j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x) <= tc[j]) ? (1u << i) : 0u;                      \
-            if (hm & (hm - 1)) {                                                                                        \
+            const uint32_t gcol = (uint32_t)(col0 + (j >> 2) * 32 + (j & 3));                                           \
+            /* fire-and-forget 64-bit min on the packed key (value bits << 32 | query row) and 32-bit min on the        \
+               running threshold: no return value, so nothing waits on L2 */                                            \
+            if ((hm & (hm - 1)) == 0) {                                                                                 \
+                const int k = __ffs(hm) - 1;                                                                            \
+                const float v = fmaxf(cm[j], 0.f);                                                                      \
+                atomicMin(ck1 + gcol, make_key(__float_as_uint(v), (uint32_t)(row0 + (k >> 2) * 64 + (k & 3))));        \
+                atomicMin(tauc + gcol, __float_as_uint(v));                                                             \
+            } else {                                                                                                    \
                 *reinterpret_cast<float4*>(myscr) = (j & 1) ? make_float4(acc[0][j >> 1].y, acc[1][j >> 1].y, acc[2][j >> 1].y, acc[3][j >> 1].y)      \
                                                               : make_float4(acc[0][j >> 1].x, acc[1][j >> 1].x, acc[2][j >> 1].x, acc[3][j >> 1].x);     \
                 *reinterpret_cast<float4*>(myscr + 4) = (j & 1) ? make_float4(acc[4][j >> 1].y, acc[5][j >> 1].y, acc[6][j >> 1].y, acc[7][j >> 1].y)  \
                                                                   : make_float4(acc[4][j >> 1].x, acc[5][j >> 1].x, acc[6][j >> 1].x, acc[7][j >> 1].x); \
+                while (hm) {                                                                                            \
+                    const int k = __ffs(hm) - 1;                                                                        \
+                    hm &= hm - 1;                                                                                       \
+                    atomicMin(ck1 + gcol, make_key(__float_as_uint(fmaxf(myscr[k], 0.f)), (uint32_t)(row0 + (k >> 2) * 64 + (k & 3)))); \
+                }                                                                                                       \
+                atomicMin(tauc + gcol, __float_as_uint(fmaxf(cm[j], 0.f)));                                             \
             }                                                                                                           \
         }                                                                                                               \
-        break;
-                            COL_CASE(0) COL_CASE(1) COL_CASE(2) COL_CASE(3) COL_CASE(4) COL_CASE(5) COL_CASE(6) COL_CASE(7)
-                            COL_CASE(8) COL_CASE(9) COL_CASE(10) COL_CASE(11) COL_CASE(12) COL_CASE(13) COL_CASE(14) COL_CASE(15)
-#undef COL_CASE
-                            default: break;
-                        }
-                        if (b >= 8 && hm) {
-                            // column candidates: fire-and-forget 64-bit min on the packed key (value bits << 32 | query row) and a
-                            // 32-bit min on the running threshold -- no return value, so nothing waits on L2
-                            const int jj = b - 8;
-                            const uint32_t gcol = (uint32_t)(col0 + (jj >> 2) * 32 + (jj & 3));
-                            const bool single = (hm & (hm - 1)) == 0;
-                            float best = __uint_as_float(kThrInit);
-                            while (hm) {
-                                const int k = __ffs(hm) - 1;
-                                hm &= hm - 1;
-                                const float v = fmaxf(single ? vmin : myscr[k], 0.f);
-                                atomicMin(ck1 + gcol, make_key(__float_as_uint(v), (uint32_t)(row0 + (k >> 2) * 64 + (k & 3))));
-                                best = fminf(best, v);
-                            }
-                            atomicMin(tauc + gcol, __float_as_uint(best));
-                        }
+    }
+                        COL_BODY(0) COL_BODY(1) COL_BODY(2) COL_BODY(3) COL_BODY(4) COL_BODY(5) COL_BODY(6) COL_BODY(7)
+                        COL_BODY(8) COL_BODY(9) COL_BODY(10) COL_BODY(11) COL_BODY(12) COL_BODY(13) COL_BODY(14) COL_BODY(15)
+#undef COL_BODY
                     }
                 }
                 __syncwarp();
