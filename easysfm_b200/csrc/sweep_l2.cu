@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                     }
                     const float* qp = Qt + ty * 4;
                     const float* tp = Tt + tx * 4;
-#pragma unroll 16
+#pragma unroll 8
                     for (int k = 0; k < kDim; ++k) {
                         const float4 a0 = lds128(qp + k * kTile), a1 = lds128(qp + k * kTile + 64);
                         const float4 b0 = lds128(tp + k * kTile), b1 = lds128(tp + k * kTile + 32);
@@ -290,39 +290,91 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                     const uint32_t wmask = __reduce_or_sync(0xffffffffu, mymask);
 
                     // ---------------- slow path: ~2 ln F hits per row, ~ln F per column over a whole sweep ----------------
-                    // Straight-line code, one warp-uniform branch per body (8 rows, 16 columns of the register tile): a body
-                    // runs only if some lane flagged it.  Per flagged lane: a hit mask of its elements <= bound; the value of
-                    // a single hit is the lane minimum already in a register, several hits (rare) go through the lane's
-                    // private scratch line.
+                    // Visit only the bodies (8 rows, 16 columns of the register tile) some lane flagged.  The switch is the
+                    // only per-body static code: it copies the flagged lane's 16 (row) or 8 (column) accumulators to its
+                    // private shared-memory line; everything else is ONE generic routine working on that line, so the whole
+                    // slow path is a few hundred instructions and stays resident in the instruction cache.
                     if (wmask) {
-#define ROW_BODY(i)                                                                                                     \
-    if (wmask & (1u << i)) {                                                                                            \
-        if (mymask & (1u << i)) {                                                                                       \
-            const float4 st4 = mystate[i * kConsumerThreads];                                                           \
-            RowTop2 t;                                                                                                  \
-            t.v1 = st4.x; t.v2 = st4.y; t.i1 = __float_as_uint(st4.z); t.i2 = __float_as_uint(st4.w);                   \
-            uint32_t hm = 0;                                                                                            \
-            _Pragma("unroll") for (int jp = 0; jp < 8; ++jp) {                                                          \
-                hm |= (acc[i][jp].x <= tr[i]) ? (1u << (2 * jp)) : 0u;                                                  \
-                hm |= (acc[i][jp].y <= tr[i]) ? (2u << (2 * jp)) : 0u;                                                  \
-            }                                                                                                           \
-            if ((hm & (hm - 1)) == 0) {                                                                                 \
-                const int k = __ffs(hm) - 1;                                                                            \
-                row_insert(t, rm[i], (uint32_t)(col0 + (k >> 2) * 32 + (k & 3)));                                       \
-            } else {                                                                                                    \
-                _Pragma("unroll") for (int m = 0; m < 4; ++m)                                                           \
-                    *reinterpret_cast<float4*>(myscr + 4 * m) = make_float4(acc[i][2 * m].x, acc[i][2 * m].y, acc[i][2 * m + 1].x, acc[i][2 * m + 1].y); \
-                while (hm) {                                                                                            \
-                    const int k = __ffs(hm) - 1;                                                                        \
-                    hm &= hm - 1;                                                                                       \
-                    row_insert(t, myscr[k], (uint32_t)(col0 + (k >> 2) * 32 + (k & 3)));                                \
-                }                                                                                                       \
-            }                                                                                                           \
-            mystate[i * kConsumerThreads] = make_float4(t.v1, t.v2, __uint_as_float(t.i1), __uint_as_float(t.i2));      \
+                        uint32_t todo = wmask;
+#pragma unroll 1
+                        while (todo) {
+                            const int b = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const bool flagged = (mymask >> b) & 1;
+                            float thr = 0.f, vmin = 0.f;
+                            switch (b) {
+#define ROW_CASE(i)                                                                                                     \
+    case i:                                                                                                             \
+        thr = tr[i]; vmin = rm[i];                                                                                      \
+        if (flagged) {                                                                                                  \
+            _Pragma("unroll") for (int m = 0; m < 4; ++m)                                                               \
+                *reinterpret_cast<float4*>(myscr + 4 * m) = make_float4(acc[i][2 * m].x, acc[i][2 * m].y, acc[i][2 * m + 1].x, acc[i][2 * m + 1].y); \
         }                                                                                                               \
-    }
-                        ROW_BODY(0) ROW_BODY(1) ROW_BODY(2) ROW_BODY(3) ROW_BODY(4) ROW_BODY(5) ROW_BODY(6) ROW_BODY(7)
-#undef ROW_BODY
+        break;
+                                ROW_CASE(0) ROW_CASE(1) ROW_CASE(2) ROW_CASE(3) ROW_CASE(4) ROW_CASE(5) ROW_CASE(6) ROW_CASE(7)
+#undef ROW_CASE
+#define COL_CASE(j)                                                                                                     \
+    case 8 + j:                                                                                                         \
+        thr = tc[j]; vmin = cm[j];                                                                                      \
+        if (flagged) {                                                                                                  \
+            *reinterpret_cast<float4*>(myscr) = (j & 1) ? make_float4(acc[0][j >> 1].y, acc[1][j >> 1].y, acc[2][j >> 1].y, acc[3][j >> 1].y)      \
+                                                          : make_float4(acc[0][j >> 1].x, acc[1][j >> 1].x, acc[2][j >> 1].x, acc[3][j >> 1].x);     \
+            *reinterpret_cast<float4*>(myscr + 4) = (j & 1) ? make_float4(acc[4][j >> 1].y, acc[5][j >> 1].y, acc[6][j >> 1].y, acc[7][j >> 1].y)  \
+                                                              : make_float4(acc[4][j >> 1].x, acc[5][j >> 1].x, acc[6][j >> 1].x, acc[7][j >> 1].x); \
+        }                                                                                                               \
+        break;
+                                COL_CASE(0) COL_CASE(1) COL_CASE(2) COL_CASE(3) COL_CASE(4) COL_CASE(5) COL_CASE(6) COL_CASE(7)
+                                COL_CASE(8) COL_CASE(9) COL_CASE(10) COL_CASE(11) COL_CASE(12) COL_CASE(13) COL_CASE(14) COL_CASE(15)
+#undef COL_CASE
+                                default: break;
+                            }
+                            if (!flagged) continue;
+                            if (b < 8) {
+                                // ---- generic row routine: lane-private top-2 of row b over this lane's columns ----
+                                const float4 v0 = *reinterpret_cast<const float4*>(myscr), v1 = *reinterpret_cast<const float4*>(myscr + 4);
+                                const float4 v2 = *reinterpret_cast<const float4*>(myscr + 8), v3 = *reinterpret_cast<const float4*>(myscr + 12);
+                                const float v[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+                                uint32_t hm = 0;
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) hm |= (v[k] <= thr) ? (1u << k) : 0u;
+                                float4* sp = mystate + b * kConsumerThreads;
+                                const float4 st4 = *sp;
+                                RowTop2 t;
+                                t.v1 = st4.x; t.v2 = st4.y; t.i1 = __float_as_uint(st4.z); t.i2 = __float_as_uint(st4.w);
+                                if (__builtin_expect((hm & (hm - 1)) == 0, 1)) {
+                                    const int k = __ffs(hm) - 1;
+                                    row_insert(t, vmin, (uint32_t)(col0 + (k >> 2) * 32 + (k & 3)));
+                                } else {
+                                    while (hm) {
+                                        const int k = __ffs(hm) - 1;
+                                        hm &= hm - 1;
+                                        row_insert(t, myscr[k], (uint32_t)(col0 + (k >> 2) * 32 + (k & 3)));
+                                    }
+                                }
+                                *sp = make_float4(t.v1, t.v2, __uint_as_float(t.i1), __uint_as_float(t.i2));
+                            } else {
+                                // ---- generic column routine: fire-and-forget 64-bit min on the packed key (value bits << 32 |
+                                // query row) and 32-bit min on the running threshold: no return value, nothing waits on L2 ----
+                                const float4 v0 = *reinterpret_cast<const float4*>(myscr), v1 = *reinterpret_cast<const float4*>(myscr + 4);
+                                const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                                uint32_t hm = 0;
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) hm |= (v[k] <= thr) ? (1u << k) : 0u;
+                                const int jj = b - 8;
+                                const uint32_t gcol = (uint32_t)(col0 + (jj >> 2) * 32 + (jj & 3));
+                                if (__builtin_expect((hm & (hm - 1)) == 0, 1)) {
+                                    const int k = __ffs(hm) - 1;
+                                    atomicMin(ck1 + gcol, make_key(__float_as_uint(fmaxf(vmin, 0.f)), (uint32_t)(row0 + (k >> 2) * 64 + (k & 3))));
+                                } else {
+                                    while (hm) {
+                                        const int k = __ffs(hm) - 1;
+                                        hm &= hm - 1;
+                                        atomicMin(ck1 + gcol, make_key(__float_as_uint(fmaxf(myscr[k], 0.f)), (uint32_t)(row0 + (k >> 2) * 64 + (k & 3))));
+                                    }
+                                }
+                                atomicMin(tauc + gcol, __float_as_uint(fmaxf(vmin, 0.f)));
+                            }
+                        }
                         if (wmask & 0xffu) {
                             // refresh the shared bound of every row: exact second best over its 8 lanes' candidate pairs
                             // (8 independent shuffle chains, so their latencies overlap)
@@ -340,37 +392,6 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
 #pragma unroll
                             for (int i = 0; i < 8; ++i) tr[i] = fminf(tr[i], hi[i]);
                         }
-#define COL_BODY(j)                                                                                                     \
-    if (wmask & (256u << j)) {                                                                                          \
-        if (mymask & (256u << j)) {                                                                                     \
-            uint32_t hm = 0;                                                                                            \
-            _Pragma("unroll") for (int i = 0; i < 8; ++i)                                                               \
-                hm |= (((j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x) <= tc[j]) ? (1u << i) : 0u;                      \
-            const uint32_t gcol = (uint32_t)(col0 + (j >> 2) * 32 + (j & 3));                                           \
-            /* fire-and-forget 64-bit min on the packed key (value bits << 32 | query row) and 32-bit min on the        \
-               running threshold: no return value, so nothing waits on L2 */                                            \
-            if ((hm & (hm - 1)) == 0) {                                                                                 \
-                const int k = __ffs(hm) - 1;                                                                            \
-                const float v = fmaxf(cm[j], 0.f);                                                                      \
-                atomicMin(ck1 + gcol, make_key(__float_as_uint(v), (uint32_t)(row0 + (k >> 2) * 64 + (k & 3))));        \
-                atomicMin(tauc + gcol, __float_as_uint(v));                                                             \
-            } else {                                                                                                    \
-                *reinterpret_cast<float4*>(myscr) = (j & 1) ? make_float4(acc[0][j >> 1].y, acc[1][j >> 1].y, acc[2][j >> 1].y, acc[3][j >> 1].y)      \
-                                                              : make_float4(acc[0][j >> 1].x, acc[1][j >> 1].x, acc[2][j >> 1].x, acc[3][j >> 1].x);     \
-                *reinterpret_cast<float4*>(myscr + 4) = (j & 1) ? make_float4(acc[4][j >> 1].y, acc[5][j >> 1].y, acc[6][j >> 1].y, acc[7][j >> 1].y)  \
-                                                                  : make_float4(acc[4][j >> 1].x, acc[5][j >> 1].x, acc[6][j >> 1].x, acc[7][j >> 1].x); \
-                while (hm) {                                                                                            \
-                    const int k = __ffs(hm) - 1;                                                                        \
-                    hm &= hm - 1;                                                                                       \
-                    atomicMin(ck1 + gcol, make_key(__float_as_uint(fmaxf(myscr[k], 0.f)), (uint32_t)(row0 + (k >> 2) * 64 + (k & 3)))); \
-                }                                                                                                       \
-                atomicMin(tauc + gcol, __float_as_uint(fmaxf(cm[j], 0.f)));                                             \
-            }                                                                                                           \
-        }                                                                                                               \
-    }
-                        COL_BODY(0) COL_BODY(1) COL_BODY(2) COL_BODY(3) COL_BODY(4) COL_BODY(5) COL_BODY(6) COL_BODY(7)
-                        COL_BODY(8) COL_BODY(9) COL_BODY(10) COL_BODY(11) COL_BODY(12) COL_BODY(13) COL_BODY(14) COL_BODY(15)
-#undef COL_BODY
                     }
                 }
                 __syncwarp();
