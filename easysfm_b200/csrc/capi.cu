@@ -57,17 +57,53 @@ struct esfm_ctx {
     unsigned long long* d_pair_off = nullptr;
     int32_t* d_pair_cnt = nullptr;
     unsigned long long* d_cursor = nullptr;  // [0] cursor, [1] overflow flag (as int)
-    // pinned host staging
+    // pinned host staging (small metadata) + a pool of large pinned buffers that banks (upload staging) and
+    // results (downloaded matches) borrow, so steady-state calls never allocate or zero-fill host memory
     void* h_stage = nullptr;       size_t h_stage_bytes = 0;
+    struct Pinned { void* ptr; size_t bytes; bool in_use; };
+    std::vector<Pinned> pool;
     uint64_t arena_generation = 0;
 };
+
+static void* pool_acquire(esfm_ctx* ctx, size_t bytes, size_t* got) {
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < ctx->pool.size(); ++i)
+        if (!ctx->pool[i].in_use && ctx->pool[i].bytes >= bytes && (best == (size_t)-1 || ctx->pool[i].bytes < ctx->pool[best].bytes)) best = i;
+    if (best != (size_t)-1) {
+        ctx->pool[best].in_use = true;
+        if (got) *got = ctx->pool[best].bytes;
+        return ctx->pool[best].ptr;
+    }
+    // drop idle buffers that were too small, then allocate with 25% headroom
+    for (size_t i = 0; i < ctx->pool.size();) {
+        if (!ctx->pool[i].in_use) { cudaFreeHost(ctx->pool[i].ptr); ctx->pool.erase(ctx->pool.begin() + i); } else ++i;
+    }
+    size_t want = bytes + bytes / 4 + 4096;
+    void* p = nullptr;
+    if (cudaMallocHost(&p, want) != cudaSuccess) {
+        want = bytes;
+        if (cudaMallocHost(&p, want) != cudaSuccess) return nullptr;
+    }
+    ctx->pool.push_back({p, want, true});
+    if (got) *got = want;
+    return p;
+}
+
+static void pool_release(esfm_ctx* ctx, void* ptr) {
+    if (!ptr) return;
+    for (auto& b : ctx->pool)
+        if (b.ptr == ptr) { b.in_use = false; return; }
+}
+
 
 struct esfm_bank {
     esfm_ctx* ctx = nullptr;
     int kind = 0;
     int n_frames = 0;
     std::vector<int> rows;                    // per frame, -1 = not set
-    std::vector<std::vector<uint8_t>> host;   // staged frame data until commit
+    uint8_t* h_up = nullptr;                  // pinned upload staging (borrowed from the ctx pool until commit)
+    size_t h_up_cap = 0, h_up_used = 0;
+    std::vector<size_t> host_off;             // per frame offset into h_up ((size_t)-1 = no host data)
     bool committed = false;
     bool device_allocated = false;
     // device
@@ -86,8 +122,9 @@ struct esfm_results {
     esfm_ctx* ctx = nullptr;
     std::vector<PairDesc> pairs;
     std::vector<int32_t> counts;
-    std::vector<uint64_t> offsets;          // into `matches`
-    std::vector<esfm_dmatch_t> matches;     // host copy (empty until fetched for device-resident results)
+    std::vector<uint64_t> offsets;          // segment index << 40 | offset (in matches) inside that segment
+    struct Segment { esfm_dmatch_t* ptr; size_t count; };
+    std::vector<Segment> segments;          // one pinned buffer per chunk, borrowed from the ctx pool
     std::unordered_map<uint64_t, int64_t> index;
     bool fetched = true;
     // device-resident variant (single chunk only)
@@ -175,6 +212,7 @@ extern "C" int esfm_destroy(esfm_ctx_t* ctx) {
     cudaFree(ctx->keys); cudaFree(ctx->col_thr); cudaFree(ctx->arena); cudaFree(ctx->d_pairs); cudaFree(ctx->d_pair_off);
     cudaFree(ctx->d_pair_cnt); cudaFree(ctx->d_cursor);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (auto& b : ctx->pool) cudaFreeHost(b.ptr);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -220,7 +258,7 @@ extern "C" int esfm_bank_create(esfm_ctx_t* ctx, esfm_kind kind, int n_frames, e
     b->kind = kind;
     b->n_frames = n_frames;
     b->rows.assign(n_frames, -1);
-    b->host.resize(n_frames);
+    b->host_off.assign(n_frames, (size_t)-1);
     *out = b;
     return ESFM_OK;
 }
@@ -243,9 +281,26 @@ extern "C" int esfm_bank_set_frame(esfm_bank_t* b, int frame_id, const void* dat
     if (rows > 0 && !data) return fail(ESFM_ERR_INVALID, "data is NULL with rows > 0");
     if (rows > 0 && step_bytes < rb) return fail(ESFM_ERR_INVALID, "step_bytes %zu smaller than a row (%zu)", step_bytes, rb);
     if (int rc = check_frame_limits(b, rows)) return rc;
-    std::vector<uint8_t>& dst = b->host[frame_id];
-    dst.resize((size_t)rows * rb);
-    for (int r = 0; r < rows; ++r) memcpy(dst.data() + (size_t)r * rb, (const uint8_t*)data + (size_t)r * step_bytes, rb);
+    // append to the pinned upload staging (frames set in order land exactly where the single H2D copy wants them)
+    const size_t need = (size_t)rows * rb;
+    if (b->h_up_used + need > b->h_up_cap) {
+        size_t cap = 0;
+        const size_t want = std::max((b->h_up_used + need) * 2, (size_t)8 << 20);
+        uint8_t* nb = (uint8_t*)pool_acquire(b->ctx, want, &cap);
+        if (!nb) return fail(ESFM_ERR_NOMEM, "pinned staging allocation of %zu bytes failed", want);
+        if (b->h_up_used) memcpy(nb, b->h_up, b->h_up_used);
+        pool_release(b->ctx, b->h_up);
+        b->h_up = nb;
+        b->h_up_cap = cap;
+    }
+    uint8_t* dst = b->h_up + b->h_up_used;
+    if (step_bytes == rb) {
+        if (need) memcpy(dst, data, need);
+    } else {
+        for (int r = 0; r < rows; ++r) memcpy(dst + (size_t)r * rb, (const uint8_t*)data + (size_t)r * step_bytes, rb);
+    }
+    b->host_off[frame_id] = b->h_up_used;
+    b->h_up_used += need;
     b->rows[frame_id] = rows;
     return ESFM_OK;
 }
@@ -257,7 +312,7 @@ extern "C" int esfm_bank_set_frame_rows(esfm_bank_t* b, int frame_id, int rows) 
     if (rows < 0) return fail(ESFM_ERR_INVALID, "rows < 0");
     if (int rc = check_frame_limits(b, rows)) return rc;
     b->rows[frame_id] = rows;
-    b->host[frame_id].clear();
+    b->host_off[frame_id] = (size_t)-1;
     return ESFM_OK;
 }
 
@@ -280,7 +335,8 @@ static int bank_alloc_layout(esfm_bank* b) {
     b->rows_bytes = (total_rows + kHamTile) * b->row_bytes();
     cudaError_t e = cudaMalloc(&b->d_rows, b->rows_bytes);
     if (e != cudaSuccess) return fail(ESFM_ERR_NOMEM, "cudaMalloc(%zu) for the descriptor bank failed: %s", b->rows_bytes, cudaGetErrorString(e));
-    CUDA_TRY(cudaMemsetAsync(b->d_rows, 0, b->rows_bytes, ctx->stream));
+    // only the slack past the last frame needs defined contents
+    CUDA_TRY(cudaMemsetAsync((uint8_t*)b->d_rows + total_rows * b->row_bytes(), 0, (size_t)kHamTile * b->row_bytes(), ctx->stream));
     if (b->kind == ESFM_KIND_F32X64) {
         b->kmajor_bytes = ((size_t)b->tile_off[b->n_frames] + 1) * kTileBytes;
         e = cudaMalloc((void**)&b->d_kmajor, b->kmajor_bytes);
@@ -324,23 +380,32 @@ extern "C" int esfm_bank_commit(esfm_bank_t* b) {
     if (b->committed) return fail(ESFM_ERR_STATE, "bank already committed");
     if (!b->device_allocated) {
         for (int f = 0; f < b->n_frames; ++f)
-            if (b->rows[f] > 0 && b->host[f].empty())
+            if (b->rows[f] > 0 && b->host_off[f] == (size_t)-1)
                 return fail(ESFM_ERR_STATE, "frame %d has rows declared but no host data; use esfm_bank_alloc_device + esfm_bank_commit_device", f);
         if (int rc = bank_alloc_layout(b)) return rc;
     }
     esfm_ctx* ctx = b->ctx;
-    // pack all frames into pinned staging, one H2D copy
     const size_t rb = b->row_bytes();
     const size_t total = (size_t)b->row_off[b->n_frames] * rb;
     if (total > 0) {
-        if (int rc = grow_stage(ctx, total)) return rc;
-        for (int f = 0; f < b->n_frames; ++f)
-            if (b->rows[f] > 0) memcpy((uint8_t*)ctx->h_stage + (size_t)b->row_off[f] * rb, b->host[f].data(), (size_t)b->rows[f] * rb);
-        CUDA_TRY(cudaMemcpyAsync(b->d_rows, ctx->h_stage, total, cudaMemcpyHostToDevice, ctx->stream));
+        bool in_order = b->h_up_used == total;
+        for (int f = 0; f < b->n_frames && in_order; ++f)
+            if (b->rows[f] > 0 && b->host_off[f] != (size_t)b->row_off[f] * rb) in_order = false;
+        if (in_order) {   // one pinned -> device copy
+            CUDA_TRY(cudaMemcpyAsync(b->d_rows, b->h_up, total, cudaMemcpyHostToDevice, ctx->stream));
+        } else {          // frames were set out of order (or re-set): one copy per frame
+            for (int f = 0; f < b->n_frames; ++f)
+                if (b->rows[f] > 0)
+                    CUDA_TRY(cudaMemcpyAsync((uint8_t*)b->d_rows + (size_t)b->row_off[f] * rb, b->h_up + b->host_off[f],
+                                             (size_t)b->rows[f] * rb, cudaMemcpyHostToDevice, ctx->stream));
+        }
         ctx->stats.h2d_bytes += total;
     }
-    for (auto& v : b->host) std::vector<uint8_t>().swap(v);
-    return bank_build_derived(b);
+    const int rc = bank_build_derived(b);   // synchronises the stream: the staging buffer is free again
+    pool_release(ctx, b->h_up);
+    b->h_up = nullptr;
+    b->h_up_cap = b->h_up_used = 0;
+    return rc;
 }
 
 extern "C" int esfm_bank_device_rows(esfm_bank_t* b, void** dev_ptr, size_t* bytes) {
@@ -384,6 +449,7 @@ extern "C" int esfm_bank_destroy(esfm_bank_t* b) {
         cudaStreamSynchronize(b->ctx->stream);
     }
     cudaFree(b->d_rows); cudaFree(b->d_kmajor); cudaFree(b->d_frame_rows); cudaFree(b->d_row_off); cudaFree(b->d_tile_off);
+    if (b->ctx) pool_release(b->ctx, b->h_up);
     delete b;
     return ESFM_OK;
 }
@@ -532,16 +598,16 @@ int match_pairs_impl(esfm_bank* b, const esfm_pair_t* pairs, int64_t n_pairs, do
     if (n_pairs == 0) { *out = res; return ESFM_OK; }
 
     const ChunkPlan pl = plan_chunks(b, n_pairs);
-    if (int rc = ensure_scratch(ctx, b, pl)) { delete res; return rc; }
+    if (int rc = ensure_scratch(ctx, b, pl)) { esfm_results_destroy(res); return rc; }
     const size_t n_chunks = ((size_t)n_pairs + pl.chunk_pairs - 1) / pl.chunk_pairs;
     for (size_t c0 = 0; c0 < (size_t)n_pairs; c0 += pl.chunk_pairs) {
         const size_t n = std::min(pl.chunk_pairs, (size_t)n_pairs - c0);
         CUDA_TRY(cudaMemcpyAsync(ctx->d_pairs, res->pairs.data() + c0, n * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
         ctx->stats.h2d_bytes += n * sizeof(PairDesc);
-        if (int rc = run_chunk(ctx, b, pl, n, ratio, cross_check, nullptr, nullptr)) { delete res; return rc; }
+        if (int rc = run_chunk(ctx, b, pl, n, ratio, cross_check, nullptr, nullptr)) { esfm_results_destroy(res); return rc; }
         // counts + offsets + cursor back
         const size_t meta = n * (sizeof(int32_t) + sizeof(unsigned long long)) + 2 * sizeof(unsigned long long);
-        if (int rc = grow_stage(ctx, meta)) { delete res; return rc; }
+        if (int rc = grow_stage(ctx, meta)) { esfm_results_destroy(res); return rc; }
         unsigned long long* h_cur = (unsigned long long*)ctx->h_stage;
         unsigned long long* h_off = h_cur + 2;
         int32_t* h_cnt = (int32_t*)(h_off + n);
@@ -550,28 +616,32 @@ int match_pairs_impl(esfm_bank* b, const esfm_pair_t* pairs, int64_t n_pairs, do
         CUDA_TRY(cudaMemcpyAsync(h_cnt, ctx->d_pair_cnt, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         ctx->stats.d2h_bytes += meta;
-        if (int rc = collect_timing(ctx)) { delete res; return rc; }
+        if (int rc = collect_timing(ctx)) { esfm_results_destroy(res); return rc; }
         const unsigned long long n_matches = h_cur[0];
-        if ((int)h_cur[1] != 0 || n_matches > ctx->arena_cap) { delete res; return fail(ESFM_ERR_CAPACITY, "match arena overflow (internal sizing error)"); }
-        const uint64_t base = res->matches.size();
-        const uint64_t vbase = (uint64_t)res->total_matches;
+        if ((int)h_cur[1] != 0 || n_matches > ctx->arena_cap) { esfm_results_destroy(res); return fail(ESFM_ERR_CAPACITY, "match arena overflow (internal sizing error)"); }
+        const uint64_t seg = (uint64_t)res->segments.size();
         for (size_t k = 0; k < n; ++k) {
             res->counts[c0 + k] = h_cnt[k];
-            res->offsets[c0 + k] = (fetch ? base : vbase) + h_off[k];
+            res->offsets[c0 + k] = (seg << 40) | (uint64_t)h_off[k];
             const PairDesc& pd = res->pairs[c0 + k];
             ctx->stats.comparisons += (uint64_t)b->rows[pd.q_frame] * (uint64_t)b->rows[pd.t_frame];
         }
         ctx->stats.pairs += n;
         res->total_matches += (int64_t)n_matches;
-        if (fetch && n_matches > 0) {
-            const size_t bytes = (size_t)n_matches * sizeof(esfm_dmatch_t);
-            res->matches.resize((size_t)base + (size_t)n_matches);
-            if (int rc = grow_stage(ctx, bytes)) { delete res; return rc; }
-            CUDA_TRY(cudaMemcpyAsync(ctx->h_stage, ctx->arena, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            memcpy(res->matches.data() + base, ctx->h_stage, bytes);
-            ctx->stats.d2h_bytes += bytes;
-        } else if (!fetch) {
+        if (fetch) {
+            esfm_results::Segment sg{nullptr, (size_t)n_matches};
+            if (n_matches > 0) {
+                const size_t bytes = (size_t)n_matches * sizeof(esfm_dmatch_t);
+                sg.ptr = (esfm_dmatch_t*)pool_acquire(ctx, bytes, nullptr);
+                if (!sg.ptr) { esfm_results_destroy(res); return fail(ESFM_ERR_NOMEM, "pinned buffer of %zu bytes for the matches failed", bytes); }
+                res->segments.push_back(sg);
+                CUDA_TRY(cudaMemcpyAsync(sg.ptr, ctx->arena, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                ctx->stats.d2h_bytes += bytes;
+            } else {
+                res->segments.push_back(sg);
+            }
+        } else {
             res->device_matches = n_matches;
             res->arena_generation = ctx->arena_generation;
             if (n_chunks > 1) res->arena_generation = 0;  // cannot be fetched later: arena is reused per chunk
@@ -609,15 +679,16 @@ extern "C" int esfm_results_fetch(esfm_results_t* r) {
     if (r->arena_generation == 0 || r->arena_generation != ctx->arena_generation)
         return fail(ESFM_ERR_STATE, "device-resident matches are gone (the arena was reused by a later batch or the batch spanned several chunks)");
     if (int rc = set_device(ctx)) return rc;
+    esfm_results::Segment sg{nullptr, (size_t)r->device_matches};
     if (r->device_matches > 0) {
         const size_t bytes = (size_t)r->device_matches * sizeof(esfm_dmatch_t);
-        r->matches.resize((size_t)r->device_matches);
-        if (int rc = grow_stage(ctx, bytes)) return rc;
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_stage, ctx->arena, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        sg.ptr = (esfm_dmatch_t*)pool_acquire(ctx, bytes, nullptr);
+        if (!sg.ptr) return fail(ESFM_ERR_NOMEM, "pinned buffer of %zu bytes for the matches failed", bytes);
+        CUDA_TRY(cudaMemcpyAsync(sg.ptr, ctx->arena, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        memcpy(r->matches.data(), ctx->h_stage, bytes);
         ctx->stats.d2h_bytes += bytes;
     }
+    r->segments.assign(1, sg);
     r->fetched = true;
     return ESFM_OK;
 }
@@ -648,12 +719,12 @@ extern "C" int esfm_match_pair(esfm_bank_t* b, int query_frame, int train_frame,
     if (int rc = match_pairs_impl(b, &p, 1, ratio, cross_check, true, &r)) return rc;
     const int n = r->counts[0];
     if (n > cap || (n > 0 && !out)) {
-        delete r;
+        esfm_results_destroy(r);
         return fail(ESFM_ERR_CAPACITY, "output buffer holds %d matches, %d needed", cap, n);
     }
-    if (n > 0) memcpy(out, r->matches.data() + r->offsets[0], (size_t)n * sizeof(esfm_dmatch_t));
+    if (n > 0) memcpy(out, r->segments[0].ptr + (r->offsets[0] & (((uint64_t)1 << 40) - 1)), (size_t)n * sizeof(esfm_dmatch_t));
     *n_matches = n;
-    delete r;
+    esfm_results_destroy(r);
     return ESFM_OK;
 }
 
@@ -729,7 +800,8 @@ extern "C" int esfm_results_pair_at(esfm_results_t* r, int64_t k, int* query_fra
     if (n_matches) *n_matches = r->counts[(size_t)k];
     if (matches) {
         if (!r->fetched) return fail(ESFM_ERR_STATE, "matches are device-resident; call esfm_results_fetch first");
-        *matches = r->counts[(size_t)k] > 0 ? r->matches.data() + r->offsets[(size_t)k] : nullptr;
+        const uint64_t o = r->offsets[(size_t)k];
+        *matches = r->counts[(size_t)k] > 0 ? r->segments[(size_t)(o >> 40)].ptr + (o & (((uint64_t)1 << 40) - 1)) : nullptr;
     }
     return ESFM_OK;
 }
@@ -751,6 +823,8 @@ extern "C" int esfm_results_pair_counts(esfm_results_t* r, int32_t* counts) {
 }
 
 extern "C" int esfm_results_destroy(esfm_results_t* r) {
+    if (!r) return ESFM_OK;
+    for (auto& s : r->segments) pool_release(r->ctx, s.ptr);
     delete r;
     return ESFM_OK;
 }
