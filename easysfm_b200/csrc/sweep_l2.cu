@@ -239,9 +239,13 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_l2_kernel(const SweepP
                                              make_float2(b3.x, b3.y), make_float2(b3.z, b3.w)};
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float2 na = make_float2(-a[i], -a[i]);
+                            const float na = -a[i];
 #pragma unroll
-                            for (int jp = 0; jp < 8; ++jp) acc[i][jp] = __ffma2_rn(na, b[jp], acc[i][jp]);
+                            for (int jp = 0; jp < 8; ++jp) {
+                                unsigned long long& c = *reinterpret_cast<unsigned long long*>(&acc[i][jp]);
+                                const unsigned long long bb = *reinterpret_cast<const unsigned long long*>(&b[jp]);
+                                asm("{ .reg .b64 aa; mov.b64 aa, {%2, %2}; fma.rn.f32x2 %0, aa, %1, %0; }" : "+l"(c) : "l"(bb), "f"(na));
+                            }
                         }
                     }
 
