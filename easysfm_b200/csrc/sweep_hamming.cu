@@ -16,6 +16,8 @@
 //                        column top-1: min over the thread's 4 rows, one warp REDUX.MIN per train row,
 //                                      one shared-memory atomicMin by lane 0.
 // Results land in the same 64-bit key scratch the L2 sweep uses (distance in the high word, as an integer).
+#include <cstdlib>
+
 #include "esfm_internal.cuh"
 
 namespace esfm {
@@ -50,12 +52,38 @@ __device__ __forceinline__ HamUnit decode_ham_unit(const SweepParams& p, int uni
     return u;
 }
 
+// Keys at or above this value mean "no candidate": 0xffffffff is the initial value, and rows past the end of the
+// query frame carry the index kHamInvalidRow so that dist * 2^20 + index can never win a column minimum
+// (largest real key < 2^29; 0x7ff00000 + 256 * 2^20 still fits in 32 bits).
+constexpr uint32_t kHamInvalidRow = 0x7ff00000u;
+
 __device__ __forceinline__ u64 expand_key(uint32_t k) {
-    return k == 0xffffffffu ? kKeyInit : make_key(k >> kHamIdxBits, k & kHamIdxMask);
+    return k >= kHamInvalidRow ? kKeyInit : make_key(k >> kHamIdxBits, k & kHamIdxMask);
+}
+
+// 256-bit Hamming distance of a query (8 words in registers) and a train descriptor (two 128-bit words).
+//   plain  : 8 LOP3 (xor) + 8 POPC + 4 IADD3                                  -> POPC-pipe bound (16 lanes/clk/SM)
+//   CSA    : 8 LOP3 (xor) + 4 carry-save adders (2 LOP3 each: xor3 0x96, majority 0xe8) compress the 8 words to
+//            ones, ones, twos, fours -> 4 POPC + 3 shift-adds: halves the load on the scarce POPC pipe by moving
+//            work to the 4x wider LOP3 pipe (Harley-Seal).  Bit-exact either way.
+template <bool CSA>
+__device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uint4& x0, const uint4& x1) {
+    const uint32_t w0 = q[0] ^ x0.x, w1 = q[1] ^ x0.y, w2 = q[2] ^ x0.z, w3 = q[3] ^ x0.w;
+    const uint32_t w4 = q[4] ^ x1.x, w5 = q[5] ^ x1.y, w6 = q[6] ^ x1.z, w7 = q[7] ^ x1.w;
+    if (!CSA) {
+        return __popc(w0) + __popc(w1) + __popc(w2) + __popc(w3) + __popc(w4) + __popc(w5) + __popc(w6) + __popc(w7);
+    } else {
+        const uint32_t s0 = w0 ^ w1 ^ w2, c0 = (w0 & w1) | (w2 & (w0 ^ w1));
+        const uint32_t s1 = w3 ^ w4 ^ w5, c1 = (w3 & w4) | (w5 & (w3 ^ w4));
+        const uint32_t s2 = s0 ^ s1 ^ w6, c2 = (s0 & s1) | (w6 & (s0 ^ s1));
+        const uint32_t s3 = c0 ^ c1 ^ c2, c3 = (c0 & c1) | (c2 & (c0 ^ c1));
+        return __popc(s2) + __popc(w7) + 2u * __popc(s3) + 4u * __popc(c3);
+    }
 }
 
 }  // namespace
 
+template <bool CSA>
 __global__ void __launch_bounds__(kHamThreads, 1) sweep_hamming_kernel(const SweepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* Ts = reinterpret_cast<uint4*>(smem_raw);                                   // kHamStages x 256 rows x 2 uint4
@@ -122,7 +150,7 @@ __global__ void __launch_bounds__(kHamThreads, 1) sweep_hamming_kernel(const Swe
                 }
                 q[r][0] = a.x; q[r][1] = a.y; q[r][2] = a.z; q[r][3] = a.w;
                 q[r][4] = b.x; q[r][5] = b.y; q[r][6] = b.z; q[r][7] = b.w;
-                qidx[r] = valid ? (uint32_t)row : 0xffffffffu;  // all-ones => this row never wins a column minimum
+                qidx[r] = valid ? (uint32_t)row : kHamInvalidRow;  // => this row never wins a column minimum
                 m1[r] = 0xffffffffu;
                 m2[r] = 0xffffffffu;
             }
@@ -139,14 +167,12 @@ __global__ void __launch_bounds__(kHamThreads, 1) sweep_hamming_kernel(const Swe
                     uint32_t cmin = 0xffffffffu;
 #pragma unroll
                     for (int r = 0; r < kHamRQ; ++r) {
-                        const uint32_t d = __popc(q[r][0] ^ x0.x) + __popc(q[r][1] ^ x0.y) + __popc(q[r][2] ^ x0.z) +
-                                           __popc(q[r][3] ^ x0.w) + __popc(q[r][4] ^ x1.x) + __popc(q[r][5] ^ x1.y) +
-                                           __popc(q[r][6] ^ x1.z) + __popc(q[r][7] ^ x1.w);
-                        const uint32_t d20 = d << kHamIdxBits;
-                        const uint32_t key = d20 + (tg0 + (uint32_t)t);
+                        const uint32_t d = hamming256<CSA>(q[r], x0, x1);
+                        // packed keys: multiply-adds run on the FMA pipe, which this kernel leaves idle
+                        const uint32_t key = d * (1u << kHamIdxBits) + (tg0 + (uint32_t)t);
                         m2[r] = min(m2[r], max(m1[r], key));
                         m1[r] = min(m1[r], key);
-                        cmin = min(cmin, d20 | qidx[r]);
+                        cmin = min(cmin, d * (1u << kHamIdxBits) + qidx[r]);
                     }
                     const uint32_t cw = __reduce_min_sync(0xffffffffu, cmin);
                     if (lane == 0) atomicMin(cm + t, cw);
@@ -157,7 +183,7 @@ __global__ void __launch_bounds__(kHamThreads, 1) sweep_hamming_kernel(const Swe
             // each query row is owned by exactly one thread of one unit: plain stores
 #pragma unroll
             for (int r = 0; r < kHamRQ; ++r) {
-                if (qidx[r] != 0xffffffffu) {
+                if (qidx[r] != kHamInvalidRow) {
                     rk1[qidx[r]] = expand_key(m1[r]);
                     rk2[qidx[r]] = expand_key(m2[r]);
                 }
@@ -167,7 +193,7 @@ __global__ void __launch_bounds__(kHamThreads, 1) sweep_hamming_kernel(const Swe
         if (u.qb1 > u.qb0) {
             for (int x = threadIdx.x; x < u.ft; x += kConsumerThreads) {
                 const uint32_t k = colmin[x];
-                if (k != 0xffffffffu) atomicMin(ck1 + x, expand_key(k));
+                if (k < kHamInvalidRow) atomicMin(ck1 + x, expand_key(k));
             }
         }
     }
@@ -189,9 +215,18 @@ cudaError_t launch_sweep_hamming(const SweepParams& p, int sm_count, cudaStream_
     const int grid = n_units < sm_count ? n_units : sm_count;
     const size_t smem = sweep_hamming_smem_bytes(p.col_cap);
     if (smem > 232448) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(sweep_hamming_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    sweep_hamming_kernel<<<grid, kHamThreads, smem, s>>>(p);
+    // ESFM_HAMMING_PLAIN=1 selects the 8-POPC form (kept for A/B measurements; results are identical)
+    static const bool plain = [] { const char* e = getenv("ESFM_HAMMING_PLAIN"); return e && e[0] == '1'; }();
+    cudaError_t e;
+    if (plain) {
+        e = cudaFuncSetAttribute(sweep_hamming_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        sweep_hamming_kernel<false><<<grid, kHamThreads, smem, s>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(sweep_hamming_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        sweep_hamming_kernel<true><<<grid, kHamThreads, smem, s>>>(p);
+    }
     return cudaGetLastError();
 }
 
