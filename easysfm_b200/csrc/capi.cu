@@ -499,10 +499,10 @@ int ensure_scratch(esfm_ctx* ctx, const esfm_bank* b, const ChunkPlan& pl) {
 }
 
 int units_per_pair(const esfm_ctx* ctx, const esfm_bank* b, size_t n_chunk_pairs) {
-    if (n_chunk_pairs >= (size_t)2 * ctx->sm_count) return 1;
+    if (n_chunk_pairs >= (size_t)4 * ctx->sm_count) return 1;
     const int qblock_rows = b->kind == ESFM_KIND_F32X64 ? kQTiles * kTile : kConsumerThreads * kHamRQ;
     const int max_blocks = std::max(1, (b->max_rows + qblock_rows - 1) / qblock_rows);
-    const int want = (int)((2 * (size_t)ctx->sm_count + n_chunk_pairs - 1) / std::max<size_t>(n_chunk_pairs, 1));
+    const int want = (int)((4 * (size_t)ctx->sm_count + n_chunk_pairs - 1) / std::max<size_t>(n_chunk_pairs, 1));
     return std::max(1, std::min(want, max_blocks));
 }
 

@@ -66,6 +66,12 @@ __device__ __forceinline__ u64 expand_key(uint32_t k) {
 //   CSA    : 8 LOP3 (xor) + 4 carry-save adders (2 LOP3 each: xor3 0x96, majority 0xe8) compress the 8 words to
 //            ones, ones, twos, fours -> 4 POPC + 3 shift-adds: halves the load on the scarce POPC pipe by moving
 //            work to the 4x wider LOP3 pipe (Harley-Seal).  Bit-exact either way.
+// carry-save adder on 32 bit-lanes: sum = a ^ b ^ c (LOP3 0x96), carry = majority(a, b, c) (LOP3 0xe8)
+__device__ __forceinline__ void csa(uint32_t& sum, uint32_t& carry, uint32_t a, uint32_t b, uint32_t c) {
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sum) : "r"(a), "r"(b), "r"(c));
+    asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(carry) : "r"(a), "r"(b), "r"(c));
+}
+
 template <bool CSA>
 __device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uint4& x0, const uint4& x1) {
     const uint32_t w0 = q[0] ^ x0.x, w1 = q[1] ^ x0.y, w2 = q[2] ^ x0.z, w3 = q[3] ^ x0.w;
@@ -73,10 +79,11 @@ __device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uin
     if (!CSA) {
         return __popc(w0) + __popc(w1) + __popc(w2) + __popc(w3) + __popc(w4) + __popc(w5) + __popc(w6) + __popc(w7);
     } else {
-        const uint32_t s0 = w0 ^ w1 ^ w2, c0 = (w0 & w1) | (w2 & (w0 ^ w1));
-        const uint32_t s1 = w3 ^ w4 ^ w5, c1 = (w3 & w4) | (w5 & (w3 ^ w4));
-        const uint32_t s2 = s0 ^ s1 ^ w6, c2 = (s0 & s1) | (w6 & (s0 ^ s1));
-        const uint32_t s3 = c0 ^ c1 ^ c2, c3 = (c0 & c1) | (c2 & (c0 ^ c1));
+        uint32_t s0, c0, s1, c1, s2, c2, s3, c3;
+        csa(s0, c0, w0, w1, w2);
+        csa(s1, c1, w3, w4, w5);
+        csa(s2, c2, s0, s1, w6);
+        csa(s3, c3, c0, c1, c2);
         return __popc(s2) + __popc(w7) + 2u * __popc(s3) + 4u * __popc(c3);
     }
 }
@@ -84,7 +91,7 @@ __device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uin
 }  // namespace
 
 template <bool CSA>
-__global__ void __launch_bounds__(kHamThreads, 1) sweep_hamming_kernel(const SweepParams p) {
+__global__ void __launch_bounds__(kHamThreads, 2) sweep_hamming_kernel(const SweepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* Ts = reinterpret_cast<uint4*>(smem_raw);                                   // kHamStages x 256 rows x 2 uint4
     uint64_t* bars = reinterpret_cast<uint64_t*>(Ts + kHamStages * kHamTile * 2);
@@ -212,9 +219,11 @@ int sweep_hamming_max_rows() {
 cudaError_t launch_sweep_hamming(const SweepParams& p, int sm_count, cudaStream_t s) {
     const int n_units = p.n_pairs * p.units_per_pair;
     if (n_units <= 0) return cudaSuccess;
-    const int grid = n_units < sm_count ? n_units : sm_count;
     const size_t smem = sweep_hamming_smem_bytes(p.col_cap);
     if (smem > 232448) return cudaErrorInvalidValue;
+    // two CTAs per SM (4 warps per scheduler) whenever their shared memory fits side by side
+    const int ctas_per_sm = (2 * (smem + 1024) <= 232448) ? 2 : 1;
+    const int grid = n_units < sm_count * ctas_per_sm ? n_units : sm_count * ctas_per_sm;
     // ESFM_HAMMING_PLAIN=1 selects the 8-POPC form (kept for A/B measurements; results are identical)
     static const bool plain = [] { const char* e = getenv("ESFM_HAMMING_PLAIN"); return e && e[0] == '1'; }();
     cudaError_t e;
