@@ -201,6 +201,14 @@ extern "C" int esfm_init(int device, void* cuda_stream, esfm_ctx_t** out) {
     }
     e = cudaMalloc((void**)&ctx->d_cursor, 2 * sizeof(unsigned long long));
     if (e != cudaSuccess) { delete ctx; return fail(ESFM_ERR_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    {   // banks come and go (one per all-pairs call in the per-call API): allocate them stream-ordered from the
+        // device's memory pool and keep freed blocks cached, so steady state never pays cudaMalloc / cudaFree
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     *out = ctx;
     return ESFM_OK;
 }
@@ -333,19 +341,19 @@ static int bank_alloc_layout(esfm_bank* b) {
     const size_t total_rows = (size_t)b->row_off[b->n_frames];
     // one extra tile of slack so tile-granular reads past the last frame stay inside the allocation
     b->rows_bytes = (total_rows + kHamTile) * b->row_bytes();
-    cudaError_t e = cudaMalloc(&b->d_rows, b->rows_bytes);
-    if (e != cudaSuccess) return fail(ESFM_ERR_NOMEM, "cudaMalloc(%zu) for the descriptor bank failed: %s", b->rows_bytes, cudaGetErrorString(e));
+    cudaError_t e = cudaMallocAsync(&b->d_rows, b->rows_bytes, ctx->stream);
+    if (e != cudaSuccess) return fail(ESFM_ERR_NOMEM, "cudaMallocAsync(%zu) for the descriptor bank failed: %s", b->rows_bytes, cudaGetErrorString(e));
     // only the slack past the last frame needs defined contents
     CUDA_TRY(cudaMemsetAsync((uint8_t*)b->d_rows + total_rows * b->row_bytes(), 0, (size_t)kHamTile * b->row_bytes(), ctx->stream));
     if (b->kind == ESFM_KIND_F32X64) {
         b->kmajor_bytes = ((size_t)b->tile_off[b->n_frames] + 1) * kTileBytes;
-        e = cudaMalloc((void**)&b->d_kmajor, b->kmajor_bytes);
-        if (e != cudaSuccess) return fail(ESFM_ERR_NOMEM, "cudaMalloc(%zu) for the k-major bank failed: %s", b->kmajor_bytes, cudaGetErrorString(e));
+        e = cudaMallocAsync((void**)&b->d_kmajor, b->kmajor_bytes, ctx->stream);
+        if (e != cudaSuccess) return fail(ESFM_ERR_NOMEM, "cudaMallocAsync(%zu) for the k-major bank failed: %s", b->kmajor_bytes, cudaGetErrorString(e));
     }
     const size_t nb = (size_t)(b->n_frames + 1) * sizeof(int);
-    CUDA_TRY(cudaMalloc((void**)&b->d_frame_rows, nb));
-    CUDA_TRY(cudaMalloc((void**)&b->d_row_off, nb));
-    CUDA_TRY(cudaMalloc((void**)&b->d_tile_off, nb));
+    CUDA_TRY(cudaMallocAsync((void**)&b->d_frame_rows, nb, ctx->stream));
+    CUDA_TRY(cudaMallocAsync((void**)&b->d_row_off, nb, ctx->stream));
+    CUDA_TRY(cudaMallocAsync((void**)&b->d_tile_off, nb, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(b->d_frame_rows, b->rows.data(), (size_t)b->n_frames * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(b->d_row_off, b->row_off.data(), nb, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(b->d_tile_off, b->tile_off.data(), nb, cudaMemcpyHostToDevice, ctx->stream));
@@ -446,10 +454,14 @@ extern "C" int esfm_bank_destroy(esfm_bank_t* b) {
     if (!b) return ESFM_OK;
     if (b->ctx) {
         cudaSetDevice(b->ctx->device);
-        cudaStreamSynchronize(b->ctx->stream);
+        cudaStream_t s = b->ctx->stream;   // stream-ordered frees: queued behind any work still using the bank
+        if (b->d_rows) cudaFreeAsync(b->d_rows, s);
+        if (b->d_kmajor) cudaFreeAsync(b->d_kmajor, s);
+        if (b->d_frame_rows) cudaFreeAsync(b->d_frame_rows, s);
+        if (b->d_row_off) cudaFreeAsync(b->d_row_off, s);
+        if (b->d_tile_off) cudaFreeAsync(b->d_tile_off, s);
+        pool_release(b->ctx, b->h_up);
     }
-    cudaFree(b->d_rows); cudaFree(b->d_kmajor); cudaFree(b->d_frame_rows); cudaFree(b->d_row_off); cudaFree(b->d_tile_off);
-    if (b->ctx) pool_release(b->ctx, b->h_up);
     delete b;
     return ESFM_OK;
 }
