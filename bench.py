@@ -402,6 +402,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args, args.kind)
 
+    # stdout carries exactly ONE line (the JSON): anything libraries print to fd 1 (e.g. NCCL's version banner)
+    # is routed to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import easysfm_b200 as esfm
@@ -426,11 +432,13 @@ def main():
         sec = bench_kind(args, other, ctx, dev, rank, world, dist, max(3, args.steps // 2), args.warmup, args.cpu_budget_s / 2)
         primary["secondary"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "dtype", "config", "pairs_per_s", "e2e",
                                                     "roofline", "cpu_baseline", "gpu_launches", "clocks", "full_job_estimate_s")}
-    if rank == 0:
-        print(json.dumps(primary))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    if rank == 0:
+        os.write(json_fd, (json.dumps(primary) + "\n").encode())
+    os.close(json_fd)
     return 0
 
 
