@@ -612,9 +612,23 @@ int match_pairs_impl(esfm_bank* b, const esfm_pair_t* pairs, int64_t n_pairs, do
     const ChunkPlan pl = plan_chunks(b, n_pairs);
     if (int rc = ensure_scratch(ctx, b, pl)) { esfm_results_destroy(res); return rc; }
     const size_t n_chunks = ((size_t)n_pairs + pl.chunk_pairs - 1) / pl.chunk_pairs;
+    std::vector<uint32_t> order;
+    std::vector<PairDesc> sorted;
     for (size_t c0 = 0; c0 < (size_t)n_pairs; c0 += pl.chunk_pairs) {
         const size_t n = std::min(pl.chunk_pairs, (size_t)n_pairs - c0);
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_pairs, res->pairs.data() + c0, n * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
+        // Launch order inside the chunk: by TRAIN frame.  The sweep re-streams the train frame once per query block
+        // (32x per pair at 8k rows), the query frame only once; CTAs that run concurrently take consecutive units, so
+        // sorting by train frame makes them stream the SAME tiles and L2 serves the re-reads (the reference's loop order
+        // shares the query frame instead and cost 6-15x the algorithmic DRAM traffic, profiles/traffic_bench_r1.csv).
+        order.resize(n);
+        for (size_t k = 0; k < n; ++k) order[k] = (uint32_t)k;
+        const PairDesc* pp = res->pairs.data() + c0;
+        std::stable_sort(order.begin(), order.end(), [pp](uint32_t a, uint32_t b2) {
+            return pp[a].t_frame != pp[b2].t_frame ? pp[a].t_frame < pp[b2].t_frame : pp[a].q_frame < pp[b2].q_frame;
+        });
+        sorted.resize(n);
+        for (size_t k = 0; k < n; ++k) sorted[k] = pp[order[k]];
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_pairs, sorted.data(), n * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
         ctx->stats.h2d_bytes += n * sizeof(PairDesc);
         if (int rc = run_chunk(ctx, b, pl, n, ratio, cross_check, nullptr, nullptr)) { esfm_results_destroy(res); return rc; }
         // counts + offsets + cursor back
@@ -633,9 +647,9 @@ int match_pairs_impl(esfm_bank* b, const esfm_pair_t* pairs, int64_t n_pairs, do
         if ((int)h_cur[1] != 0 || n_matches > ctx->arena_cap) { esfm_results_destroy(res); return fail(ESFM_ERR_CAPACITY, "match arena overflow (internal sizing error)"); }
         const uint64_t seg = (uint64_t)res->segments.size();
         for (size_t k = 0; k < n; ++k) {
-            res->counts[c0 + k] = h_cnt[k];
-            res->offsets[c0 + k] = (seg << 40) | (uint64_t)h_off[k];
-            const PairDesc& pd = res->pairs[c0 + k];
+            res->counts[c0 + order[k]] = h_cnt[k];
+            res->offsets[c0 + order[k]] = (seg << 40) | (uint64_t)h_off[k];
+            const PairDesc& pd = sorted[k];
             ctx->stats.comparisons += (uint64_t)b->rows[pd.q_frame] * (uint64_t)b->rows[pd.t_frame];
         }
         ctx->stats.pairs += n;
