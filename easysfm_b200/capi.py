@@ -20,6 +20,10 @@ DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<
 PAIR_DTYPE = np.dtype([("query", "<i4"), ("train", "<i4")])
 
 
+L2_ENGINE_FFMA = 0
+L2_ENGINE_TC = 1
+
+
 class EsfmError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"esfm error {code}: {msg}")
@@ -53,6 +57,8 @@ SIGNATURES = {
     "esfm_get_stats": (c_int, [c_void_p, POINTER(Stats)]),
     "esfm_set_profiling": (c_int, [c_void_p, c_int]),
     "esfm_device_sm_count": (c_int, [c_void_p, POINTER(c_int)]),
+    "esfm_set_l2_engine": (c_int, [c_void_p, c_int]),
+    "esfm_get_l2_engine": (c_int, [c_void_p, POINTER(c_int)]),
     "esfm_bank_create": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
     "esfm_bank_set_frame": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_size_t]),
     "esfm_bank_set_frame_rows": (c_int, [c_void_p, c_int, c_int]),
@@ -171,6 +177,16 @@ class Context:
         n = c_int()
         _check(self._lib.esfm_device_sm_count(self._h, ctypes.byref(n)))
         return n.value
+
+    def set_l2_engine(self, engine):
+        """'ffma' (exact-FP32 FMA pipe) or 'tc' (3xTF32 on the tcgen05 tensor cores) for the SURF / L2 sweep."""
+        code = {"ffma": L2_ENGINE_FFMA, "tc": L2_ENGINE_TC}.get(engine, engine)
+        _check(self._lib.esfm_set_l2_engine(self._h, int(code)))
+
+    def l2_engine(self) -> str:
+        e = c_int(0)
+        _check(self._lib.esfm_get_l2_engine(self._h, ctypes.byref(e)))
+        return {L2_ENGINE_FFMA: "ffma", L2_ENGINE_TC: "tc"}[e.value]
 
     def bank(self, kind: int, n_frames: int) -> "Bank":
         return Bank(self, kind, n_frames)

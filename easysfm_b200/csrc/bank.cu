@@ -3,7 +3,7 @@
 // F32X64: rows_f32[total_rows][64] (row-major, as the reference's cv::Mat holds SURF descriptors,
 // cpp_code/include/utility.h:31) -> k-major 128-row tiles + half squared norms, the operand layout the
 // sweep kernel bulk-copies into shared memory with one cp.async.bulk per tile.
-#include "esfm_internal.cuh"
+#include "tc_layout.cuh"
 
 namespace esfm {
 
@@ -53,6 +53,66 @@ cudaError_t launch_pack_f32(const float* rows, const int* frame_rows, const int*
                             int n_frames, int n_tiles_total, float* kmajor, cudaStream_t s) {
     if (n_tiles_total <= 0) return cudaSuccess;
     pack_f32_kernel<<<n_tiles_total, 256, 0, s>>>(rows, frame_rows, frame_row_off, frame_tile_off, n_frames, kmajor);
+    return cudaGetLastError();
+}
+
+// F32X64 -> the tensor-core operand images of tc_layout.cuh: per 128-row tile, 16 groups x 4096 B of SWIZZLE_128B
+// hi/lo atoms plus the four (role, part) augmented arrays.  One block per tile; byte-for-byte what tc_pack_row_host writes.
+__global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ rows, const int* __restrict__ frame_rows,
+                                                      const int* __restrict__ frame_row_off,
+                                                      const int* __restrict__ frame_tile_off, int n_frames, int n_groups_total,
+                                                      unsigned char* __restrict__ tc_main, unsigned char* __restrict__ tc_aug) {
+    __shared__ float tile[kTile][kDim + 4];
+    const int t = blockIdx.x;
+    int lo = 0, hi = n_frames - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (frame_tile_off[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const int f = lo;
+    const int row0 = (t - frame_tile_off[f]) * kTile;
+    int valid = frame_rows[f] - row0;
+    valid = valid < 0 ? 0 : (valid > kTile ? kTile : valid);
+    const float4* src = reinterpret_cast<const float4*>(rows + ((size_t)frame_row_off[f] + row0) * kDim);
+    unsigned char* out = tc_main + (size_t)t * 16 * kTcGroupBytes;
+    for (int idx = threadIdx.x; idx < kTile * (kDim / 4); idx += blockDim.x) {
+        const int r = idx / (kDim / 4), c4 = idx % (kDim / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < valid) v = src[(size_t)r * (kDim / 4) + c4];
+        *reinterpret_cast<float4*>(&tile[r][c4 * 4]) = v;
+        const float4 h = make_float4(tc_tf32_hi(v.x), tc_tf32_hi(v.y), tc_tf32_hi(v.z), tc_tf32_hi(v.w));
+        const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        const int k = c4 * 4;
+        const int off = (r >> 3) * kTcGroupBytes + (k >> 5) * 1024 + tc_sw128_off(r & 7, k & 31);
+        *reinterpret_cast<float4*>(out + off) = h;
+        *reinterpret_cast<float4*>(out + off + 2048) = l;
+    }
+    __syncthreads();
+    if (threadIdx.x < kTile) {
+        const int r = threadIdx.x;
+        float s = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < kDim; ++k) s = __fmaf_rn(tile[r][k], tile[r][k], s);
+        const float h = (r < valid) ? 0.5f * s : kTcPadNorm;
+        const float hh = tc_tf32_hi(h), hl = h - hh;
+        const size_t part = (size_t)n_groups_total * kTcAugGroupBytes;
+        unsigned char* a = tc_aug + ((size_t)t * 16 + (r >> 3)) * kTcAugGroupBytes + (r & 7) * 16;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        // query role: (1, h, 0, 0 | 0 x 4); train role: (-h, -1, 0, 0 | 0 x 4); k-chunk 1 (columns 4..7) is all zero
+        *reinterpret_cast<float4*>(a + 0 * part) = make_float4(1.f, hh, 0.f, 0.f);
+        *reinterpret_cast<float4*>(a + 1 * part) = make_float4(0.f, hl, 0.f, 0.f);
+        *reinterpret_cast<float4*>(a + 2 * part) = make_float4(-hh, -1.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(a + 3 * part) = make_float4(-hl, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(a + q * part + 128) = z;
+    }
+}
+
+cudaError_t launch_pack_tc(const float* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
+                           int n_frames, int n_tiles_total, unsigned char* tc_main, unsigned char* tc_aug, cudaStream_t s) {
+    if (n_tiles_total <= 0) return cudaSuccess;
+    pack_tc_kernel<<<n_tiles_total, 256, 0, s>>>(rows, frame_rows, frame_row_off, frame_tile_off, n_frames, n_tiles_total * 16,
+                                                 tc_main, tc_aug);
     return cudaGetLastError();
 }
 

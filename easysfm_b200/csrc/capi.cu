@@ -6,13 +6,14 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
 #include <unordered_map>
 #include <vector>
 
-#include "esfm_internal.cuh"
+#include "tc_layout.cuh"
 
 using namespace esfm;
 
@@ -47,6 +48,7 @@ struct esfm_ctx {
     bool own_stream = false;
     int sm_count = 0;
     bool profiling = true;
+    int l2_engine = ESFM_L2_ENGINE_FFMA;   // which sweep kernel serves ESFM_KIND_F32X64 (esfm_set_l2_engine / $ESFM_L2_ENGINE)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     esfm_stats_t stats{};
     // device scratch, grown on demand
@@ -109,6 +111,7 @@ struct esfm_bank {
     // device
     void* d_rows = nullptr;  size_t rows_bytes = 0;
     float* d_kmajor = nullptr; size_t kmajor_bytes = 0;
+    unsigned char* d_tc = nullptr; size_t tc_bytes = 0;   // tensor-core operand images (built on first use), main then aug
     int* d_frame_rows = nullptr;
     int* d_row_off = nullptr;
     int* d_tile_off = nullptr;
@@ -188,6 +191,11 @@ extern "C" int esfm_init(int device, void* cuda_stream, esfm_ctx_t** out) {
     if (!ctx) return fail(ESFM_ERR_NOMEM, "esfm_init: out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* eng = getenv("ESFM_L2_ENGINE")) {
+        if (!strcmp(eng, "tc") || !strcmp(eng, "tensor")) ctx->l2_engine = ESFM_L2_ENGINE_TC;
+        else if (!strcmp(eng, "ffma")) ctx->l2_engine = ESFM_L2_ENGINE_FFMA;
+        else { delete ctx; return fail(ESFM_ERR_INVALID, "ESFM_L2_ENGINE=%s: expected 'ffma' or 'tc'", eng); }
+    }
     if (cuda_stream) {
         ctx->stream = (cudaStream_t)cuda_stream;
     } else {
@@ -243,6 +251,19 @@ extern "C" int esfm_get_stats(esfm_ctx_t* ctx, esfm_stats_t* out) {
 extern "C" int esfm_set_profiling(esfm_ctx_t* ctx, int enabled) {
     if (!ctx) return fail(ESFM_ERR_INVALID, "ctx is NULL");
     ctx->profiling = enabled != 0;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_set_l2_engine(esfm_ctx_t* ctx, int engine) {
+    if (!ctx) return fail(ESFM_ERR_INVALID, "ctx is NULL");
+    if (engine != ESFM_L2_ENGINE_FFMA && engine != ESFM_L2_ENGINE_TC) return fail(ESFM_ERR_INVALID, "unknown L2 engine %d", engine);
+    ctx->l2_engine = engine;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_get_l2_engine(esfm_ctx_t* ctx, int* engine) {
+    if (!ctx || !engine) return fail(ESFM_ERR_INVALID, "esfm_get_l2_engine: NULL argument");
+    *engine = ctx->l2_engine;
     return ESFM_OK;
 }
 
@@ -446,7 +467,7 @@ extern "C" int esfm_bank_frame_rows(esfm_bank_t* b, int frame_id, int* rows) {
 
 extern "C" int esfm_bank_device_bytes(esfm_bank_t* b, size_t* bytes) {
     if (!b || !bytes) return fail(ESFM_ERR_INVALID, "NULL argument");
-    *bytes = b->device_allocated ? b->rows_bytes + b->kmajor_bytes : 0;
+    *bytes = b->device_allocated ? b->rows_bytes + b->kmajor_bytes + b->tc_bytes : 0;
     return ESFM_OK;
 }
 
@@ -457,6 +478,7 @@ extern "C" int esfm_bank_destroy(esfm_bank_t* b) {
         cudaStream_t s = b->ctx->stream;   // stream-ordered frees: queued behind any work still using the bank
         if (b->d_rows) cudaFreeAsync(b->d_rows, s);
         if (b->d_kmajor) cudaFreeAsync(b->d_kmajor, s);
+        if (b->d_tc) cudaFreeAsync(b->d_tc, s);
         if (b->d_frame_rows) cudaFreeAsync(b->d_frame_rows, s);
         if (b->d_row_off) cudaFreeAsync(b->d_row_off, s);
         if (b->d_tile_off) cudaFreeAsync(b->d_tile_off, s);
@@ -510,9 +532,26 @@ int ensure_scratch(esfm_ctx* ctx, const esfm_bank* b, const ChunkPlan& pl) {
     return ESFM_OK;
 }
 
+// Tensor-core operand images of an F32X64 bank, built the first time the TC engine sweeps it.
+int ensure_tc_layout(esfm_ctx* ctx, esfm_bank* b) {
+    if (b->d_tc || b->kind != ESFM_KIND_F32X64) return ESFM_OK;
+    const int n_tiles = b->tile_off[b->n_frames];
+    const size_t groups = (size_t)n_tiles * 16;
+    b->tc_bytes = (groups + 16) * ((size_t)kTcGroupBytes + 4 * kTcAugGroupBytes);
+    cudaError_t e = cudaMallocAsync((void**)&b->d_tc, b->tc_bytes, ctx->stream);
+    if (e != cudaSuccess) { b->d_tc = nullptr; b->tc_bytes = 0; return fail(ESFM_ERR_NOMEM, "cudaMallocAsync(%zu) for the tensor-core bank failed: %s", (groups + 16) * ((size_t)kTcGroupBytes + 4 * kTcAugGroupBytes), cudaGetErrorString(e)); }
+    e = launch_pack_tc((const float*)b->d_rows, b->d_frame_rows, b->d_row_off, b->d_tile_off, b->n_frames, n_tiles, b->d_tc,
+                       b->d_tc + groups * kTcGroupBytes, ctx->stream);
+    if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "pack_tc kernel launch failed: %s", cudaGetErrorString(e));
+    if (n_tiles > 0) ctx->stats.kernel_launches += 1;
+    return ESFM_OK;
+}
+
+bool use_tc(const esfm_ctx* ctx, const esfm_bank* b) { return b->kind == ESFM_KIND_F32X64 && ctx->l2_engine == ESFM_L2_ENGINE_TC; }
+
 int units_per_pair(const esfm_ctx* ctx, const esfm_bank* b, size_t n_chunk_pairs) {
     if (n_chunk_pairs >= (size_t)4 * ctx->sm_count) return 1;
-    const int qblock_rows = b->kind == ESFM_KIND_F32X64 ? kQTiles * kTile : kConsumerThreads * kHamRQ;
+    const int qblock_rows = b->kind == ESFM_KIND_F32X64 ? (use_tc(ctx, b) ? kTile : kQTiles * kTile) : kConsumerThreads * kHamRQ;
     const int max_blocks = std::max(1, (b->max_rows + qblock_rows - 1) / qblock_rows);
     const int want = (int)((4 * (size_t)ctx->sm_count + n_chunk_pairs - 1) / std::max<size_t>(n_chunk_pairs, 1));
     return std::max(1, std::min(want, max_blocks));
@@ -523,10 +562,16 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
               float* knn_dist) {
     CUDA_TRY(cudaMemsetAsync(ctx->keys, 0xFF, n * 4 * (size_t)pl.stride * sizeof(u64), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_cursor, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    if (b->kind == ESFM_KIND_F32X64)  // column thresholds start at 0x7f7f7f7f = 3.39e38f ("no bound yet")
-        CUDA_TRY(cudaMemsetAsync(ctx->col_thr, 0x7F, n * (size_t)pl.stride * sizeof(uint32_t), ctx->stream));
+    const bool tc = use_tc(ctx, b);
+    if (tc) if (int rc = ensure_tc_layout(ctx, b)) return rc;
+    if (b->kind == ESFM_KIND_F32X64)  // column thresholds start at "no bound yet": 0x7f7f7f7f = 3.39e38f (FFMA engine),
+                                      // 0x6f6f6f6f = 7.4e28f (TC engine: below its 1e30 pad-row norm)
+        CUDA_TRY(cudaMemsetAsync(ctx->col_thr, tc ? 0x6F : 0x7F, n * (size_t)pl.stride * sizeof(uint32_t), ctx->stream));
     SweepParams sp{};
     sp.kmajor = b->d_kmajor;
+    sp.tc_main = b->d_tc;
+    sp.tc_groups = b->tile_off.empty() ? 0 : b->tile_off[b->n_frames] * 16;
+    sp.tc_aug = b->d_tc ? b->d_tc + (size_t)sp.tc_groups * kTcGroupBytes : nullptr;
     sp.rows_b256 = (const uint4*)b->d_rows;
     sp.frame_rows = b->d_frame_rows;
     sp.frame_row_off = b->d_row_off;
@@ -539,7 +584,8 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     sp.stride = pl.stride;
     sp.col_cap = pl.col_cap;
     if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
-    cudaError_t e = b->kind == ESFM_KIND_F32X64 ? launch_sweep_l2(sp, ctx->sm_count, ctx->stream)
+    cudaError_t e = b->kind == ESFM_KIND_F32X64 ? (tc ? launch_sweep_l2_tc(sp, ctx->sm_count, ctx->stream)
+                                                      : launch_sweep_l2(sp, ctx->sm_count, ctx->stream))
                                                 : launch_sweep_hamming(sp, ctx->sm_count, ctx->stream);
     if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(e));
     if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));

@@ -1,0 +1,195 @@
+// tc_probe.cu -- standalone probe for the tcgen05 (kind::tf32) building blocks of sweep_l2_tc.cu.
+//
+// 1. correctness: one 128-row query tile x N train rows, K = 64 (+8 augmented: norms), 3xTF32 split
+//    (hi.hi + hi.lo + lo.hi), accumulators read back from TMEM and compared with float64 -1/2 d^2;
+// 2. pacing: cycles per tcgen05.mma (M=128, N in {64,128,256}, K=8, both operands in shared memory),
+//    which decides the train-stage width of the sweep (shared-memory operand reads vs the MMA floor).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ../../bin/tc_probe tc_probe.cu
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../tc_layout.cuh"
+
+using namespace esfm;
+
+#define CK(x)                                                                                  \
+    do {                                                                                       \
+        cudaError_t e = (x);                                                                   \
+        if (e != cudaSuccess) {                                                                \
+            printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__);     \
+            exit(2);                                                                           \
+        }                                                                                      \
+    } while (0)
+
+template <int N>
+__global__ void __launch_bounds__(192, 1)
+probe_kernel(const uint8_t* __restrict__ q_main, const uint8_t* __restrict__ q_aug_hi, const uint8_t* __restrict__ q_aug_lo,
+             const uint8_t* __restrict__ t_main, const uint8_t* __restrict__ t_aug_hi, const uint8_t* __restrict__ t_aug_lo,
+             float* __restrict__ out, int terms, int reps, long long* __restrict__ cycles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // Q: 128 rows main (16 groups x 4096) + aug hi/lo (16 x 256 each); T: N rows likewise
+    uint8_t* Qm = smem;                               // 64 KB
+    uint8_t* Tm = Qm + 16 * kTcGroupBytes;            // N/8 * 4096
+    uint8_t* Qa = Tm + (N / 8) * kTcGroupBytes;       // aug hi, then aug lo
+    uint8_t* Ta = Qa + 2 * 16 * kTcAugGroupBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Ta + 2 * (N / 8) * kTcAugGroupBytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4 && lane == 0) {
+        const uint32_t bytes = (16 + N / 8) * (kTcGroupBytes + 2 * kTcAugGroupBytes);
+        mbar_arrive_expect_tx(&bars[0], bytes);
+        bulk_g2s(Qm, q_main, 16 * kTcGroupBytes, &bars[0]);
+        bulk_g2s(Qa, q_aug_hi, 16 * kTcAugGroupBytes, &bars[0]);
+        bulk_g2s(Qa + 16 * kTcAugGroupBytes, q_aug_lo, 16 * kTcAugGroupBytes, &bars[0]);
+        bulk_g2s(Tm, t_main, (N / 8) * kTcGroupBytes, &bars[0]);
+        bulk_g2s(Ta, t_aug_hi, (N / 8) * kTcAugGroupBytes, &bars[0]);
+        bulk_g2s(Ta + (N / 8) * kTcAugGroupBytes, t_aug_lo, (N / 8) * kTcAugGroupBytes, &bars[0]);
+        mbar_wait(&bars[0], 0);
+        tc_fence_after();
+        const uint32_t idesc = tc_idesc_tf32(128, N);
+        const uint32_t qm = smem_u32(Qm), tm = smem_u32(Tm), qa = smem_u32(Qa), ta = smem_u32(Ta);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            const uint32_t d = tmem + (uint32_t)((r & 1) * N) % 512u;
+            bool first = true;
+            for (int term = 0; term < terms; ++term) {
+                // term 0: hi.hi   1: hi.lo   2: lo.hi     (A part, B part)
+                const int pa = term == 2 ? 1 : 0, pb = term == 1 ? 1 : 0;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint64_t da = tc_desc_sw128(qm + pa * 2048 + (ks >> 2) * 1024 + (ks & 3) * 32, kTcGroupBytes);
+                    const uint64_t db = tc_desc_sw128(tm + pb * 2048 + (ks >> 2) * 1024 + (ks & 3) * 32, kTcGroupBytes);
+                    tc_mma_tf32(d, da, db, idesc, !first);
+                    first = false;
+                }
+                const uint64_t da = tc_desc_nosw(qa + pa * 16 * kTcAugGroupBytes, 128, kTcAugGroupBytes);
+                const uint64_t db = tc_desc_nosw(ta + pb * (N / 8) * kTcAugGroupBytes, 128, kTcAugGroupBytes);
+                tc_mma_tf32(d, da, db, idesc, true);
+            }
+        }
+        tc_commit(&bars[1]);
+        mbar_wait(&bars[1], 0);
+        const long long t1 = clock64();
+        if (cycles) *cycles = t1 - t0;
+    }
+    if (warp < 4) {
+        mbar_wait(&bars[1], 0);
+        tc_fence_after();
+        const int row = warp * 32 + lane;
+        const uint32_t dsel = ((reps - 1) & 1) * N % 512;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + dsel + c0, v);
+            tmem_ld_wait();
+            for (int j = 0; j < 32; ++j) out[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) tmem_free(tmem, 512);
+}
+
+static void fill_rows(std::vector<float>& x, int rows, unsigned seed, bool unit) {
+    srand(seed);
+    x.resize((size_t)rows * 64);
+    for (int r = 0; r < rows; ++r) {
+        double n = 0;
+        for (int k = 0; k < 64; ++k) {
+            const float v = (float)rand() / RAND_MAX - 0.5f;
+            x[(size_t)r * 64 + k] = v;
+            n += (double)v * v;
+        }
+        if (unit)
+            for (int k = 0; k < 64; ++k) x[(size_t)r * 64 + k] = (float)(x[(size_t)r * 64 + k] / std::sqrt(n));
+    }
+}
+
+template <int N>
+static int run(int terms, int reps, bool check) {
+    std::vector<float> q, t;
+    fill_rows(q, 128, 1, true);
+    fill_rows(t, N, 2, true);
+    // make a few near-duplicates so small distances are exercised
+    for (int k = 0; k < 64; ++k) t[(size_t)3 * 64 + k] = q[(size_t)5 * 64 + k];
+    for (int k = 0; k < 64; ++k) t[(size_t)7 * 64 + k] = q[(size_t)9 * 64 + k] * (1.f + 1e-3f * (k & 1));
+    std::vector<uint8_t> qm(16 * kTcGroupBytes), tm((N / 8) * kTcGroupBytes);
+    std::vector<uint8_t> qa(2 * 16 * kTcAugGroupBytes), ta(2 * (N / 8) * kTcAugGroupBytes);
+    for (int r = 0; r < 128; ++r)
+        tc_pack_row_host(q.data() + (size_t)r * 64, true, true, qm.data(), qa.data(), qa.data() + 16 * kTcAugGroupBytes, r);
+    for (int r = 0; r < N; ++r)
+        tc_pack_row_host(t.data() + (size_t)r * 64, true, false, tm.data(), ta.data(), ta.data() + (N / 8) * kTcAugGroupBytes, r);
+    uint8_t *dqm, *dtm, *dqa, *dta;
+    float* dout;
+    long long* dcyc;
+    CK(cudaMalloc(&dqm, qm.size())); CK(cudaMalloc(&dtm, tm.size()));
+    CK(cudaMalloc(&dqa, qa.size())); CK(cudaMalloc(&dta, ta.size()));
+    CK(cudaMalloc(&dout, (size_t)128 * N * 4)); CK(cudaMalloc(&dcyc, 8));
+    CK(cudaMemcpy(dqm, qm.data(), qm.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dtm, tm.data(), tm.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dqa, qa.data(), qa.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dta, ta.data(), ta.size(), cudaMemcpyHostToDevice));
+    const size_t smem = (16 + N / 8) * (kTcGroupBytes + 2 * kTcAugGroupBytes) + 64;
+    CK(cudaFuncSetAttribute(probe_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    probe_kernel<N><<<1, 192, smem>>>(dqm, dqa, dqa + 16 * kTcAugGroupBytes, dtm, dta, dta + (N / 8) * kTcAugGroupBytes, dout,
+                                     terms, reps, dcyc);
+    CK(cudaDeviceSynchronize());
+    long long cyc = 0;
+    CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
+    std::vector<float> out((size_t)128 * N);
+    CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
+    int bad = 0;
+    double maxerr = 0;
+    if (check) {
+        for (int r = 0; r < 128; ++r)
+            for (int c = 0; c < N; ++c) {
+                double d2 = 0;
+                for (int k = 0; k < 64; ++k) {
+                    const double df = (double)q[(size_t)r * 64 + k] - (double)t[(size_t)c * 64 + k];
+                    d2 += df * df;
+                }
+                const double want = -0.5 * d2, got = out[(size_t)r * N + c];
+                const double err = std::fabs(want - got);
+                if (err > maxerr) maxerr = err;
+                if (err > (terms == 3 ? 2e-5 : 2e-3)) {
+                    if (bad < 8) printf("  mismatch r=%d c=%d want %.8f got %.8f\n", r, c, want, got);
+                    ++bad;
+                }
+            }
+    }
+    const int mmas = reps * terms * 9;
+    printf("N=%3d terms=%d reps=%4d: %lld cycles, %.1f cycles/MMA (floor %d)%s max|err|=%.3g bad=%d\n", N, terms, reps, cyc,
+           (double)cyc / mmas, N / 2, check ? "" : " [timing only]", maxerr, bad);
+    cudaFree(dqm); cudaFree(dtm); cudaFree(dqa); cudaFree(dta); cudaFree(dout); cudaFree(dcyc);
+    return bad;
+}
+
+int main() {
+    int bad = 0;
+    bad += run<64>(1, 1, true);
+    bad += run<64>(3, 1, true);
+    bad += run<128>(3, 1, true);
+    bad += run<256>(3, 1, true);
+    run<64>(3, 200, false);
+    run<128>(3, 200, false);
+    run<256>(3, 100, false);
+    printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
+    return bad ? 1 : 0;
+}

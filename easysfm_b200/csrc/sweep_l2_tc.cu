@@ -1,0 +1,322 @@
+// sweep_l2_tc.cu -- SURF / L2 distance sweep on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Same contract as sweep_l2.cu (the FP32-FFMA engine): for every image pair, the two best train rows of every
+// query row and the best query row of every train row, as packed (1/2 d^2 bits << 32 | index) keys, ranked with
+// OpenCV's lowest-index tie-break (BFMatcher(NORM_L2).knnMatch(k=2), python_code/feature_match.py:33-34, and the
+// crossCheck of :26-27; C++ call site cpp_code/src/feature_matching.cpp:125).  finalize.cu then re-evaluates the
+// candidates in direct form, so what this kernel must get right is the RANKING; its arithmetic is the 3xTF32 split
+// product of tc_layout.cuh (|error| ~ 2e-6 on 1/2 d^2, measured by csrc/microbench/tc_probe.cu).
+//
+// One persistent CTA per SM, 10 warps, three pipelines (TMA -> shared memory -> tensor memory -> registers):
+//   warp 8 (one lane)  TMA producer: 128-row operand images (main 64 KB + augmented hi/lo 2 x 4 KB) with cp.async.bulk;
+//                      the query tile once per query block, train tiles through a 2-stage full/empty mbarrier ring;
+//                      the 128 running column thresholds of a train tile ride along with it.
+//   warp 9 (one lane)  MMA issuer: per train tile 27 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8):
+//                      8 k-steps over SWIZZLE_128B atoms + 1 augmented k-step (the norms), for hi.hi, hi.lo, lo.hi,
+//                      accumulating -1/2 d^2 in one of 4 tensor-memory stages (128 columns each);
+//                      tcgen05.commit releases the shared-memory stage and publishes the accumulator stage.
+//   warps 0-7          epilogue: warp w owns TMEM lanes 32*(w%4).. (= query rows) and column half w/4.  tcgen05.ld
+//                      gives each THREAD one query row x 64 train columns, so the row's running top-2 is thread-private
+//                      (no shuffles); column minima go through a warp REDUX + one fire-and-forget atomicMin per hit.
+//                      The accumulator stage is released as soon as it is in registers.
+#include "tc_layout.cuh"
+
+namespace esfm {
+
+namespace {
+
+constexpr int kTcThreads = 320;
+constexpr int kTcEpiWarps = 8;
+constexpr int kTcStages = 2;                 // shared-memory train stages
+constexpr int kTcAccStages = 4;              // tensor-memory accumulator stages (128 columns each)
+constexpr int kTcMainBytes = 16 * kTcGroupBytes;       // 65536: main image of a 128-row tile
+constexpr int kTcAugBytes = 16 * kTcAugGroupBytes;     // 4096: one (role, part) augmented image of a tile
+constexpr int kTcTileBytes = kTcMainBytes + 2 * kTcAugBytes;   // 73728 bytes per operand tile in shared memory
+constexpr int kTcThrBytes = kTile * 4;                  // 512: column thresholds riding with a train tile
+constexpr int kTcStageBytes = kTcTileBytes + kTcThrBytes;
+constexpr uint32_t kTcBoundBits = 0x6f6f6f6fu;          // 7.4e28f: "no bound yet" (what memset(0x6f) writes); pads are 1e30
+
+struct TcUnit {
+    int pair, q_frame, t_frame;
+    int nqt, ntt;
+    int qb0, qb1;
+};
+
+__device__ __forceinline__ TcUnit tc_decode_unit(const SweepParams& p, int unit) {
+    TcUnit u;
+    u.pair = unit / p.units_per_pair;
+    const int part = unit - u.pair * p.units_per_pair;
+    const PairDesc pd = p.pairs[u.pair];
+    u.q_frame = pd.q_frame;
+    u.t_frame = pd.t_frame;
+    u.nqt = p.frame_tile_off[pd.q_frame + 1] - p.frame_tile_off[pd.q_frame];
+    u.ntt = p.frame_tile_off[pd.t_frame + 1] - p.frame_tile_off[pd.t_frame];
+    u.qb0 = (int)((long long)u.nqt * part / p.units_per_pair);
+    u.qb1 = (int)((long long)u.nqt * (part + 1) / p.units_per_pair);
+    if (p.frame_rows[pd.t_frame] < 1) u.qb1 = u.qb0;
+    return u;
+}
+
+struct RowTop2 {
+    float v1, v2;        // 1/2 d^2 of the best / second best so far
+    uint32_t i1, i2;
+};
+
+__device__ __forceinline__ void epi_arrive(uint64_t* bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B atoms need 1024-byte alignment
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* Qs = base;                                   // query tile image
+    unsigned char* Ts = Qs + kTcTileBytes;                      // kTcStages train tile images (each 72 x 1024 B: atoms stay aligned)
+    unsigned char* Thr = Ts + kTcStages * kTcTileBytes;         // kTcStages x 128 column thresholds
+    float4* merge = reinterpret_cast<float4*>(Thr + kTcStages * kTcThrBytes);   // [128] second-half row candidates
+    uint64_t* bars = reinterpret_cast<uint64_t*>(merge + kTile);
+    uint64_t* fullQ = bars;
+    uint64_t* emptyQ = bars + 1;
+    uint64_t* fullT = bars + 2;
+    uint64_t* emptyT = fullT + kTcStages;
+    uint64_t* accFull = emptyT + kTcStages;
+    uint64_t* accEmpty = accFull + kTcAccStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accEmpty + kTcAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_units = p.n_pairs * p.units_per_pair;
+
+    if (threadIdx.x == 0) {
+        mbar_init(fullQ, 1);
+        mbar_init(emptyQ, 1);
+        for (int s = 0; s < kTcStages; ++s) {
+            mbar_init(&fullT[s], 1);
+            mbar_init(&emptyT[s], 1 + kTcEpiWarps);   // MMA commit + every epilogue warp (threshold snapshot read)
+        }
+        for (int s = 0; s < kTcAccStages; ++s) {
+            mbar_init(&accFull[s], 1);
+            mbar_init(&accEmpty[s], kTcEpiWarps);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        // ======================= TMA producer =======================
+        if (lane == 0) {
+            const size_t aug_part = (size_t)p.tc_groups * kTcAugGroupBytes;   // bytes of one (role, part) augmented array
+            uint32_t g = 0, qseq = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+                const TcUnit u = tc_decode_unit(p, unit);
+                const size_t qg0 = (size_t)p.frame_tile_off[u.q_frame] * 16, tg0 = (size_t)p.frame_tile_off[u.t_frame] * 16;
+                const uint32_t* tauc = p.col_thr + (size_t)u.pair * p.stride;
+                for (int qb = u.qb0; qb < u.qb1; ++qb) {
+                    mbar_wait_backoff(emptyQ, (qseq & 1) ^ 1);
+                    mbar_arrive_expect_tx(fullQ, kTcTileBytes);
+                    const size_t qg = qg0 + (size_t)qb * 16;
+                    bulk_g2s(Qs, p.tc_main + qg * kTcGroupBytes, kTcMainBytes, fullQ);
+                    bulk_g2s(Qs + kTcMainBytes, p.tc_aug + 0 * aug_part + qg * kTcAugGroupBytes, kTcAugBytes, fullQ);
+                    bulk_g2s(Qs + kTcMainBytes + kTcAugBytes, p.tc_aug + 1 * aug_part + qg * kTcAugGroupBytes, kTcAugBytes, fullQ);
+                    ++qseq;
+                    for (int tt = 0; tt < u.ntt; ++tt, ++g) {
+                        const uint32_t st = g % kTcStages, ph = (g / kTcStages) & 1;
+                        mbar_wait_backoff(&emptyT[st], ph ^ 1);
+                        mbar_arrive_expect_tx(&fullT[st], kTcStageBytes);
+                        unsigned char* dst = Ts + (size_t)st * kTcTileBytes;
+                        const size_t tg = tg0 + (size_t)tt * 16;
+                        bulk_g2s(dst, p.tc_main + tg * kTcGroupBytes, kTcMainBytes, &fullT[st]);
+                        bulk_g2s(dst + kTcMainBytes, p.tc_aug + 2 * aug_part + tg * kTcAugGroupBytes, kTcAugBytes, &fullT[st]);
+                        bulk_g2s(dst + kTcMainBytes + kTcAugBytes, p.tc_aug + 3 * aug_part + tg * kTcAugGroupBytes, kTcAugBytes, &fullT[st]);
+                        bulk_g2s(Thr + st * kTcThrBytes, tauc + (size_t)tt * kTile, kTcThrBytes, &fullT[st]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc_tf32(128, 128);
+            const uint32_t qm = smem_u32(Qs), qa = qm + kTcMainBytes;
+            uint32_t g = 0, qseq = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+                const TcUnit u = tc_decode_unit(p, unit);
+                for (int qb = u.qb0; qb < u.qb1; ++qb) {
+                    mbar_wait(fullQ, qseq & 1);
+                    ++qseq;
+                    for (int tt = 0; tt < u.ntt; ++tt, ++g) {
+                        const uint32_t st = g % kTcStages, ph = (g / kTcStages) & 1;
+                        const uint32_t as = g % kTcAccStages, aph = (g / kTcAccStages) & 1;
+                        mbar_wait(&fullT[st], ph);
+                        mbar_wait(&accEmpty[as], aph ^ 1);
+                        tc_fence_after();
+                        const uint32_t tm = smem_u32(Ts + (size_t)st * kTcTileBytes), ta = tm + kTcMainBytes;
+                        const uint32_t d = tmem + as * 128;
+                        bool first = true;
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {
+                            // (A part, B part): lo.hi, hi.lo first (small terms), hi.hi last
+                            const int pa = term == 0 ? 1 : 0, pb = term == 1 ? 1 : 0;
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks) {
+                                const uint32_t off = (ks >> 2) * 1024 + (ks & 3) * 32;
+                                tc_mma_tf32(d, tc_desc_sw128(qm + pa * 2048 + off, kTcGroupBytes),
+                                            tc_desc_sw128(tm + pb * 2048 + off, kTcGroupBytes), idesc, !first);
+                                first = false;
+                            }
+                            tc_mma_tf32(d, tc_desc_nosw(qa + pa * kTcAugBytes, 128, kTcAugGroupBytes),
+                                        tc_desc_nosw(ta + pb * kTcAugBytes, 128, kTcAugGroupBytes), idesc, true);
+                        }
+                        tc_commit(&emptyT[st]);     // shared-memory stage consumed once these MMAs retire
+                        tc_commit(&accFull[as]);    // accumulator stage ready for the epilogue
+                    }
+                    tc_commit(emptyQ);
+                }
+            }
+        }
+    } else {
+        // ======================= epilogue warps =======================
+        const int quarter = warp & 3, half = warp >> 2;
+        const int trow = quarter * 32 + lane;               // row inside the 128-row query tile (= TMEM lane)
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        uint32_t g = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const TcUnit u = tc_decode_unit(p, unit);
+            u64* rk1 = p.keys + (size_t)u.pair * 4 * p.stride;
+            u64* rk2 = rk1 + p.stride;
+            u64* ck1 = rk2 + p.stride;
+            uint32_t* tauc = p.col_thr + (size_t)u.pair * p.stride;
+            for (int qb = u.qb0; qb < u.qb1; ++qb) {
+                const uint32_t qrow = (uint32_t)(qb * kTile + trow);     // frame row of this thread
+                RowTop2 t;
+                t.v1 = t.v2 = __uint_as_float(kTcBoundBits);
+                t.i1 = t.i2 = 0xffffffffu;
+                for (int tt = 0; tt < u.ntt; ++tt, ++g) {
+                    const uint32_t st = g % kTcStages, ph = (g / kTcStages) & 1;
+                    const uint32_t as = g % kTcAccStages, aph = (g / kTcAccStages) & 1;
+                    // ---- column thresholds of this tile half (snapshot that arrived with the tile) ----
+                    mbar_wait(&fullT[st], ph);
+                    float thr[64];
+                    {
+                        const float4* tp = reinterpret_cast<const float4*>(Thr + st * kTcThrBytes) + half * 16;
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) {
+                            const float4 x = tp[m];
+                            thr[4 * m] = x.x; thr[4 * m + 1] = x.y; thr[4 * m + 2] = x.z; thr[4 * m + 3] = x.w;
+                        }
+                    }
+                    epi_arrive(&emptyT[st], lane);
+                    // ---- accumulators: this thread's row x 64 columns ----
+                    mbar_wait(&accFull[as], aph);
+                    tc_fence_after();
+                    uint32_t vb[2][32];
+                    const uint32_t taddr = tmem + lane_addr + as * 128 + half * 64;
+                    tmem_ld32(taddr, vb[0]);
+                    tmem_ld32(taddr + 32, vb[1]);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    epi_arrive(&accEmpty[as], lane);
+                    float v[64];
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) v[c] = __uint_as_float(vb[c >> 5][c & 31]);   // v = -1/2 d^2
+
+                    const uint32_t col0 = (uint32_t)(tt * kTile + half * 64);
+#pragma unroll
+                    for (int gq = 0; gq < 8; ++gq) {
+                        // ---- row side: anything in these 8 columns better than the row's second best? ----
+                        float gm = fmaxf(fmaxf(v[8 * gq], v[8 * gq + 1]), v[8 * gq + 2]);
+                        gm = fmaxf(fmaxf(gm, v[8 * gq + 3]), v[8 * gq + 4]);
+                        gm = fmaxf(fmaxf(gm, v[8 * gq + 5]), v[8 * gq + 6]);
+                        gm = fmaxf(gm, v[8 * gq + 7]);
+                        if (gm > -t.v2) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float d = -v[8 * gq + j];
+                                if (d < t.v2) {     // ascending column order + strict '<' keeps the lowest index on ties
+                                    const uint32_t idx = col0 + 8 * gq + j;
+                                    if (d < t.v1) {
+                                        t.v2 = t.v1; t.i2 = t.i1;
+                                        t.v1 = d;    t.i1 = idx;
+                                    } else {
+                                        t.v2 = d;    t.i2 = idx;
+                                    }
+                                }
+                            }
+                        }
+                        // ---- column side: does any row of this warp beat a column's running best? ----
+                        bool any = false;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) any |= (v[8 * gq + j] >= -thr[8 * gq + j]);
+                        if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const bool hit = v[8 * gq + j] >= -thr[8 * gq + j];
+                                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                                if (bal) {     // warp-uniform
+                                    const uint32_t bits = hit ? __float_as_uint(fmaxf(-v[8 * gq + j], 0.f)) : 0xffffffffu;
+                                    const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
+                                    const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
+                                    if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
+                                        const uint32_t gcol = col0 + 8 * gq + j;
+                                        atomicMin(ck1 + gcol, make_key(mn, qrow));
+                                        atomicMin(tauc + gcol, mn);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                // ---- end of the sweep for this query block: merge the two column halves of every row, publish ----
+                if (half == 1) merge[trow] = make_float4(t.v1, t.v2, __uint_as_float(t.i1), __uint_as_float(t.i2));
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (half == 0) {
+                    const float4 o = merge[trow];
+                    const float ov1 = o.x, ov2 = o.y;
+                    const uint32_t oi1 = __float_as_uint(o.z), oi2 = __float_as_uint(o.w);
+                    // all indices of half 1 are larger than those of half 0 within a tile, but tiles interleave: order by (value, index)
+                    auto less = [](float va, uint32_t ia, float vb2, uint32_t ib) { return va < vb2 || (va == vb2 && ia < ib); };
+                    RowTop2 r;
+                    if (less(ov1, oi1, t.v1, t.i1)) {
+                        r.v1 = ov1; r.i1 = oi1;
+                        if (less(ov2, oi2, t.v1, t.i1)) { r.v2 = ov2; r.i2 = oi2; } else { r.v2 = t.v1; r.i2 = t.i1; }
+                    } else {
+                        r.v1 = t.v1; r.i1 = t.i1;
+                        if (less(ov1, oi1, t.v2, t.i2)) { r.v2 = ov1; r.i2 = oi1; } else { r.v2 = t.v2; r.i2 = t.i2; }
+                    }
+                    rk1[qrow] = r.i1 == 0xffffffffu ? kKeyInit : make_key(__float_as_uint(fmaxf(r.v1, 0.f)), r.i1);
+                    rk2[qrow] = r.i2 == 0xffffffffu ? kKeyInit : make_key(__float_as_uint(fmaxf(r.v2, 0.f)), r.i2);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // merge[] is reused by the next query block
+            }
+        }
+    }
+
+    // ---- teardown: everything issued has been consumed (the epilogue waited on every accumulator stage) ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_free(tmem, 512);
+}
+
+size_t sweep_l2_tc_smem_bytes() {
+    return 1024 + (size_t)kTcTileBytes + (size_t)kTcStages * kTcStageBytes + kTile * sizeof(float4) +
+           (2 + 2 * kTcStages + 2 * kTcAccStages) * 8 + 16;
+}
+
+cudaError_t launch_sweep_l2_tc(const SweepParams& p, int sm_count, cudaStream_t s) {
+    const int n_units = p.n_pairs * p.units_per_pair;
+    if (n_units <= 0) return cudaSuccess;
+    const int grid = n_units < sm_count ? n_units : sm_count;
+    const size_t smem = sweep_l2_tc_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(sweep_l2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    sweep_l2_tc_kernel<<<grid, kTcThreads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace esfm

@@ -1,0 +1,128 @@
+// tc_layout.cuh -- operand layout and PTX wrappers of the tcgen05 (5th-gen tensor core) L2 sweep.
+//
+// The SURF distance is ranked as  -1/2 d^2 = q.t - 1/2|q|^2 - 1/2|t|^2  by ONE augmented inner product
+//     q' = (q_0..q_63,  1,     hq, 0 x 6)        hq = 1/2|q|^2
+//     t' = (t_0..t_63, -ht,   -1,  0 x 6)        ht = 1/2|t|^2
+// evaluated on the tensor cores as a 3xTF32 split product: every fp32 operand x is stored as
+//     hi = x rounded to TF32 (10 explicit mantissa bits),  lo = x - hi (exact in fp32; the MMA reads its top 19 bits)
+// and  q'.t' ~= hi.hi + hi.lo + lo.hi  accumulates in fp32 in tensor memory (dropped term ~2^-24 |q||t|).
+//
+// HBM / shared-memory image ("TC bank"), per group of 8 consecutive rows of a frame:
+//   main  4096 B : [hi k0..31][hi k32..63][lo k0..31][lo k32..63], each a 1024-byte SWIZZLE_128B K-major atom
+//                  (8 rows x 128 B; 16-byte chunk c of row r stored at chunk c ^ r) -- what tcgen05.mma's shared-memory
+//                  descriptor calls layout_type 2, stride-byte-offset 4096 between 8-row groups;
+//   aug    256 B : per (role in {query, train}) x (part in {hi, lo}), the 8 augmented columns in the no-swizzle
+//                  K-major canonical form [k-chunk 2][row 8][16 B]  (leading-byte-offset 128, stride-byte-offset 256).
+// Frames are padded to 128 rows; pad rows are zero with hq (resp. ht) = 1e30, so every accumulator involving them is
+// <= -1e30 and can never be selected: no index masking in the kernel.
+#pragma once
+#include <cmath>
+#include <cstring>
+
+#include "esfm_internal.cuh"
+
+namespace esfm {
+
+constexpr int kTcGroupBytes = 4096;      // main image of one 8-row group
+constexpr int kTcAugGroupBytes = 256;    // one (role, part) augmented block of one 8-row group
+constexpr float kTcPadNorm = 1e30f;
+
+__host__ __device__ __forceinline__ float tc_tf32_hi(float x) {
+#ifdef __CUDA_ARCH__
+    const uint32_t b = __float_as_uint(x);
+    return __uint_as_float((b + 0x1000u) & 0xffffe000u);
+#else
+    uint32_t b;
+    memcpy(&b, &x, 4);
+    b = (b + 0x1000u) & 0xffffe000u;
+    float r;
+    memcpy(&r, &b, 4);
+    return r;
+#endif
+}
+
+// byte offset of element (row rr in [0,8), k in [0,32)) inside one 1024-byte SWIZZLE_128B atom
+__host__ __device__ __forceinline__ int tc_sw128_off(int rr, int k) { return rr * 128 + ((((k >> 2) ^ rr) & 7) << 4) + ((k & 3) << 2); }
+
+// byte offset of augmented column j in [0,8) of row rr inside one 256-byte no-swizzle block
+__host__ __device__ __forceinline__ int tc_aug_off(int rr, int j) { return (j >> 2) * 128 + rr * 16 + ((j & 3) << 2); }
+
+// Host reference of the packing (used by the probe and by the CPU tests of the layout); the device pack kernel in
+// bank.cu computes exactly the same bytes.  `main` / `aug_hi` / `aug_lo` point at group 0 of the destination arrays.
+inline void tc_pack_row_host(const float* x, bool valid, bool query_role, uint8_t* main, uint8_t* aug_hi, uint8_t* aug_lo, int r) {
+    const int g = r >> 3, rr = r & 7;
+    float s = 0.f;
+    for (int k = 0; k < kDim; ++k) s = fmaf(x[k], x[k], s);
+    const float h = valid ? 0.5f * s : kTcPadNorm;
+    for (int k = 0; k < kDim; ++k) {
+        const float v = valid ? x[k] : 0.f;
+        const float hi = tc_tf32_hi(v), lo = v - hi;
+        const int off = g * kTcGroupBytes + (k >> 5) * 1024 + tc_sw128_off(rr, k & 31);
+        memcpy(main + off, &hi, 4);
+        memcpy(main + off + 2048, &lo, 4);
+    }
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (query_role) { a[0] = 1.f; a[1] = h; } else { a[0] = -h; a[1] = -1.f; }
+    for (int j = 0; j < 8; ++j) {
+        const float hi = tc_tf32_hi(a[j]), lo = a[j] - hi;
+        const int off = g * kTcAugGroupBytes + tc_aug_off(rr, j);
+        memcpy(aug_hi + off, &hi, 4);
+        memcpy(aug_lo + off, &lo, 4);
+    }
+}
+
+#ifdef __CUDACC__
+// ---- shared-memory matrix descriptors (tcgen05.mma operand A / B), K-major ---------------------------------------
+// bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
+// [46,48) descriptor version (1 on sm_100), [61,64) layout type (0 = no swizzle, 2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t tc_desc_sw128(uint32_t saddr, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t tc_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::tf32: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__host__ __device__ constexpr uint32_t tc_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread complete -> one arrival on the mbarrier (implies fence::before_thread_sync)
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// tensor-memory allocation: executed by ONE full warp; the base address lands in shared memory
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives lane (base lane + i), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+#endif  // __CUDACC__
+
+}  // namespace esfm

@@ -103,6 +103,17 @@ int esfm_set_profiling(esfm_ctx_t* ctx, int enabled);
 /* Number of SMs of the bound device (grid sizing is a multiple of this). */
 int esfm_device_sm_count(esfm_ctx_t* ctx, int* sms);
 
+/* Which kernel serves ESFM_KIND_F32X64 sweeps.  Both produce the same candidates for finalize's direct-form
+ * re-evaluation (the reference's arithmetic, BFMatcher(NORM_L2): feature_match.py:33-34); they differ in how the
+ * RANKING distance is computed:
+ *   ESFM_L2_ENGINE_FFMA  exact-FP32 FFMA expansion  1/2|q|^2 + 1/2|t|^2 - q.t  on the FP32 pipe;
+ *   ESFM_L2_ENGINE_TC    the same quantity as a 3xTF32 split product on the tcgen05 tensor cores.
+ * Default: $ESFM_L2_ENGINE ("ffma" | "tc") at esfm_init, else the library default. */
+#define ESFM_L2_ENGINE_FFMA 0
+#define ESFM_L2_ENGINE_TC 1
+int esfm_set_l2_engine(esfm_ctx_t* ctx, int engine);
+int esfm_get_l2_engine(esfm_ctx_t* ctx, int* engine);
+
 /* ---- descriptor bank (replaces the per-call cv::Mat arguments; utility.h:31) ---------------- */
 
 int esfm_bank_create(esfm_ctx_t* ctx, esfm_kind kind, int n_frames, esfm_bank_t** bank);
