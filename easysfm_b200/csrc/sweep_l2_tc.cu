@@ -33,7 +33,7 @@ constexpr int kTcMainBytes = 16 * kTcGroupBytes;       // 65536: main image of a
 constexpr int kTcAugBytes = 16 * kTcAugGroupBytes;     // 4096: one (role, part) augmented image of a tile
 constexpr int kTcTileBytes = kTcMainBytes + 2 * kTcAugBytes;   // 73728 bytes per operand tile in shared memory
 constexpr int kTcThrBytes = kTile * 4;                  // 512: column thresholds riding with a train tile
-constexpr int kTcStageBytes = kTcTileBytes + kTcThrBytes;
+constexpr int kTcThrStages = 4;                         // threshold snapshots have their own (deeper) ring
 constexpr uint32_t kTcBoundBits = 0x6f6f6f6fu;          // 7.4e28f: "no bound yet" (what memset(0x6f) writes); pads are 1e30
 
 struct TcUnit {
@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* Qs = base;                                   // query tile image
     unsigned char* Ts = Qs + kTcTileBytes;                      // kTcStages train tile images (each 72 x 1024 B: atoms stay aligned)
-    unsigned char* Thr = Ts + kTcStages * kTcTileBytes;         // kTcStages x 128 column thresholds
-    float4* merge = reinterpret_cast<float4*>(Thr + kTcStages * kTcThrBytes);   // [128] second-half row candidates
+    unsigned char* Thr = Ts + kTcStages * kTcTileBytes;         // kTcThrStages x 128 column thresholds
+    float4* merge = reinterpret_cast<float4*>(Thr + kTcThrStages * kTcThrBytes);   // [128] second-half row candidates
     uint64_t* bars = reinterpret_cast<uint64_t*>(merge + kTile);
     uint64_t* fullQ = bars;
     uint64_t* emptyQ = bars + 1;
@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     uint64_t* emptyT = fullT + kTcStages;
     uint64_t* accFull = emptyT + kTcStages;
     uint64_t* accEmpty = accFull + kTcAccStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accEmpty + kTcAccStages);
+    uint64_t* thrFull = accEmpty + kTcAccStages;
+    uint64_t* thrEmpty = thrFull + kTcThrStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(thrEmpty + kTcThrStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_units = p.n_pairs * p.units_per_pair;
@@ -94,7 +96,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
         mbar_init(emptyQ, 1);
         for (int s = 0; s < kTcStages; ++s) {
             mbar_init(&fullT[s], 1);
-            mbar_init(&emptyT[s], 1 + kTcEpiWarps);   // MMA commit + every epilogue warp (threshold snapshot read)
+            mbar_init(&emptyT[s], 1);                 // MMA commit
+        }
+        for (int s = 0; s < kTcThrStages; ++s) {
+            mbar_init(&thrFull[s], 1);
+            mbar_init(&thrEmpty[s], kTcEpiWarps);
         }
         for (int s = 0; s < kTcAccStages; ++s) {
             mbar_init(&accFull[s], 1);
@@ -128,13 +134,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                     for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                         const uint32_t st = g % kTcStages, ph = (g / kTcStages) & 1;
                         mbar_wait_backoff(&emptyT[st], ph ^ 1);
-                        mbar_arrive_expect_tx(&fullT[st], kTcStageBytes);
+                        mbar_arrive_expect_tx(&fullT[st], kTcTileBytes);
                         unsigned char* dst = Ts + (size_t)st * kTcTileBytes;
                         const size_t tg = tg0 + (size_t)tt * 16;
                         bulk_g2s(dst, p.tc_main + tg * kTcGroupBytes, kTcMainBytes, &fullT[st]);
                         bulk_g2s(dst + kTcMainBytes, p.tc_aug + 2 * aug_part + tg * kTcAugGroupBytes, kTcAugBytes, &fullT[st]);
                         bulk_g2s(dst + kTcMainBytes + kTcAugBytes, p.tc_aug + 3 * aug_part + tg * kTcAugGroupBytes, kTcAugBytes, &fullT[st]);
-                        bulk_g2s(Thr + st * kTcThrBytes, tauc + (size_t)tt * kTile, kTcThrBytes, &fullT[st]);
+                        // the running column thresholds of this tile ride along in their own ring (a snapshot a few tiles
+                        // old is fine: a stale threshold is only looser, never wrong)
+                        const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
+                        mbar_wait_backoff(&thrEmpty[ts], tph ^ 1);
+                        mbar_arrive_expect_tx(&thrFull[ts], kTcThrBytes);
+                        bulk_g2s(Thr + ts * kTcThrBytes, tauc + (size_t)tt * kTile, kTcThrBytes, &thrFull[ts]);
                     }
                 }
             }
@@ -198,74 +209,75 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                 t.v1 = t.v2 = __uint_as_float(kTcBoundBits);
                 t.i1 = t.i2 = 0xffffffffu;
                 for (int tt = 0; tt < u.ntt; ++tt, ++g) {
-                    const uint32_t st = g % kTcStages, ph = (g / kTcStages) & 1;
                     const uint32_t as = g % kTcAccStages, aph = (g / kTcAccStages) & 1;
-                    // ---- column thresholds of this tile half (snapshot that arrived with the tile) ----
-                    mbar_wait(&fullT[st], ph);
-                    float thr[64];
-                    {
-                        const float4* tp = reinterpret_cast<const float4*>(Thr + st * kTcThrBytes) + half * 16;
-#pragma unroll
-                        for (int m = 0; m < 16; ++m) {
-                            const float4 x = tp[m];
-                            thr[4 * m] = x.x; thr[4 * m + 1] = x.y; thr[4 * m + 2] = x.z; thr[4 * m + 3] = x.w;
-                        }
-                    }
-                    epi_arrive(&emptyT[st], lane);
-                    // ---- accumulators: this thread's row x 64 columns ----
+                    const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
+                    mbar_wait(&thrFull[ts], tph);
                     mbar_wait(&accFull[as], aph);
                     tc_fence_after();
-                    uint32_t vb[2][32];
+                    const float4* tp = reinterpret_cast<const float4*>(Thr + ts * kTcThrBytes) + half * 16;
                     const uint32_t taddr = tmem + lane_addr + as * 128 + half * 64;
-                    tmem_ld32(taddr, vb[0]);
-                    tmem_ld32(taddr + 32, vb[1]);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    epi_arrive(&accEmpty[as], lane);
-                    float v[64];
+                    // 64 columns in 4 chunks of 16: a real loop, so the epilogue body stays small enough for the
+                    // instruction cache (the fully unrolled 64-column body was 64 KB of SASS and stalled on fetch)
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t vb[16];
+                        tmem_ld16(taddr + ch * 16, vb);
+                        float thr[16];
 #pragma unroll
-                    for (int c = 0; c < 64; ++c) v[c] = __uint_as_float(vb[c >> 5][c & 31]);   // v = -1/2 d^2
-
-                    const uint32_t col0 = (uint32_t)(tt * kTile + half * 64);
+                        for (int m = 0; m < 4; ++m) {
+                            const float4 x = tp[ch * 4 + m];
+                            thr[4 * m] = x.x; thr[4 * m + 1] = x.y; thr[4 * m + 2] = x.z; thr[4 * m + 3] = x.w;
+                        }
+                        tmem_ld_wait();
+                        if (ch == 3) {      // everything this warp needs from the two rings is in registers
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) { mbar_arrive(&accEmpty[as]); mbar_arrive(&thrEmpty[ts]); }
+                        }
+                        float v[16];
 #pragma unroll
-                    for (int gq = 0; gq < 8; ++gq) {
-                        // ---- row side: anything in these 8 columns better than the row's second best? ----
-                        float gm = fmaxf(fmaxf(v[8 * gq], v[8 * gq + 1]), v[8 * gq + 2]);
-                        gm = fmaxf(fmaxf(gm, v[8 * gq + 3]), v[8 * gq + 4]);
-                        gm = fmaxf(fmaxf(gm, v[8 * gq + 5]), v[8 * gq + 6]);
-                        gm = fmaxf(gm, v[8 * gq + 7]);
-                        if (gm > -t.v2) {
+                        for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(vb[c]);   // v = -1/2 d^2
+                        const uint32_t col0 = (uint32_t)(tt * kTile + half * 64 + ch * 16);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float d = -v[8 * gq + j];
-                                if (d < t.v2) {     // ascending column order + strict '<' keeps the lowest index on ties
-                                    const uint32_t idx = col0 + 8 * gq + j;
-                                    if (d < t.v1) {
-                                        t.v2 = t.v1; t.i2 = t.i1;
-                                        t.v1 = d;    t.i1 = idx;
-                                    } else {
-                                        t.v2 = d;    t.i2 = idx;
+                        for (int gq = 0; gq < 2; ++gq) {
+                            // ---- row side: anything in these 8 columns better than the row's second best? ----
+                            float gm = fmaxf(fmaxf(v[8 * gq], v[8 * gq + 1]), v[8 * gq + 2]);
+                            gm = fmaxf(fmaxf(gm, v[8 * gq + 3]), v[8 * gq + 4]);
+                            gm = fmaxf(fmaxf(gm, v[8 * gq + 5]), v[8 * gq + 6]);
+                            gm = fmaxf(gm, v[8 * gq + 7]);
+                            if (gm > -t.v2) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float d = -v[8 * gq + j];
+                                    if (d < t.v2) {     // ascending column order + strict '<' keeps the lowest index on ties
+                                        const uint32_t idx = col0 + 8 * gq + j;
+                                        if (d < t.v1) {
+                                            t.v2 = t.v1; t.i2 = t.i1;
+                                            t.v1 = d;    t.i1 = idx;
+                                        } else {
+                                            t.v2 = d;    t.i2 = idx;
+                                        }
                                     }
                                 }
                             }
-                        }
-                        // ---- column side: does any row of this warp beat a column's running best? ----
-                        bool any = false;
+                            // ---- column side: does any row of this warp beat a column's running best? ----
+                            bool any = false;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) any |= (v[8 * gq + j] >= -thr[8 * gq + j]);
-                        if (__any_sync(0xffffffffu, any)) {
+                            for (int j = 0; j < 8; ++j) any |= (v[8 * gq + j] >= -thr[8 * gq + j]);
+                            if (__any_sync(0xffffffffu, any)) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const bool hit = v[8 * gq + j] >= -thr[8 * gq + j];
-                                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-                                if (bal) {     // warp-uniform
-                                    const uint32_t bits = hit ? __float_as_uint(fmaxf(-v[8 * gq + j], 0.f)) : 0xffffffffu;
-                                    const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
-                                    const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
-                                    if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
-                                        const uint32_t gcol = col0 + 8 * gq + j;
-                                        atomicMin(ck1 + gcol, make_key(mn, qrow));
-                                        atomicMin(tauc + gcol, mn);
+                                for (int j = 0; j < 8; ++j) {
+                                    const bool hit = v[8 * gq + j] >= -thr[8 * gq + j];
+                                    const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                                    if (bal) {     // warp-uniform
+                                        const uint32_t bits = hit ? __float_as_uint(fmaxf(-v[8 * gq + j], 0.f)) : 0xffffffffu;
+                                        const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
+                                        const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
+                                        if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
+                                            const uint32_t gcol = col0 + 8 * gq + j;
+                                            atomicMin(ck1 + gcol, make_key(mn, qrow));
+                                            atomicMin(tauc + gcol, mn);
+                                        }
                                     }
                                 }
                             }
@@ -304,8 +316,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
 }
 
 size_t sweep_l2_tc_smem_bytes() {
-    return 1024 + (size_t)kTcTileBytes + (size_t)kTcStages * kTcStageBytes + kTile * sizeof(float4) +
-           (2 + 2 * kTcStages + 2 * kTcAccStages) * 8 + 16;
+    return 1024 + (size_t)kTcTileBytes + (size_t)kTcStages * kTcTileBytes + (size_t)kTcThrStages * kTcThrBytes + kTile * sizeof(float4) +
+           (2 + 2 * kTcStages + 2 * kTcAccStages + 2 * kTcThrStages) * 8 + 16;
 }
 
 cudaError_t launch_sweep_l2_tc(const SweepParams& p, int sm_count, cudaStream_t s) {
