@@ -25,8 +25,11 @@ namespace esfm {
 
 namespace {
 
-constexpr int kTcThreads = 320;
-constexpr int kTcEpiWarps = 8;
+constexpr int kTcColParts = 4;                          // column quarters of a train tile, one per epilogue warp of a lane quarter
+constexpr int kTcEpiWarps = 4 * kTcColParts;            // 16 epilogue warps: enough to hide the epilogue's dependent-issue latency
+constexpr int kTcEpiThreads = kTcEpiWarps * 32;
+constexpr int kTcThreads = kTcEpiThreads + 64;          // + TMA producer warp + MMA issuer warp
+constexpr int kTcPartCols = kTile / kTcColParts;        // 32 columns per epilogue thread and stage
 constexpr int kTcStages = 2;                 // shared-memory train stages
 constexpr int kTcAccStages = 4;              // tensor-memory accumulator stages (128 columns each)
 constexpr int kTcMainBytes = 16 * kTcGroupBytes;       // 65536: main image of a 128-row tile
@@ -76,8 +79,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     unsigned char* Qs = base;                                   // query tile image
     unsigned char* Ts = Qs + kTcTileBytes;                      // kTcStages train tile images (each 72 x 1024 B: atoms stay aligned)
     unsigned char* Thr = Ts + kTcStages * kTcTileBytes;         // kTcThrStages x 128 column thresholds
-    float4* merge = reinterpret_cast<float4*>(Thr + kTcThrStages * kTcThrBytes);   // [128] second-half row candidates
-    uint64_t* bars = reinterpret_cast<uint64_t*>(merge + kTile);
+    float4* merge = reinterpret_cast<float4*>(Thr + kTcThrStages * kTcThrBytes);   // [parts-1][128] row candidates of parts 1..
+    uint32_t* sbound = reinterpret_cast<uint32_t*>(merge + (kTcColParts - 1) * kTile);  // [128] row bound shared by a row's parts
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sbound + kTile);
     uint64_t* fullQ = bars;
     uint64_t* emptyQ = bars + 1;
     uint64_t* fullT = bars + 2;
@@ -108,13 +112,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
         }
         fence_mbar_init();
     }
-    if (warp == 9) tmem_alloc(tmem_slot, 512);
+    if (warp == kTcEpiWarps + 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == kTcEpiWarps) {
         // ======================= TMA producer =======================
         if (lane == 0) {
             const size_t aug_part = (size_t)p.tc_groups * kTcAugGroupBytes;   // bytes of one (role, part) augmented array
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kTcEpiWarps + 1) {
         // ======================= MMA issuer =======================
         if (lane == 0) {
             constexpr uint32_t idesc = tc_idesc_tf32(128, 128);
@@ -193,9 +197,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
         }
     } else {
         // ======================= epilogue warps =======================
-        const int quarter = warp & 3, half = warp >> 2;
+        const int quarter = warp & 3, part = warp >> 2;
         const int trow = quarter * 32 + lane;               // row inside the 128-row query tile (= TMEM lane)
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        auto less = [](float va, uint32_t ia, float vb2, uint32_t ib) { return va < vb2 || (va == vb2 && ia < ib); };
+        if (part == 0) sbound[trow] = kTcBoundBits;
+        asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");
         uint32_t g = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const TcUnit u = tc_decode_unit(p, unit);
@@ -214,12 +221,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                     mbar_wait(&thrFull[ts], tph);
                     mbar_wait(&accFull[as], aph);
                     tc_fence_after();
-                    const float4* tp = reinterpret_cast<const float4*>(Thr + ts * kTcThrBytes) + half * 16;
-                    const uint32_t taddr = tmem + lane_addr + as * 128 + half * 64;
-                    // 64 columns in 4 chunks of 16: a real loop, so the epilogue body stays small enough for the
-                    // instruction cache (the fully unrolled 64-column body was 64 KB of SASS and stalled on fetch)
+                    const float4* tp = reinterpret_cast<const float4*>(Thr + ts * kTcThrBytes) + part * (kTcPartCols / 4);
+                    const uint32_t taddr = tmem + lane_addr + as * 128 + part * kTcPartCols;
+                    // The row's running second best over ALL column parts (each part keeps a private top-2; the shared
+                    // bound only filters, with '>=' so equal values still reach the private strict-'<' insertion).
+                    const float nb = -__uint_as_float(*reinterpret_cast<volatile uint32_t*>(&sbound[trow]));
+                    // columns in chunks of 16: a real loop, so the epilogue body stays small enough for the instruction
+                    // cache (a fully unrolled 64-column body was 64 KB of SASS and stalled on instruction fetch)
 #pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
+                    for (int ch = 0; ch < kTcPartCols / 16; ++ch) {
                         uint32_t vb[16];
                         tmem_ld16(taddr + ch * 16, vb);
                         float thr[16];
@@ -229,7 +239,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                             thr[4 * m] = x.x; thr[4 * m + 1] = x.y; thr[4 * m + 2] = x.z; thr[4 * m + 3] = x.w;
                         }
                         tmem_ld_wait();
-                        if (ch == 3) {      // everything this warp needs from the two rings is in registers
+                        if (ch == kTcPartCols / 16 - 1) {      // everything this warp needs from the two rings is in registers
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) { mbar_arrive(&accEmpty[as]); mbar_arrive(&thrEmpty[ts]); }
@@ -237,30 +247,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                         float v[16];
 #pragma unroll
                         for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(vb[c]);   // v = -1/2 d^2
-                        const uint32_t col0 = (uint32_t)(tt * kTile + half * 64 + ch * 16);
+                        const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols + ch * 16);
+                        // ---- row side, 4 columns at a time: anything at least as good as the row's second best? ----
 #pragma unroll
-                        for (int gq = 0; gq < 2; ++gq) {
-                            // ---- row side: anything in these 8 columns better than the row's second best? ----
-                            float gm = fmaxf(fmaxf(v[8 * gq], v[8 * gq + 1]), v[8 * gq + 2]);
-                            gm = fmaxf(fmaxf(gm, v[8 * gq + 3]), v[8 * gq + 4]);
-                            gm = fmaxf(fmaxf(gm, v[8 * gq + 5]), v[8 * gq + 6]);
-                            gm = fmaxf(gm, v[8 * gq + 7]);
-                            if (gm > -t.v2) {
+                        for (int gq = 0; gq < 4; ++gq) {
+                            const float gm = fmaxf(fmaxf(fmaxf(v[4 * gq], v[4 * gq + 1]), v[4 * gq + 2]), v[4 * gq + 3]);
+                            if (gm >= nb) {
+                                bool ins = false;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float d = -v[8 * gq + j];
+                                for (int j = 0; j < 4; ++j) {
+                                    const float d = -v[4 * gq + j];
                                     if (d < t.v2) {     // ascending column order + strict '<' keeps the lowest index on ties
-                                        const uint32_t idx = col0 + 8 * gq + j;
+                                        const uint32_t idx = col0 + 4 * gq + j;
                                         if (d < t.v1) {
                                             t.v2 = t.v1; t.i2 = t.i1;
                                             t.v1 = d;    t.i1 = idx;
                                         } else {
                                             t.v2 = d;    t.i2 = idx;
                                         }
+                                        ins = true;
                                     }
                                 }
+                                if (ins) atomicMin(&sbound[trow], __float_as_uint(fmaxf(t.v2, 0.f)));
                             }
-                            // ---- column side: does any row of this warp beat a column's running best? ----
+                        }
+                        // ---- column side, 8 columns at a time: does any row of this warp beat a column's running best? ----
+#pragma unroll
+                        for (int gq = 0; gq < 2; ++gq) {
                             bool any = false;
 #pragma unroll
                             for (int j = 0; j < 8; ++j) any |= (v[8 * gq + j] >= -thr[8 * gq + j]);
@@ -284,27 +297,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                         }
                     }
                 }
-                // ---- end of the sweep for this query block: merge the two column halves of every row, publish ----
-                if (half == 1) merge[trow] = make_float4(t.v1, t.v2, __uint_as_float(t.i1), __uint_as_float(t.i2));
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (half == 0) {
-                    const float4 o = merge[trow];
-                    const float ov1 = o.x, ov2 = o.y;
-                    const uint32_t oi1 = __float_as_uint(o.z), oi2 = __float_as_uint(o.w);
-                    // all indices of half 1 are larger than those of half 0 within a tile, but tiles interleave: order by (value, index)
-                    auto less = [](float va, uint32_t ia, float vb2, uint32_t ib) { return va < vb2 || (va == vb2 && ia < ib); };
-                    RowTop2 r;
-                    if (less(ov1, oi1, t.v1, t.i1)) {
-                        r.v1 = ov1; r.i1 = oi1;
-                        if (less(ov2, oi2, t.v1, t.i1)) { r.v2 = ov2; r.i2 = oi2; } else { r.v2 = t.v1; r.i2 = t.i1; }
-                    } else {
-                        r.v1 = t.v1; r.i1 = t.i1;
-                        if (less(ov1, oi1, t.v2, t.i2)) { r.v2 = ov1; r.i2 = oi1; } else { r.v2 = t.v2; r.i2 = t.i2; }
+                // ---- end of the sweep for this query block: merge the column parts of every row, publish ----
+                if (part > 0) merge[(part - 1) * kTile + trow] = make_float4(t.v1, t.v2, __uint_as_float(t.i1), __uint_as_float(t.i2));
+                asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");
+                if (part == 0) {
+#pragma unroll
+                    for (int o = 0; o < kTcColParts - 1; ++o) {
+                        const float4 m4 = merge[o * kTile + trow];
+                        const float ov[2] = {m4.x, m4.y};
+                        const uint32_t oi[2] = {__float_as_uint(m4.z), __float_as_uint(m4.w)};
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {      // insert by (value, index): the parts hold disjoint column sets
+                            if (oi[e] != 0xffffffffu && less(ov[e], oi[e], t.v2, t.i2)) {
+                                if (less(ov[e], oi[e], t.v1, t.i1)) {
+                                    t.v2 = t.v1; t.i2 = t.i1;
+                                    t.v1 = ov[e]; t.i1 = oi[e];
+                                } else {
+                                    t.v2 = ov[e]; t.i2 = oi[e];
+                                }
+                            }
+                        }
                     }
-                    rk1[qrow] = r.i1 == 0xffffffffu ? kKeyInit : make_key(__float_as_uint(fmaxf(r.v1, 0.f)), r.i1);
-                    rk2[qrow] = r.i2 == 0xffffffffu ? kKeyInit : make_key(__float_as_uint(fmaxf(r.v2, 0.f)), r.i2);
+                    rk1[qrow] = t.i1 == 0xffffffffu ? kKeyInit : make_key(__float_as_uint(fmaxf(t.v1, 0.f)), t.i1);
+                    rk2[qrow] = t.i2 == 0xffffffffu ? kKeyInit : make_key(__float_as_uint(fmaxf(t.v2, 0.f)), t.i2);
+                    sbound[trow] = kTcBoundBits;
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");   // merge[] is reused by the next query block
+                asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");   // merge[] / sbound[] are reused by the next query block
             }
         }
     }
@@ -312,11 +330,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     // ---- teardown: everything issued has been consumed (the epilogue waited on every accumulator stage) ----
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_free(tmem, 512);
+    if (warp == kTcEpiWarps + 1) tmem_free(tmem, 512);
 }
 
 size_t sweep_l2_tc_smem_bytes() {
-    return 1024 + (size_t)kTcTileBytes + (size_t)kTcStages * kTcTileBytes + (size_t)kTcThrStages * kTcThrBytes + kTile * sizeof(float4) +
+    return 1024 + (size_t)kTcTileBytes + (size_t)kTcStages * kTcTileBytes + (size_t)kTcThrStages * kTcThrBytes + (kTcColParts - 1) * kTile * sizeof(float4) + kTile * 4 +
            (2 + 2 * kTcStages + 2 * kTcAccStages + 2 * kTcThrStages) * 8 + 16;
 }
 
