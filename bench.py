@@ -37,12 +37,16 @@ SM_LANES_FP32 = 128      # FFMA lanes per SM per clock (verified: profiles/pipes
 POPC_LANES = 16          # POPC lanes per SM per clock (verified: profiles/pipes_r1.txt)
 
 
+TC_FLOP_PER_CMP = 3 * 72 * 2   # 3xTF32 split x (64 dims + 8 augmented columns) x 2: FLOPs the tensor cores execute per comparison
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f), "measured"
-    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+    # fallback stated by /opt/skills/guides/B200_PROFILING.md: 6.65 TB/s copy, 1.59 PFLOP/s cuBLAS bf16 (burst)
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "bf16_tflops": 1590.0}, "fallback"
 
 
 class ClockSampler:
@@ -175,11 +179,15 @@ def workload_config(kind, pairs_per_step, e2e_frames):
     return cfg
 
 
-def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budget_s):
-    """Returns the result dict for one descriptor kind (device-resident value, e2e, roofline, cpu baseline)."""
+def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budget_s, engine=None, e2e_arm=True):
+    """Returns the result dict for one descriptor kind (device-resident value, e2e, roofline, cpu baseline).
+    `engine` selects the SURF sweep kernel ('tc' = tcgen05 3xTF32, 'ffma' = exact-FP32 FMA pipe); None = library default."""
     import torch
     from easysfm_b200 import scheduler
     import easysfm_b200 as esfm
+    if kind == "surf" and engine:
+        ctx.set_l2_engine(engine)
+    engine = ctx.l2_engine() if kind == "surf" else None
 
     n_images, n_feat = N_IMAGES[kind], N_FEAT[kind]
     if args.images:
@@ -299,17 +307,18 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
                 s, *[1e3 * (t[i + 1] - t[i]) for i in range(3)], st["last_sweep_ms"], st["last_finalize_ms"], 1e3 * (t[4] - t[3])), file=sys.stderr)
         return nm
 
-    for s in range(warmup):
+    e2e_steps = steps if e2e_arm else 0
+    for s in range(warmup if e2e_arm else 0):
         e2e_step(s)
     sync_all()
     st2 = ctx.stats()
     ev0.record()
-    for s in range(warmup, warmup + steps):
+    for s in range(warmup, warmup + e2e_steps):
         e2e_step(s)
     ev1.record()
     sync_all()
     st3 = ctx.stats()
-    e2e_ms = ev0.elapsed_time(ev1)
+    e2e_ms = max(ev0.elapsed_time(ev1), 1e-9)
     e2e_comps_local = st3["comparisons"] - st2["comparisons"]
     if world > 1:
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -324,13 +333,21 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
            "h2d_bytes_per_step": int((st3["h2d_bytes"] - st2["h2d_bytes"]) / steps),
            "d2h_bytes_per_step": int((st3["d2h_bytes"] - st2["d2h_bytes"]) / steps),
            "ms_per_step": e2e_ms / steps}
+    if not e2e_arm:
+        e2e = None
 
     # ---- roofline of the dominant kernel (the sweep) -----------------------------------------------------
     peaks, peak_src = _peaks()
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
-    if kind == "surf":
+    fp32_pipe_peak = sms * SM_LANES_FP32 * 2 * sm_max * 1e6 / 1e12
+    if kind == "surf" and engine == "tc":
+        unit_ops, unit = 128.0, "TFLOP/s"                      # algorithmic: 64 FMA = 128 FLOP per comparison
+        peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0   # dense TF32 = half the measured dense bf16 rate
+        bound = "tensor"
+        kern = "sweep_l2_tc_kernel"
+    elif kind == "surf":
         unit_ops, unit = 128.0, "TFLOP/s"                      # 64 FFMA = 128 FLOP per comparison
-        peak = sms * SM_LANES_FP32 * 2 * sm_max * 1e6 / 1e12
+        peak = fp32_pipe_peak
         bound = "fp32-fma-pipe"
         kern = "sweep_l2_kernel"
     else:
@@ -340,10 +357,21 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
         kern = "sweep_hamming_kernel"
     achieved = comps_per_launch * unit_ops / (sweep_ms * 1e-3) / 1e12
     roofline = {"bound": bound, "kernel": kern, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-                "peak_source": f"{sms} SMs x {'128 FFMA lanes x 2 FLOP' if kind == 'surf' else '16 POPC lanes'} x {sm_max:.0f} MHz "
+                "peak_source": (f"dense TF32 tensor peak = bf16_tflops / 2 of MEASURED_PEAKS.json ({peak_src}: "
+                                f"{peaks.get('bf16_tflops', 1590.0):.0f} TFLOP/s bf16)") if bound == "tensor" else
+                               f"{sms} SMs x {'128 FFMA lanes x 2 FLOP' if kind == 'surf' else '16 POPC lanes'} x {sm_max:.0f} MHz "
                                f"(sm_max_mhz {peak_src}; lanes/clk measured by csrc/microbench/pipes.cu, profiles/pipes_r1.txt)",
                 "kernel_ms": sweep_ms, "comparisons_per_launch": comps_per_launch,
                 "hbm_gbs_algorithmic": None, "traffic": None}
+    if bound == "tensor":
+        # `achieved`/`frac` use the ALGORITHMIC 128 FLOP per comparison.  The tensor cores execute 3.375x that
+        # (3xTF32 split over 72 columns); `frac_executed` is that executed rate over the same peak (= tensor-pipe utilisation),
+        # and `frac_of_fp32_pipe_roofline` compares the algorithmic rate with the FP32-FFMA pipe peak the FFMA engine is bound by.
+        roofline["executed_tflops"] = achieved * TC_FLOP_PER_CMP / 128.0
+        roofline["frac_executed"] = roofline["executed_tflops"] / peak
+        roofline["frac_of_fp32_pipe_roofline"] = achieved / fp32_pipe_peak
+        roofline["note"] = ("3xTF32 split product (hi.hi + hi.lo + lo.hi over 64 dims + 8 augmented norm columns) on tcgen05; "
+                            "432 tensor FLOP executed per 128 algorithmic FLOP")
     if kind == "orb":
         # The kernel compresses the 8 xor words with carry-save adders and issues only 4 POPC per comparison, so it can
         # exceed the algorithmic 8-POPC roofline; what binds it is instruction issue (~36 warp-instructions per 32
@@ -354,7 +382,8 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
     if clocks.get("sm_mhz"):
         roofline["frac_at_sampled_clock"] = achieved / (peak * clocks["sm_mhz"] / sm_max)
     # algorithmic HBM bytes: every pair reads both frames once + writes its matches
-    bytes_per_pair = 2 * n_feat * (260 if kind == "surf" else 32)
+    # (SURF rows: 260 B in the FFMA engine's k-major bank, 640 B in the tensor-core bank = hi + lo images + augmented columns)
+    bytes_per_pair = 2 * n_feat * ((640 if engine == "tc" else 260) if kind == "surf" else 32)
     roofline["hbm_gbs_algorithmic"] = (comps_per_launch / (n_feat * n_feat)) * bytes_per_pair / (sweep_ms * 1e-3) / 1e9
     roofline["hbm_peak_gbs"] = peaks.get("hbm_gbs")
     # measured DRAM traffic of this kernel on this command (one ncu pass, committed under profiles/): far BELOW the per-pair
@@ -362,7 +391,7 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            tr = json.load(f).get(kind)
+            tr = json.load(f).get("surf_tc" if engine == "tc" else kind)
         if tr:
             per_pair = (tr["dram_read_bytes_per_launch"] + tr["dram_write_bytes_per_launch"]) / tr["pairs_per_launch"]
             roofline["traffic"] = per_pair * (comps_per_launch / (n_feat * n_feat))
@@ -384,7 +413,7 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if kind == "surf" else "u8", "data": "synthetic",
         "config": workload_config(kind, pairs_per_step, e2e_frames),
         "pairs_per_s": value / (n_feat * n_feat), "matches_per_step": n_matches / steps,
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "engine": engine, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "setup_s": setup_s, "bank_broadcast_ms": bcast_ms,
         "full_job_estimate_s": (n_images * (n_images - 1) / 2) * (n_feat * n_feat) / value,
     }
@@ -406,6 +435,9 @@ def main():
     ap.add_argument("--images", type=int, default=0, help="override the number of images (smoke runs)")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--ref-pairs-per-step", type=int, default=4)
+    ap.add_argument("--l2-engine", default=None, choices=["tc", "ffma"],
+                    help="SURF sweep kernel: tcgen05 3xTF32 ('tc', library default) or exact-FP32 FMA pipe ('ffma')")
+    ap.add_argument("--no-alt-engine", action="store_true", help="skip the short run of the other SURF engine")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -437,12 +469,27 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = esfm.Context(local_rank, stream=stream.cuda_stream)
 
-    primary = bench_kind(args, args.kind, ctx, dev, rank, world, dist, args.steps, args.warmup, args.cpu_budget_s)
+    surf_engine = args.l2_engine or ctx.l2_engine()
+    primary = bench_kind(args, args.kind, ctx, dev, rank, world, dist, args.steps, args.warmup, args.cpu_budget_s,
+                         engine=surf_engine)
+    if not args.no_alt_engine and world == 1:
+        # the other SURF engine on the same workload, device-resident arm only (short: it is context, not the headline)
+        alt = "ffma" if surf_engine == "tc" else "tc"
+        a = bench_kind(args, "surf", ctx, dev, rank, world, dist, 3, 3, 0.0, engine=alt, e2e_arm=False)
+        alt_obj = {k: a[k] for k in ("engine", "value", "unit", "ms_per_step", "roofline", "clocks")}
+        if args.kind == "surf":
+            primary["alt_engine"] = alt_obj
+        ctx.set_l2_engine(surf_engine)
+    else:
+        alt_obj = None
     if not args.no_secondary:
         other = "orb" if args.kind == "surf" else "surf"
-        sec = bench_kind(args, other, ctx, dev, rank, world, dist, max(3, args.steps // 2), args.warmup, args.cpu_budget_s / 2)
-        primary["secondary"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "dtype", "config", "pairs_per_s", "e2e",
+        sec = bench_kind(args, other, ctx, dev, rank, world, dist, max(3, args.steps // 2), args.warmup, args.cpu_budget_s / 2,
+                         engine=surf_engine)
+        primary["secondary"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "dtype", "config", "pairs_per_s", "e2e", "engine",
                                                     "roofline", "cpu_baseline", "gpu_launches", "clocks", "full_job_estimate_s")}
+        if args.kind != "surf" and alt_obj:
+            primary["secondary"]["alt_engine"] = alt_obj
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

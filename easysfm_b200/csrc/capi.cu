@@ -48,7 +48,7 @@ struct esfm_ctx {
     bool own_stream = false;
     int sm_count = 0;
     bool profiling = true;
-    int l2_engine = ESFM_L2_ENGINE_FFMA;   // which sweep kernel serves ESFM_KIND_F32X64 (esfm_set_l2_engine / $ESFM_L2_ENGINE)
+    int l2_engine = ESFM_L2_ENGINE_TC;     // which sweep kernel serves ESFM_KIND_F32X64 (esfm_set_l2_engine / $ESFM_L2_ENGINE)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     esfm_stats_t stats{};
     // device scratch, grown on demand

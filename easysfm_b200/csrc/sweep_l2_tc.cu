@@ -65,9 +65,22 @@ struct RowTop2 {
     uint32_t i1, i2;
 };
 
-__device__ __forceinline__ void epi_arrive(uint64_t* bar, int lane) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar);
+// Wait of the single MMA-issuing lane: it shares an SM sub-partition with four epilogue warps, so a tight try_wait loop
+// (3 issue slots every ~12 cycles) would steal a quarter of their issue bandwidth.  The accumulator ring keeps the
+// issuer up to 4 tiles ahead, so a ~100 ns wake-up latency costs nothing.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+        if (ok) break;
+        __nanosleep(100);
+    }
 }
 
 }  // namespace
@@ -163,13 +176,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
             for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
                 const TcUnit u = tc_decode_unit(p, unit);
                 for (int qb = u.qb0; qb < u.qb1; ++qb) {
-                    mbar_wait(fullQ, qseq & 1);
+                    mbar_wait_relaxed(fullQ, qseq & 1);
                     ++qseq;
                     for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                         const uint32_t st = g % kTcStages, ph = (g / kTcStages) & 1;
                         const uint32_t as = g % kTcAccStages, aph = (g / kTcAccStages) & 1;
-                        mbar_wait(&fullT[st], ph);
-                        mbar_wait(&accEmpty[as], aph ^ 1);
+                        mbar_wait_relaxed(&fullT[st], ph);
+                        mbar_wait_relaxed(&accEmpty[as], aph ^ 1);
                         tc_fence_after();
                         const uint32_t tm = smem_u32(Ts + (size_t)st * kTcTileBytes), ta = tm + kTcMainBytes;
                         const uint32_t d = tmem + as * 128;
@@ -249,9 +262,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                         for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(vb[c]);   // v = -1/2 d^2
                         const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols + ch * 16);
                         // ---- row side, 4 columns at a time: anything at least as good as the row's second best? ----
+                        float gmx[4];
+#pragma unroll
+                        for (int gq = 0; gq < 4; ++gq)
+                            gmx[gq] = fmaxf(fmaxf(fmaxf(v[4 * gq], v[4 * gq + 1]), v[4 * gq + 2]), v[4 * gq + 3]);
+                        if (fmaxf(fmaxf(gmx[0], gmx[1]), fmaxf(gmx[2], gmx[3])) >= nb)
 #pragma unroll
                         for (int gq = 0; gq < 4; ++gq) {
-                            const float gm = fmaxf(fmaxf(fmaxf(v[4 * gq], v[4 * gq + 1]), v[4 * gq + 2]), v[4 * gq + 3]);
+                            const float gm = gmx[gq];
                             if (gm >= nb) {
                                 bool ins = false;
 #pragma unroll

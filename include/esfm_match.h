@@ -108,7 +108,7 @@ int esfm_device_sm_count(esfm_ctx_t* ctx, int* sms);
  * RANKING distance is computed:
  *   ESFM_L2_ENGINE_FFMA  exact-FP32 FFMA expansion  1/2|q|^2 + 1/2|t|^2 - q.t  on the FP32 pipe;
  *   ESFM_L2_ENGINE_TC    the same quantity as a 3xTF32 split product on the tcgen05 tensor cores.
- * Default: $ESFM_L2_ENGINE ("ffma" | "tc") at esfm_init, else the library default. */
+ * Default: $ESFM_L2_ENGINE ("ffma" | "tc") at esfm_init, else ESFM_L2_ENGINE_TC. */
 #define ESFM_L2_ENGINE_FFMA 0
 #define ESFM_L2_ENGINE_TC 1
 int esfm_set_l2_engine(esfm_ctx_t* ctx, int engine);
