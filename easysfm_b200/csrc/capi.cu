@@ -583,6 +583,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     sp.col_thr = ctx->col_thr;
     sp.stride = pl.stride;
     sp.col_cap = pl.col_cap;
+    if (const char* dbg = getenv("ESFM_TC_DEBUG")) sp.debug_flags = atoi(dbg);
     if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
     cudaError_t e = b->kind == ESFM_KIND_F32X64 ? (tc ? launch_sweep_l2_tc(sp, ctx->sm_count, ctx->stream)
                                                       : launch_sweep_l2(sp, ctx->sm_count, ctx->stream))

@@ -57,6 +57,8 @@ struct SweepParams {
     uint32_t* col_thr;          // [n_pairs][stride] running column thresholds (float bits), L2 sweep only
     int stride;                 // keys per array (>= padded rows of the largest frame in the chunk)
     int col_cap;                // Hamming sweep: smem column-minimum capacity in entries
+    int debug_flags;            // TC sweep pipeline probes ($ESFM_TC_DEBUG; results are WRONG when set): 1 = epilogue only drains,
+                                // 2 = no MMAs issued, 4 = no train-tile loads
 };
 
 struct FinalizeParams {

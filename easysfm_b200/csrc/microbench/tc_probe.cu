@@ -31,7 +31,7 @@ template <int N>
 __global__ void __launch_bounds__(192, 1)
 probe_kernel(const uint8_t* __restrict__ q_main, const uint8_t* __restrict__ q_aug_hi, const uint8_t* __restrict__ q_aug_lo,
              const uint8_t* __restrict__ t_main, const uint8_t* __restrict__ t_aug_hi, const uint8_t* __restrict__ t_aug_lo,
-             float* __restrict__ out, int terms, int reps, long long* __restrict__ cycles) {
+             float* __restrict__ out, int terms, int reps, long long* __restrict__ cycles, const float* __restrict__ q_rows, int ts_mode) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // Q: 128 rows main (16 groups x 4096) + aug hi/lo (16 x 256 each); T: N rows likewise
     uint8_t* Qm = smem;                               // 64 KB
@@ -52,6 +52,25 @@ probe_kernel(const uint8_t* __restrict__ q_main, const uint8_t* __restrict__ q_a
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+
+    if (ts_mode && warp < 4) {
+        // operand A into tensor memory: lane = row, columns 384.. = hi(k 0..63), 448.. = lo(k 0..63)
+        const int row = warp * 32 + lane;
+        for (int k0 = 0; k0 < 64; k0 += 8) {
+            uint32_t hi[8], lo[8];
+            for (int j = 0; j < 8; ++j) {
+                const float x = q_rows[row * 64 + k0 + j];
+                const float h = tc_tf32_hi(x);
+                hi[j] = __float_as_uint(h);
+                lo[j] = __float_as_uint(x - h);
+            }
+            tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + 384 + k0, hi);
+            tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + 448 + k0, lo);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+    }
+    if (ts_mode) { __syncthreads(); tc_fence_after(); }
 
     if (warp == 4 && lane == 0) {
         const uint32_t bytes = (16 + N / 8) * (kTcGroupBytes + 2 * kTcAugGroupBytes);
@@ -77,7 +96,8 @@ probe_kernel(const uint8_t* __restrict__ q_main, const uint8_t* __restrict__ q_a
                 for (int ks = 0; ks < 8; ++ks) {
                     const uint64_t da = tc_desc_sw128(qm + pa * 2048 + (ks >> 2) * 1024 + (ks & 3) * 32, kTcGroupBytes);
                     const uint64_t db = tc_desc_sw128(tm + pb * 2048 + (ks >> 2) * 1024 + (ks & 3) * 32, kTcGroupBytes);
-                    tc_mma_tf32(d, da, db, idesc, !first);
+                    if (ts_mode) tc_mma_tf32_ts(d, tmem + 384 + pa * 64 + ks * 8, db, idesc, !first);
+                    else tc_mma_tf32(d, da, db, idesc, !first);
                     first = false;
                 }
                 const uint64_t da = tc_desc_nosw(qa + pa * 16 * kTcAugGroupBytes, 128, kTcAugGroupBytes);
@@ -123,7 +143,7 @@ static void fill_rows(std::vector<float>& x, int rows, unsigned seed, bool unit)
 }
 
 template <int N>
-static int run(int terms, int reps, bool check) {
+static int run(int terms, int reps, bool check, int ts_mode = 0) {
     std::vector<float> q, t;
     fill_rows(q, 128, 1, true);
     fill_rows(t, N, 2, true);
@@ -138,7 +158,10 @@ static int run(int terms, int reps, bool check) {
         tc_pack_row_host(t.data() + (size_t)r * 64, true, false, tm.data(), ta.data(), ta.data() + (N / 8) * kTcAugGroupBytes, r);
     uint8_t *dqm, *dtm, *dqa, *dta;
     float* dout;
+    float* dq;
     long long* dcyc;
+    CK(cudaMalloc(&dq, q.size() * 4));
+    CK(cudaMemcpy(dq, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&dqm, qm.size())); CK(cudaMalloc(&dtm, tm.size()));
     CK(cudaMalloc(&dqa, qa.size())); CK(cudaMalloc(&dta, ta.size()));
     CK(cudaMalloc(&dout, (size_t)128 * N * 4)); CK(cudaMalloc(&dcyc, 8));
@@ -149,7 +172,7 @@ static int run(int terms, int reps, bool check) {
     const size_t smem = (16 + N / 8) * (kTcGroupBytes + 2 * kTcAugGroupBytes) + 64;
     CK(cudaFuncSetAttribute(probe_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     probe_kernel<N><<<1, 192, smem>>>(dqm, dqa, dqa + 16 * kTcAugGroupBytes, dtm, dta, dta + (N / 8) * kTcAugGroupBytes, dout,
-                                     terms, reps, dcyc);
+                                     terms, reps, dcyc, dq, ts_mode);
     CK(cudaDeviceSynchronize());
     long long cyc = 0;
     CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
@@ -175,7 +198,7 @@ static int run(int terms, int reps, bool check) {
             }
     }
     const int mmas = reps * terms * 9;
-    printf("N=%3d terms=%d reps=%4d: %lld cycles, %.1f cycles/MMA (floor %d)%s max|err|=%.3g bad=%d\n", N, terms, reps, cyc,
+    printf("%s N=%3d terms=%d reps=%4d: %lld cycles, %.1f cycles/MMA (floor %d)%s max|err|=%.3g bad=%d\n", ts_mode ? "A-in-TMEM" : "A-in-smem", N, terms, reps, cyc,
            (double)cyc / mmas, N / 2, check ? "" : " [timing only]", maxerr, bad);
     cudaFree(dqm); cudaFree(dtm); cudaFree(dqa); cudaFree(dta); cudaFree(dout); cudaFree(dcyc);
     return bad;
@@ -190,6 +213,10 @@ int main() {
     run<64>(3, 200, false);
     run<128>(3, 200, false);
     run<256>(3, 100, false);
+    bad += run<64>(3, 1, true, 1);
+    bad += run<128>(3, 1, true, 1);
+    run<64>(3, 200, false, 1);
+    run<128>(3, 200, false, 1);
     printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
     return bad ? 1 : 0;
 }

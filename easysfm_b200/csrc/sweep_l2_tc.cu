@@ -65,9 +65,10 @@ struct RowTop2 {
     uint32_t i1, i2;
 };
 
-// Wait of the single MMA-issuing lane: it shares an SM sub-partition with four epilogue warps, so a tight try_wait loop
-// (3 issue slots every ~12 cycles) would steal a quarter of their issue bandwidth.  The accumulator ring keeps the
-// issuer up to 4 tiles ahead, so a ~100 ns wake-up latency costs nothing.
+// Wait of the single producer / MMA-issuing lanes: each shares an SM sub-partition with four epilogue warps, so a tight
+// try_wait loop (measured: 3 issue slots every ~7 cycles) steals a large part of their issue bandwidth, while the 2 us
+// back-off of the FFMA sweep's producer is longer than a whole tile here (~1 us) and starves the tensor pipe.  Poll every
+// few tens of nanoseconds instead.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
     while (true) {
@@ -79,7 +80,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
             : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
             : "memory");
         if (ok) break;
-        __nanosleep(100);
+        __nanosleep(40);
     }
 }
 
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                 const size_t qg0 = (size_t)p.frame_tile_off[u.q_frame] * 16, tg0 = (size_t)p.frame_tile_off[u.t_frame] * 16;
                 const uint32_t* tauc = p.col_thr + (size_t)u.pair * p.stride;
                 for (int qb = u.qb0; qb < u.qb1; ++qb) {
-                    mbar_wait_backoff(emptyQ, (qseq & 1) ^ 1);
+                    mbar_wait_relaxed(emptyQ, (qseq & 1) ^ 1);
                     mbar_arrive_expect_tx(fullQ, kTcTileBytes);
                     const size_t qg = qg0 + (size_t)qb * 16;
                     bulk_g2s(Qs, p.tc_main + qg * kTcGroupBytes, kTcMainBytes, fullQ);
@@ -150,17 +151,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                     ++qseq;
                     for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                         const uint32_t st = g % kTcStages, ph = (g / kTcStages) & 1;
-                        mbar_wait_backoff(&emptyT[st], ph ^ 1);
+                        mbar_wait_relaxed(&emptyT[st], ph ^ 1);
                         mbar_arrive_expect_tx(&fullT[st], kTcTileBytes);
                         unsigned char* dst = Ts + (size_t)st * kTcTileBytes;
                         const size_t tg = tg0 + (size_t)tt * 16;
+                        if (p.debug_flags & 4) { mbar_arrive_expect_tx(&fullT[st], 0); asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&fullT[st])), "r"(kTcTileBytes) : "memory"); } else {
                         bulk_g2s(dst, p.tc_main + tg * kTcGroupBytes, kTcMainBytes, &fullT[st]);
                         bulk_g2s(dst + kTcMainBytes, p.tc_aug + 2 * aug_part + tg * kTcAugGroupBytes, kTcAugBytes, &fullT[st]);
                         bulk_g2s(dst + kTcMainBytes + kTcAugBytes, p.tc_aug + 3 * aug_part + tg * kTcAugGroupBytes, kTcAugBytes, &fullT[st]);
+                        }
                         // the running column thresholds of this tile ride along in their own ring (a snapshot a few tiles
                         // old is fine: a stale threshold is only looser, never wrong)
                         const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
-                        mbar_wait_backoff(&thrEmpty[ts], tph ^ 1);
+                        mbar_wait_relaxed(&thrEmpty[ts], tph ^ 1);
                         mbar_arrive_expect_tx(&thrFull[ts], kTcThrBytes);
                         bulk_g2s(Thr + ts * kTcThrBytes, tauc + (size_t)tt * kTile, kTcThrBytes, &thrFull[ts]);
                     }
@@ -169,23 +172,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
         }
     } else if (warp == kTcEpiWarps + 1) {
         // ======================= MMA issuer =======================
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc_idesc_tf32(128, 128);
-            const uint32_t qm = smem_u32(Qs), qa = qm + kTcMainBytes;
-            uint32_t g = 0, qseq = 0;
-            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-                const TcUnit u = tc_decode_unit(p, unit);
-                for (int qb = u.qb0; qb < u.qb1; ++qb) {
-                    mbar_wait_relaxed(fullQ, qseq & 1);
-                    ++qseq;
-                    for (int tt = 0; tt < u.ntt; ++tt, ++g) {
-                        const uint32_t st = g % kTcStages, ph = (g / kTcStages) & 1;
-                        const uint32_t as = g % kTcAccStages, aph = (g / kTcAccStages) & 1;
-                        mbar_wait_relaxed(&fullT[st], ph);
-                        mbar_wait_relaxed(&accEmpty[as], aph ^ 1);
-                        tc_fence_after();
-                        const uint32_t tm = smem_u32(Ts + (size_t)st * kTcTileBytes), ta = tm + kTcMainBytes;
-                        const uint32_t d = tmem + as * 128;
+        // The WHOLE warp walks the loops and waits on the barriers (warp-uniform control flow, so the shared-memory
+        // descriptors live in uniform registers); one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
+        // (Issuing from inside `if (lane == 0)` made the compiler wrap every MMA in an ELECT / R2UR.BROADCAST waterfall
+        // loop: 16 dependent instructions and ~90 cycles per MMA, longer than the MMA itself.)
+        constexpr uint32_t idesc = tc_idesc_tf32(128, 128);
+        const uint64_t qd = tc_desc_sw128(smem_u32(Qs), kTcGroupBytes);
+        const uint64_t qad = tc_desc_nosw(smem_u32(Qs) + kTcMainBytes, 128, kTcAugGroupBytes);
+        const uint64_t td0 = tc_desc_sw128(smem_u32(Ts), kTcGroupBytes);
+        const uint64_t tad0 = tc_desc_nosw(smem_u32(Ts) + kTcMainBytes, 128, kTcAugGroupBytes);
+        uint32_t g = 0, qseq = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const TcUnit u = tc_decode_unit(p, unit);
+            for (int qb = u.qb0; qb < u.qb1; ++qb) {
+                mbar_wait_relaxed(fullQ, qseq & 1);
+                ++qseq;
+                for (int tt = 0; tt < u.ntt; ++tt, ++g) {
+                    const uint32_t st = g % kTcStages, ph = (g / kTcStages) & 1;
+                    const uint32_t as = g % kTcAccStages, aph = (g / kTcAccStages) & 1;
+                    mbar_wait_relaxed(&fullT[st], ph);
+                    mbar_wait_relaxed(&accEmpty[as], aph ^ 1);
+                    tc_fence_after();
+                    // descriptor start addresses are in 16-byte units: adding (bytes >> 4) to the low word moves the window
+                    const uint64_t td = td0 + (uint64_t)(st * (kTcTileBytes >> 4));
+                    const uint64_t tad = tad0 + (uint64_t)(st * (kTcTileBytes >> 4));
+                    const uint32_t d = tmem + as * 128;
+                    if (!(p.debug_flags & 2) && elect_one()) {
                         bool first = true;
 #pragma unroll
                         for (int term = 0; term < 3; ++term) {
@@ -193,19 +205,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                             const int pa = term == 0 ? 1 : 0, pb = term == 1 ? 1 : 0;
 #pragma unroll
                             for (int ks = 0; ks < 8; ++ks) {
-                                const uint32_t off = (ks >> 2) * 1024 + (ks & 3) * 32;
-                                tc_mma_tf32(d, tc_desc_sw128(qm + pa * 2048 + off, kTcGroupBytes),
-                                            tc_desc_sw128(tm + pb * 2048 + off, kTcGroupBytes), idesc, !first);
+                                const uint32_t off = ((ks >> 2) * 1024 + (ks & 3) * 32) >> 4;
+                                tc_mma_tf32(d, qd + (uint64_t)(pa * (2048 >> 4) + off), td + (uint64_t)(pb * (2048 >> 4) + off), idesc, !first);
                                 first = false;
                             }
-                            tc_mma_tf32(d, tc_desc_nosw(qa + pa * kTcAugBytes, 128, kTcAugGroupBytes),
-                                        tc_desc_nosw(ta + pb * kTcAugBytes, 128, kTcAugGroupBytes), idesc, true);
+                            tc_mma_tf32(d, qad + (uint64_t)(pa * (kTcAugBytes >> 4)), tad + (uint64_t)(pb * (kTcAugBytes >> 4)), idesc, true);
                         }
+                    }
+                    __syncwarp();
+                    if (elect_one()) {
                         tc_commit(&emptyT[st]);     // shared-memory stage consumed once these MMAs retire
                         tc_commit(&accFull[as]);    // accumulator stage ready for the epilogue
                     }
-                    tc_commit(emptyQ);
+                    __syncwarp();
                 }
+                if (elect_one()) tc_commit(emptyQ);
+                __syncwarp();
             }
         }
     } else {
@@ -238,7 +253,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                     const uint32_t taddr = tmem + lane_addr + as * 128 + part * kTcPartCols;
                     // The row's running second best over ALL column parts (each part keeps a private top-2; the shared
                     // bound only filters, with '>=' so equal values still reach the private strict-'<' insertion).
-                    const float nb = -__uint_as_float(*reinterpret_cast<volatile uint32_t*>(&sbound[trow]));
+                    float nb = -__uint_as_float(*reinterpret_cast<volatile uint32_t*>(&sbound[trow]));
                     // columns in chunks of 16: a real loop, so the epilogue body stays small enough for the instruction
                     // cache (a fully unrolled 64-column body was 64 KB of SASS and stalled on instruction fetch)
 #pragma unroll 1
@@ -260,54 +275,67 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                         float v[16];
 #pragma unroll
                         for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(vb[c]);   // v = -1/2 d^2
-                        const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols + ch * 16);
-                        // ---- row side, 4 columns at a time: anything at least as good as the row's second best? ----
+                        if (p.debug_flags & 1) continue;
+                        // ---- fast path (~40 instructions): one row test + 16 column tests + ONE vote ----
                         float gmx[4];
 #pragma unroll
                         for (int gq = 0; gq < 4; ++gq)
                             gmx[gq] = fmaxf(fmaxf(fmaxf(v[4 * gq], v[4 * gq + 1]), v[4 * gq + 2]), v[4 * gq + 3]);
-                        if (fmaxf(fmaxf(gmx[0], gmx[1]), fmaxf(gmx[2], gmx[3])) >= nb)
+                        const bool rflag = fmaxf(fmaxf(fmaxf(gmx[0], gmx[1]), gmx[2]), gmx[3]) >= nb;
+                        bool cflag = false;
 #pragma unroll
-                        for (int gq = 0; gq < 4; ++gq) {
-                            const float gm = gmx[gq];
-                            if (gm >= nb) {
-                                bool ins = false;
+                        for (int j = 0; j < 16; ++j) cflag |= (v[j] >= -thr[j]);
+                        if (!__any_sync(0xffffffffu, rflag || cflag)) continue;
+
+                        // ---- slow path: ~2 ln F hits per row and ~ln F per column over a whole sweep ----
+                        const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols + ch * 16);
+                        if (rflag) {
+                            bool ins = false;
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float d = -v[4 * gq + j];
-                                    if (d < t.v2) {     // ascending column order + strict '<' keeps the lowest index on ties
-                                        const uint32_t idx = col0 + 4 * gq + j;
-                                        if (d < t.v1) {
-                                            t.v2 = t.v1; t.i2 = t.i1;
-                                            t.v1 = d;    t.i1 = idx;
-                                        } else {
-                                            t.v2 = d;    t.i2 = idx;
+                            for (int gq = 0; gq < 4; ++gq) {
+                                if (gmx[gq] >= nb) {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const float d = -v[4 * gq + j];
+                                        if (d < t.v2) {     // ascending column order + strict '<' keeps the lowest index on ties
+                                            const uint32_t idx = col0 + 4 * gq + j;
+                                            if (d < t.v1) {
+                                                t.v2 = t.v1; t.i2 = t.i1;
+                                                t.v1 = d;    t.i1 = idx;
+                                            } else {
+                                                t.v2 = d;    t.i2 = idx;
+                                            }
+                                            ins = true;
                                         }
-                                        ins = true;
                                     }
                                 }
-                                if (ins) atomicMin(&sbound[trow], __float_as_uint(fmaxf(t.v2, 0.f)));
+                            }
+                            if (ins) {
+                                atomicMin(&sbound[trow], __float_as_uint(fmaxf(t.v2, 0.f)));
+                                nb = fmaxf(nb, -t.v2);
                             }
                         }
-                        // ---- column side, 8 columns at a time: does any row of this warp beat a column's running best? ----
+                        if (__any_sync(0xffffffffu, cflag)) {
 #pragma unroll
-                        for (int gq = 0; gq < 2; ++gq) {
-                            bool any = false;
+                            for (int gq = 0; gq < 2; ++gq) {
+                                bool any = false;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) any |= (v[8 * gq + j] >= -thr[8 * gq + j]);
-                            if (__any_sync(0xffffffffu, any)) {
+                                for (int j = 0; j < 8; ++j) any |= (v[8 * gq + j] >= -thr[8 * gq + j]);
+                                if (__any_sync(0xffffffffu, any)) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const bool hit = v[8 * gq + j] >= -thr[8 * gq + j];
-                                    const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-                                    if (bal) {     // warp-uniform
-                                        const uint32_t bits = hit ? __float_as_uint(fmaxf(-v[8 * gq + j], 0.f)) : 0xffffffffu;
-                                        const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
-                                        const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
-                                        if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
-                                            const uint32_t gcol = col0 + 8 * gq + j;
-                                            atomicMin(ck1 + gcol, make_key(mn, qrow));
-                                            atomicMin(tauc + gcol, mn);
+                                    for (int j = 0; j < 8; ++j) {
+                                        const bool hit = v[8 * gq + j] >= -thr[8 * gq + j];
+                                        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                                        if (bal) {     // warp-uniform
+                                            const uint32_t bits = hit ? __float_as_uint(fmaxf(-v[8 * gq + j], 0.f)) : 0xffffffffu;
+                                            const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
+                                            const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
+                                            if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
+                                                uint32_t gcol = col0 + 8 * gq + j;
+                                                asm volatile("" : "+r"(gcol));   // keep the 64-bit address arithmetic inside this (rare) branch
+                                                atomicMin(ck1 + gcol, make_key(mn, qrow));
+                                                atomicMin(tauc + gcol, mn);
+                                            }
                                         }
                                     }
                                 }
