@@ -569,6 +569,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
         CUDA_TRY(cudaMemsetAsync(ctx->col_thr, tc ? 0x6F : 0x7F, n * (size_t)pl.stride * sizeof(uint32_t), ctx->stream));
     SweepParams sp{};
     sp.kmajor = b->d_kmajor;
+    sp.rows_f32 = (const float*)b->d_rows;
     sp.tc_main = b->d_tc;
     sp.tc_groups = b->tile_off.empty() ? 0 : b->tile_off[b->n_frames] * 16;
     sp.tc_aug = b->d_tc ? b->d_tc + (size_t)sp.tc_groups * kTcGroupBytes : nullptr;

@@ -42,6 +42,7 @@ struct SweepParams {
     // bank
     const float* kmajor;        // F32X64
     const uint4* rows_b256;     // B256
+    const float* rows_f32;         // F32X64 row-major rows (the TC sweep converts its query tiles from these)
     const unsigned char* tc_main;  // F32X64, tensor-core engine: [tiles*16 groups][4096 B]  (tc_layout.cuh)
     const unsigned char* tc_aug;   //   [4 = role*2 + part][tiles*16 groups][256 B]
     int tc_groups;                 //   tiles*16

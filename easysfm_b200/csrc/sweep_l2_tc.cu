@@ -28,10 +28,14 @@ namespace {
 constexpr int kTcColParts = 4;                          // column quarters of a train tile, one per epilogue warp of a lane quarter
 constexpr int kTcEpiWarps = 4 * kTcColParts;            // 16 epilogue warps: enough to hide the epilogue's dependent-issue latency
 constexpr int kTcEpiThreads = kTcEpiWarps * 32;
-constexpr int kTcThreads = kTcEpiThreads + 64;          // + TMA producer warp + MMA issuer warp
+constexpr int kTcThreads = kTcEpiThreads + 64 + 128;    // + TMA producer warp + MMA issuer warp + 4 query-writer warps
+constexpr int kTcWriterWarp0 = kTcEpiWarps + 2;         // warps 18..21: warp % 4 covers the four TMEM lane quarters
+constexpr uint32_t kTcAColHi = 384, kTcAColLo = 448;    // tensor-memory columns of the query operand (hi, lo: 64 each)
 constexpr int kTcPartCols = kTile / kTcColParts;        // 32 columns per epilogue thread and stage
-constexpr int kTcStages = 2;                 // shared-memory train stages
-constexpr int kTcAccStages = 4;              // tensor-memory accumulator stages (128 columns each)
+constexpr int kTcStages = 3;                 // shared-memory train stages (2 starve the tensor pipe: a 72 KB tile takes longer to
+                                             // land than one tile's MMAs while those MMAs are reading the same shared memory)
+constexpr int kTcQaBytes = 16 * 128 + 128;   // one (hi | lo) block of the query tile's augmented columns: 16 B per row + pad
+constexpr int kTcAccStages = 3;              // tensor-memory accumulator stages (128 columns each; columns 384..511 hold the query operand)
 constexpr int kTcMainBytes = 16 * kTcGroupBytes;       // 65536: main image of a 128-row tile
 constexpr int kTcAugBytes = 16 * kTcAugGroupBytes;     // 4096: one (role, part) augmented image of a tile
 constexpr int kTcTileBytes = kTcMainBytes + 2 * kTcAugBytes;   // 73728 bytes per operand tile in shared memory
@@ -90,11 +94,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char* Qs = base;                                   // query tile image
-    unsigned char* Ts = Qs + kTcTileBytes;                      // kTcStages train tile images (each 72 x 1024 B: atoms stay aligned)
-    unsigned char* Thr = Ts + kTcStages * kTcTileBytes;         // kTcThrStages x 128 column thresholds
-    float4* merge = reinterpret_cast<float4*>(Thr + kTcThrStages * kTcThrBytes);   // [parts-1][128] row candidates of parts 1..
-    uint32_t* sbound = reinterpret_cast<uint32_t*>(merge + (kTcColParts - 1) * kTile);  // [128] row bound shared by a row's parts
+    unsigned char* Ts = base;                                   // kTcStages train tile images (each 72 x 1024 B: atoms stay aligned)
+    unsigned char* Qa = Ts + kTcStages * kTcTileBytes;          // augmented columns (1, 1/2|q|^2, 0, 0) of the query tile: hi, lo
+    unsigned char* Thr = Qa + 2 * kTcQaBytes;                   // kTcThrStages x 128 column thresholds
+    u64* mkey = reinterpret_cast<u64*>(Thr + kTcThrStages * kTcThrBytes);          // [2][128] merged best / second-best row keys
+    uint32_t* sbound = reinterpret_cast<uint32_t*>(mkey + 2 * kTile);              // [128] row bound shared by a row's parts
     uint64_t* bars = reinterpret_cast<uint64_t*>(sbound + kTile);
     uint64_t* fullQ = bars;
     uint64_t* emptyQ = bars + 1;
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     const int n_units = p.n_pairs * p.units_per_pair;
 
     if (threadIdx.x == 0) {
-        mbar_init(fullQ, 1);
+        mbar_init(fullQ, 4);                          // the 4 query-writer warps
         mbar_init(emptyQ, 1);
         for (int s = 0; s < kTcStages; ++s) {
             mbar_init(&fullT[s], 1);
@@ -136,19 +140,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
         // ======================= TMA producer =======================
         if (lane == 0) {
             const size_t aug_part = (size_t)p.tc_groups * kTcAugGroupBytes;   // bytes of one (role, part) augmented array
-            uint32_t g = 0, qseq = 0;
+            uint32_t g = 0;
             for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
                 const TcUnit u = tc_decode_unit(p, unit);
-                const size_t qg0 = (size_t)p.frame_tile_off[u.q_frame] * 16, tg0 = (size_t)p.frame_tile_off[u.t_frame] * 16;
+                const size_t tg0 = (size_t)p.frame_tile_off[u.t_frame] * 16;
                 const uint32_t* tauc = p.col_thr + (size_t)u.pair * p.stride;
                 for (int qb = u.qb0; qb < u.qb1; ++qb) {
-                    mbar_wait_relaxed(emptyQ, (qseq & 1) ^ 1);
-                    mbar_arrive_expect_tx(fullQ, kTcTileBytes);
-                    const size_t qg = qg0 + (size_t)qb * 16;
-                    bulk_g2s(Qs, p.tc_main + qg * kTcGroupBytes, kTcMainBytes, fullQ);
-                    bulk_g2s(Qs + kTcMainBytes, p.tc_aug + 0 * aug_part + qg * kTcAugGroupBytes, kTcAugBytes, fullQ);
-                    bulk_g2s(Qs + kTcMainBytes + kTcAugBytes, p.tc_aug + 1 * aug_part + qg * kTcAugGroupBytes, kTcAugBytes, fullQ);
-                    ++qseq;
                     for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                         const uint32_t st = g % kTcStages, ph = (g / kTcStages) & 1;
                         mbar_wait_relaxed(&emptyT[st], ph ^ 1);
@@ -177,8 +174,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
         // (Issuing from inside `if (lane == 0)` made the compiler wrap every MMA in an ELECT / R2UR.BROADCAST waterfall
         // loop: 16 dependent instructions and ~90 cycles per MMA, longer than the MMA itself.)
         constexpr uint32_t idesc = tc_idesc_tf32(128, 128);
-        const uint64_t qd = tc_desc_sw128(smem_u32(Qs), kTcGroupBytes);
-        const uint64_t qad = tc_desc_nosw(smem_u32(Qs) + kTcMainBytes, 128, kTcAugGroupBytes);
+        // query augmented columns: 16 B per row ([group][8 rows][16 B], group stride 128 B).  Only k-chunk 0 exists; the
+        // descriptor's k-chunk 1 aliases the NEXT group's rows, which is harmless because the train side's k-chunk 1 is all
+        // zeros and every aliased value is finite.
+        const uint64_t qad = tc_desc_nosw(smem_u32(Qa), 128, 128);
         const uint64_t td0 = tc_desc_sw128(smem_u32(Ts), kTcGroupBytes);
         const uint64_t tad0 = tc_desc_nosw(smem_u32(Ts) + kTcMainBytes, 128, kTcAugGroupBytes);
         uint32_t g = 0, qseq = 0;
@@ -206,10 +205,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
 #pragma unroll
                             for (int ks = 0; ks < 8; ++ks) {
                                 const uint32_t off = ((ks >> 2) * 1024 + (ks & 3) * 32) >> 4;
-                                tc_mma_tf32(d, qd + (uint64_t)(pa * (2048 >> 4) + off), td + (uint64_t)(pb * (2048 >> 4) + off), idesc, !first);
+                                // A (query) from tensor memory: lane = row, column = k.  With both operands in shared memory the
+                                // 8 KB of operand reads per MMA plus the TMA writes saturate the 128 B/clk shared-memory port
+                                // (measured 87 cycles per MMA instead of 64).
+                                tc_mma_tf32_ts(d, tmem + (pa ? kTcAColLo : kTcAColHi) + ks * 8, td + (uint64_t)(pb * (2048 >> 4) + off), idesc, !first);
                                 first = false;
                             }
-                            tc_mma_tf32(d, qad + (uint64_t)(pa * (kTcAugBytes >> 4)), tad + (uint64_t)(pb * (kTcAugBytes >> 4)), idesc, true);
+                            tc_mma_tf32(d, qad + (uint64_t)(pa * (kTcQaBytes >> 4)), tad + (uint64_t)(pb * (kTcAugBytes >> 4)), idesc, true);
                         }
                     }
                     __syncwarp();
@@ -223,13 +225,65 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                 __syncwarp();
             }
         }
+    } else if (warp >= kTcWriterWarp0) {
+        // ======================= query writers: fp32 rows -> (hi, lo) TF32 operand in tensor memory =======================
+        const int quarter = warp & 3;
+        const int trow = quarter * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        uint32_t qseq = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const TcUnit u = tc_decode_unit(p, unit);
+            const int fq = p.frame_rows[u.q_frame];
+            const float4* qrows = reinterpret_cast<const float4*>(p.rows_f32 + (size_t)p.frame_row_off[u.q_frame] * kDim);
+            for (int qb = u.qb0; qb < u.qb1; ++qb) {
+                const int r = qb * kTile + trow;
+                float4 x[16];
+#pragma unroll
+                for (int m = 0; m < 16; ++m) x[m] = r < fq ? __ldg(qrows + (size_t)r * 16 + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float hs = 0.f;     // 1/2|q|^2 in the summation order of bank.cu's pack kernels
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    hs = __fmaf_rn(x[m].x, x[m].x, hs); hs = __fmaf_rn(x[m].y, x[m].y, hs);
+                    hs = __fmaf_rn(x[m].z, x[m].z, hs); hs = __fmaf_rn(x[m].w, x[m].w, hs);
+                }
+                const float hq = r < fq ? 0.5f * hs : kTcPadNorm;   // pad rows can never win a column
+                const float hqh = tc_tf32_hi(hq);
+                mbar_wait(emptyQ, (qseq & 1) ^ 1);      // every MMA reading the previous query operand has retired
+                ++qseq;
+                tc_fence_after();
+                *reinterpret_cast<float4*>(Qa + trow * 16) = make_float4(1.f, hqh, 0.f, 0.f);
+                *reinterpret_cast<float4*>(Qa + kTcQaBytes + trow * 16) = make_float4(0.f, hq - hqh, 0.f, 0.f);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async reads
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const float xs[8] = {x[2 * m].x, x[2 * m].y, x[2 * m].z, x[2 * m].w, x[2 * m + 1].x, x[2 * m + 1].y, x[2 * m + 1].z, x[2 * m + 1].w};
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float h = tc_tf32_hi(xs[j]);
+                        hi[j] = __float_as_uint(h);
+                        lo[j] = __float_as_uint(xs[j] - h);
+                    }
+                    tmem_st8(tmem + lane_addr + kTcAColHi + m * 8, hi);
+                    tmem_st8(tmem + lane_addr + kTcAColLo + m * 8, lo);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(fullQ);
+            }
+        }
     } else {
         // ======================= epilogue warps =======================
         const int quarter = warp & 3, part = warp >> 2;
         const int trow = quarter * 32 + lane;               // row inside the 128-row query tile (= TMEM lane)
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        auto less = [](float va, uint32_t ia, float vb2, uint32_t ib) { return va < vb2 || (va == vb2 && ia < ib); };
-        if (part == 0) sbound[trow] = kTcBoundBits;
+        if (part == 0) { sbound[trow] = kTcBoundBits; mkey[trow] = kKeyInit; mkey[kTile + trow] = kKeyInit; }
+        if (part == 1 && trow < 8) {      // the 128-byte pads behind the two augmented blocks (aliased k-chunk of the last group)
+            *reinterpret_cast<float4*>(Qa + 16 * 128 + trow * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(Qa + kTcQaBytes + 16 * 128 + trow * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");
         uint32_t g = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -344,31 +398,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                     }
                 }
                 // ---- end of the sweep for this query block: merge the column parts of every row, publish ----
-                if (part > 0) merge[(part - 1) * kTile + trow] = make_float4(t.v1, t.v2, __uint_as_float(t.i1), __uint_as_float(t.i2));
+                // 64-bit shared-memory atomics on packed keys: the smallest key ends in mkey[0], the smallest of all the
+                // "losers" (displaced old minimum, or the newcomer if it did not win) in mkey[1] = the second smallest overall.
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const uint32_t idx = e ? t.i2 : t.i1;
+                    if (idx != 0xffffffffu) {
+                        const u64 k = make_key(__float_as_uint(fmaxf(e ? t.v2 : t.v1, 0.f)), idx);
+                        const u64 old = atomicMin(&mkey[trow], k);
+                        atomicMin(&mkey[kTile + trow], old > k ? old : k);
+                    }
+                }
                 asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");
                 if (part == 0) {
-#pragma unroll
-                    for (int o = 0; o < kTcColParts - 1; ++o) {
-                        const float4 m4 = merge[o * kTile + trow];
-                        const float ov[2] = {m4.x, m4.y};
-                        const uint32_t oi[2] = {__float_as_uint(m4.z), __float_as_uint(m4.w)};
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {      // insert by (value, index): the parts hold disjoint column sets
-                            if (oi[e] != 0xffffffffu && less(ov[e], oi[e], t.v2, t.i2)) {
-                                if (less(ov[e], oi[e], t.v1, t.i1)) {
-                                    t.v2 = t.v1; t.i2 = t.i1;
-                                    t.v1 = ov[e]; t.i1 = oi[e];
-                                } else {
-                                    t.v2 = ov[e]; t.i2 = oi[e];
-                                }
-                            }
-                        }
-                    }
-                    rk1[qrow] = t.i1 == 0xffffffffu ? kKeyInit : make_key(__float_as_uint(fmaxf(t.v1, 0.f)), t.i1);
-                    rk2[qrow] = t.i2 == 0xffffffffu ? kKeyInit : make_key(__float_as_uint(fmaxf(t.v2, 0.f)), t.i2);
+                    rk1[qrow] = mkey[trow];
+                    rk2[qrow] = mkey[kTile + trow];
+                    mkey[trow] = kKeyInit;
+                    mkey[kTile + trow] = kKeyInit;
                     sbound[trow] = kTcBoundBits;
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");   // merge[] / sbound[] are reused by the next query block
+                asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");   // mkey[] / sbound[] are reused by the next query block
             }
         }
     }
@@ -380,7 +429,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
 }
 
 size_t sweep_l2_tc_smem_bytes() {
-    return 1024 + (size_t)kTcTileBytes + (size_t)kTcStages * kTcTileBytes + (size_t)kTcThrStages * kTcThrBytes + (kTcColParts - 1) * kTile * sizeof(float4) + kTile * 4 +
+    return 1024 + (size_t)2 * kTcQaBytes + (size_t)kTcStages * kTcTileBytes + (size_t)kTcThrStages * kTcThrBytes + 2 * kTile * sizeof(u64) + kTile * 4 +
            (2 + 2 * kTcStages + 2 * kTcAccStages + 2 * kTcThrStages) * 8 + 16;
 }
 
