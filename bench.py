@@ -37,7 +37,7 @@ SM_LANES_FP32 = 128      # FFMA lanes per SM per clock (verified: profiles/pipes
 POPC_LANES = 16          # POPC lanes per SM per clock (verified: profiles/pipes_r1.txt)
 
 
-TC_FLOP_PER_CMP = 3 * 72 * 2   # 3xTF32 split x (64 dims + 8 augmented columns) x 2: FLOPs the tensor cores execute per comparison
+TC_FLOP_PER_CMP = (3 * 64 + 8) * 2   # 3xTF32 split over 64 dims + one K=8 augmented step (norms), x 2: tensor FLOPs executed per comparison
 
 
 def _peaks():
@@ -364,14 +364,14 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
                 "kernel_ms": sweep_ms, "comparisons_per_launch": comps_per_launch,
                 "hbm_gbs_algorithmic": None, "traffic": None}
     if bound == "tensor":
-        # `achieved`/`frac` use the ALGORITHMIC 128 FLOP per comparison.  The tensor cores execute 3.375x that
-        # (3xTF32 split over 72 columns); `frac_executed` is that executed rate over the same peak (= tensor-pipe utilisation),
+        # `achieved`/`frac` use the ALGORITHMIC 128 FLOP per comparison.  The tensor cores execute 3.125x that
+        # (3xTF32 split over 64 dims + 8 augmented columns); `frac_executed` is that executed rate over the same peak (= tensor-pipe utilisation),
         # and `frac_of_fp32_pipe_roofline` compares the algorithmic rate with the FP32-FFMA pipe peak the FFMA engine is bound by.
         roofline["executed_tflops"] = achieved * TC_FLOP_PER_CMP / 128.0
         roofline["frac_executed"] = roofline["executed_tflops"] / peak
         roofline["frac_of_fp32_pipe_roofline"] = achieved / fp32_pipe_peak
-        roofline["note"] = ("3xTF32 split product (hi.hi + hi.lo + lo.hi over 64 dims + 8 augmented norm columns) on tcgen05; "
-                            "432 tensor FLOP executed per 128 algorithmic FLOP")
+        roofline["note"] = ("3xTF32 split product (lo.hi + hi.lo + hi.hi over 64 dims, + one K=8 step adding the norms) on tcgen05; "
+                            f"{TC_FLOP_PER_CMP} tensor FLOP executed per 128 algorithmic FLOP")
     if kind == "orb":
         # The kernel compresses the 8 xor words with carry-save adders and issues only 4 POPC per comparison, so it can
         # exceed the algorithmic 8-POPC roofline; what binds it is instruction issue (~36 warp-instructions per 32
@@ -382,8 +382,9 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
     if clocks.get("sm_mhz"):
         roofline["frac_at_sampled_clock"] = achieved / (peak * clocks["sm_mhz"] / sm_max)
     # algorithmic HBM bytes: every pair reads both frames once + writes its matches
-    # (SURF rows: 260 B in the FFMA engine's k-major bank, 640 B in the tensor-core bank = hi + lo images + augmented columns)
-    bytes_per_pair = 2 * n_feat * ((640 if engine == "tc" else 260) if kind == "surf" else 32)
+    # (SURF rows: 260 B in the FFMA engine's k-major bank; tensor-core engine: 544 B per train row = hi + lo images + augmented
+    #  columns, 256 B per query row = the fp32 rows the sweep converts on the fly)
+    bytes_per_pair = n_feat * (((544 + 256) if engine == "tc" else 520) if kind == "surf" else 64)
     roofline["hbm_gbs_algorithmic"] = (comps_per_launch / (n_feat * n_feat)) * bytes_per_pair / (sweep_ms * 1e-3) / 1e9
     roofline["hbm_peak_gbs"] = peaks.get("hbm_gbs")
     # measured DRAM traffic of this kernel on this command (one ncu pass, committed under profiles/): far BELOW the per-pair

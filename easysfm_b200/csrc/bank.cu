@@ -56,12 +56,13 @@ cudaError_t launch_pack_f32(const float* rows, const int* frame_rows, const int*
     return cudaGetLastError();
 }
 
-// F32X64 -> the tensor-core operand images of tc_layout.cuh: per 128-row tile, 16 groups x 4096 B of SWIZZLE_128B
-// hi/lo atoms plus the four (role, part) augmented arrays.  One block per tile; byte-for-byte what tc_pack_row_host writes.
+// F32X64 -> the tensor-core operand images of tc_layout.cuh: per 128-row tile one contiguous 69632-byte image = 16 groups
+// x 4096 B of SWIZZLE_128B hi/lo atoms + 16 x 256 B of augmented (train-role) columns.  One block per tile; byte-for-byte
+// what tc_pack_row_host(query_role = false) writes.
 __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ rows, const int* __restrict__ frame_rows,
                                                       const int* __restrict__ frame_row_off,
-                                                      const int* __restrict__ frame_tile_off, int n_frames, int n_groups_total,
-                                                      unsigned char* __restrict__ tc_main, unsigned char* __restrict__ tc_aug) {
+                                                      const int* __restrict__ frame_tile_off, int n_frames,
+                                                      unsigned char* __restrict__ tc_main) {
     __shared__ float tile[kTile][kDim + 4];
     const int t = blockIdx.x;
     int lo = 0, hi = n_frames - 1;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ 
     int valid = frame_rows[f] - row0;
     valid = valid < 0 ? 0 : (valid > kTile ? kTile : valid);
     const float4* src = reinterpret_cast<const float4*>(rows + ((size_t)frame_row_off[f] + row0) * kDim);
-    unsigned char* out = tc_main + (size_t)t * 16 * kTcGroupBytes;
+    unsigned char* out = tc_main + (size_t)t * kTcTileBytes;
     for (int idx = threadIdx.x; idx < kTile * (kDim / 4); idx += blockDim.x) {
         const int r = idx / (kDim / 4), c4 = idx % (kDim / 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -94,25 +95,19 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ 
 #pragma unroll 8
         for (int k = 0; k < kDim; ++k) s = __fmaf_rn(tile[r][k], tile[r][k], s);
         const float h = (r < valid) ? 0.5f * s : kTcPadNorm;
-        const float hh = tc_tf32_hi(h), hl = h - hh;
-        const size_t part = (size_t)n_groups_total * kTcAugGroupBytes;
-        unsigned char* a = tc_aug + ((size_t)t * 16 + (r >> 3)) * kTcAugGroupBytes + (r & 7) * 16;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        // query role: (1, h, 0, 0 | 0 x 4); train role: (-h, -1, 0, 0 | 0 x 4); k-chunk 1 (columns 4..7) is all zero
-        *reinterpret_cast<float4*>(a + 0 * part) = make_float4(1.f, hh, 0.f, 0.f);
-        *reinterpret_cast<float4*>(a + 1 * part) = make_float4(0.f, hl, 0.f, 0.f);
-        *reinterpret_cast<float4*>(a + 2 * part) = make_float4(-hh, -1.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(a + 3 * part) = make_float4(-hl, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(a + q * part + 128) = z;
+        float hh, hm, hl;
+        tc_split3(h, hh, hm, hl);
+        // train role: (-h_h, -h_m, -h_l, -1 | -1, -1, 0, 0) against the query's (1, 1, 1, hq_h | hq_m, hq_l, 0, 0)
+        unsigned char* a = out + kTcMainBytes + (r >> 3) * kTcAugGroupBytes + (r & 7) * 16;
+        *reinterpret_cast<float4*>(a) = make_float4(-hh, -hm, -hl, -1.f);
+        *reinterpret_cast<float4*>(a + 128) = make_float4(-1.f, -1.f, 0.f, 0.f);
     }
 }
 
 cudaError_t launch_pack_tc(const float* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
-                           int n_frames, int n_tiles_total, unsigned char* tc_main, unsigned char* tc_aug, cudaStream_t s) {
+                           int n_frames, int n_tiles_total, unsigned char* tc_main, cudaStream_t s) {
     if (n_tiles_total <= 0) return cudaSuccess;
-    pack_tc_kernel<<<n_tiles_total, 256, 0, s>>>(rows, frame_rows, frame_row_off, frame_tile_off, n_frames, n_tiles_total * 16,
-                                                 tc_main, tc_aug);
+    pack_tc_kernel<<<n_tiles_total, 256, 0, s>>>(rows, frame_rows, frame_row_off, frame_tile_off, n_frames, tc_main);
     return cudaGetLastError();
 }
 

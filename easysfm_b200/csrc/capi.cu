@@ -536,12 +536,15 @@ int ensure_scratch(esfm_ctx* ctx, const esfm_bank* b, const ChunkPlan& pl) {
 int ensure_tc_layout(esfm_ctx* ctx, esfm_bank* b) {
     if (b->d_tc || b->kind != ESFM_KIND_F32X64) return ESFM_OK;
     const int n_tiles = b->tile_off[b->n_frames];
-    const size_t groups = (size_t)n_tiles * 16;
-    b->tc_bytes = (groups + 16) * ((size_t)kTcGroupBytes + 4 * kTcAugGroupBytes);
+    b->tc_bytes = ((size_t)n_tiles + 1) * kTcTileBytes;
     cudaError_t e = cudaMallocAsync((void**)&b->d_tc, b->tc_bytes, ctx->stream);
-    if (e != cudaSuccess) { b->d_tc = nullptr; b->tc_bytes = 0; return fail(ESFM_ERR_NOMEM, "cudaMallocAsync(%zu) for the tensor-core bank failed: %s", (groups + 16) * ((size_t)kTcGroupBytes + 4 * kTcAugGroupBytes), cudaGetErrorString(e)); }
-    e = launch_pack_tc((const float*)b->d_rows, b->d_frame_rows, b->d_row_off, b->d_tile_off, b->n_frames, n_tiles, b->d_tc,
-                       b->d_tc + groups * kTcGroupBytes, ctx->stream);
+    if (e != cudaSuccess) {
+        const size_t want = b->tc_bytes;
+        b->d_tc = nullptr;
+        b->tc_bytes = 0;
+        return fail(ESFM_ERR_NOMEM, "cudaMallocAsync(%zu) for the tensor-core bank failed: %s", want, cudaGetErrorString(e));
+    }
+    e = launch_pack_tc((const float*)b->d_rows, b->d_frame_rows, b->d_row_off, b->d_tile_off, b->n_frames, n_tiles, b->d_tc, ctx->stream);
     if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "pack_tc kernel launch failed: %s", cudaGetErrorString(e));
     if (n_tiles > 0) ctx->stats.kernel_launches += 1;
     return ESFM_OK;
@@ -571,8 +574,6 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     sp.kmajor = b->d_kmajor;
     sp.rows_f32 = (const float*)b->d_rows;
     sp.tc_main = b->d_tc;
-    sp.tc_groups = b->tile_off.empty() ? 0 : b->tile_off[b->n_frames] * 16;
-    sp.tc_aug = b->d_tc ? b->d_tc + (size_t)sp.tc_groups * kTcGroupBytes : nullptr;
     sp.rows_b256 = (const uint4*)b->d_rows;
     sp.frame_rows = b->d_frame_rows;
     sp.frame_row_off = b->d_row_off;

@@ -43,9 +43,7 @@ struct SweepParams {
     const float* kmajor;        // F32X64
     const uint4* rows_b256;     // B256
     const float* rows_f32;         // F32X64 row-major rows (the TC sweep converts its query tiles from these)
-    const unsigned char* tc_main;  // F32X64, tensor-core engine: [tiles*16 groups][4096 B]  (tc_layout.cuh)
-    const unsigned char* tc_aug;   //   [4 = role*2 + part][tiles*16 groups][256 B]
-    int tc_groups;                 //   tiles*16
+    const unsigned char* tc_main;  // F32X64, tensor-core engine: [tiles][69632 B] operand images (tc_layout.cuh)
     const int* frame_rows;      // [n_frames]
     const int* frame_row_off;   // [n_frames + 1]
     const int* frame_tile_off;  // [n_frames + 1]   (F32X64, in tiles)
@@ -89,7 +87,7 @@ struct FinalizeParams {
 cudaError_t launch_pack_f32(const float* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
                             int n_frames, int n_tiles_total, float* kmajor, cudaStream_t s);
 cudaError_t launch_pack_tc(const float* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
-                           int n_frames, int n_tiles_total, unsigned char* tc_main, unsigned char* tc_aug, cudaStream_t s);
+                           int n_frames, int n_tiles_total, unsigned char* tc_main, cudaStream_t s);
 cudaError_t launch_sweep_l2(const SweepParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_sweep_l2_tc(const SweepParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_sweep_hamming(const SweepParams& p, int sm_count, cudaStream_t s);

@@ -1,7 +1,8 @@
 // tc_probe.cu -- standalone probe for the tcgen05 (kind::tf32) building blocks of sweep_l2_tc.cu.
 //
-// 1. correctness: one 128-row query tile x N train rows, K = 64 (+8 augmented: norms), 3xTF32 split
-//    (hi.hi + hi.lo + lo.hi), accumulators read back from TMEM and compared with float64 -1/2 d^2;
+// 1. correctness: one 128-row query tile x N train rows, K = 64, 3xTF32 split (hi.hi + hi.lo + lo.hi) + ONE augmented
+//    K = 8 MMA that adds the two half norms (three-way split, exact), accumulators read back from TMEM and compared
+//    with float64 -1/2 d^2;
 // 2. pacing: cycles per tcgen05.mma (M=128, N in {64,128,256}, K=8, both operands in shared memory),
 //    which decides the train-stage width of the sweep (shared-memory operand reads vs the MMA floor).
 //
@@ -29,16 +30,15 @@ using namespace esfm;
 
 template <int N>
 __global__ void __launch_bounds__(192, 1)
-probe_kernel(const uint8_t* __restrict__ q_main, const uint8_t* __restrict__ q_aug_hi, const uint8_t* __restrict__ q_aug_lo,
-             const uint8_t* __restrict__ t_main, const uint8_t* __restrict__ t_aug_hi, const uint8_t* __restrict__ t_aug_lo,
+probe_kernel(const uint8_t* __restrict__ q_img, const uint8_t* __restrict__ t_img,     // tile images of tc_layout.cuh
              float* __restrict__ out, int terms, int reps, long long* __restrict__ cycles, const float* __restrict__ q_rows, int ts_mode) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // Q: 128 rows main (16 groups x 4096) + aug hi/lo (16 x 256 each); T: N rows likewise
+    // Q: 128 rows main (16 groups x 4096) + aug (16 x 256); T: N rows likewise (groups of all tiles made contiguous)
     uint8_t* Qm = smem;                               // 64 KB
     uint8_t* Tm = Qm + 16 * kTcGroupBytes;            // N/8 * 4096
-    uint8_t* Qa = Tm + (N / 8) * kTcGroupBytes;       // aug hi, then aug lo
-    uint8_t* Ta = Qa + 2 * 16 * kTcAugGroupBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Ta + 2 * (N / 8) * kTcAugGroupBytes);
+    uint8_t* Qa = Tm + (N / 8) * kTcGroupBytes;
+    uint8_t* Ta = Qa + 16 * kTcAugGroupBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Ta + (N / 8) * kTcAugGroupBytes);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -73,14 +73,16 @@ probe_kernel(const uint8_t* __restrict__ q_main, const uint8_t* __restrict__ q_a
     if (ts_mode) { __syncthreads(); tc_fence_after(); }
 
     if (warp == 4 && lane == 0) {
-        const uint32_t bytes = (16 + N / 8) * (kTcGroupBytes + 2 * kTcAugGroupBytes);
+        const uint32_t bytes = (16 + N / 8) * (kTcGroupBytes + kTcAugGroupBytes);
         mbar_arrive_expect_tx(&bars[0], bytes);
-        bulk_g2s(Qm, q_main, 16 * kTcGroupBytes, &bars[0]);
-        bulk_g2s(Qa, q_aug_hi, 16 * kTcAugGroupBytes, &bars[0]);
-        bulk_g2s(Qa + 16 * kTcAugGroupBytes, q_aug_lo, 16 * kTcAugGroupBytes, &bars[0]);
-        bulk_g2s(Tm, t_main, (N / 8) * kTcGroupBytes, &bars[0]);
-        bulk_g2s(Ta, t_aug_hi, (N / 8) * kTcAugGroupBytes, &bars[0]);
-        bulk_g2s(Ta + (N / 8) * kTcAugGroupBytes, t_aug_lo, (N / 8) * kTcAugGroupBytes, &bars[0]);
+        bulk_g2s(Qm, q_img, kTcMainBytes, &bars[0]);
+        bulk_g2s(Qa, q_img + kTcMainBytes, kTcAugBytes, &bars[0]);
+        for (int r0 = 0; r0 < N; r0 += 128) {
+            const int g = (N - r0 < 128 ? N - r0 : 128) / 8;      // groups of this tile that are used
+            const uint8_t* img = t_img + (size_t)(r0 / 128) * kTcTileBytes;
+            bulk_g2s(Tm + (r0 / 8) * kTcGroupBytes, img, g * kTcGroupBytes, &bars[0]);
+            bulk_g2s(Ta + (r0 / 8) * kTcAugGroupBytes, img + kTcMainBytes, g * kTcAugGroupBytes, &bars[0]);
+        }
         mbar_wait(&bars[0], 0);
         tc_fence_after();
         const uint32_t idesc = tc_idesc_tf32(128, N);
@@ -90,8 +92,8 @@ probe_kernel(const uint8_t* __restrict__ q_main, const uint8_t* __restrict__ q_a
             const uint32_t d = tmem + (uint32_t)((r & 1) * N) % 512u;
             bool first = true;
             for (int term = 0; term < terms; ++term) {
-                // term 0: hi.hi   1: hi.lo   2: lo.hi     (A part, B part)
-                const int pa = term == 2 ? 1 : 0, pb = term == 1 ? 1 : 0;
+                // small terms first -- term 0: lo.hi   1: hi.lo   2: hi.hi     (A part, B part); a 1-term run is hi.hi only
+                const int pa = (terms == 3 && term == 0) ? 1 : 0, pb = (terms == 3 && term == 1) ? 1 : 0;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
                     const uint64_t da = tc_desc_sw128(qm + pa * 2048 + (ks >> 2) * 1024 + (ks & 3) * 32, kTcGroupBytes);
@@ -100,10 +102,9 @@ probe_kernel(const uint8_t* __restrict__ q_main, const uint8_t* __restrict__ q_a
                     else tc_mma_tf32(d, da, db, idesc, !first);
                     first = false;
                 }
-                const uint64_t da = tc_desc_nosw(qa + pa * 16 * kTcAugGroupBytes, 128, kTcAugGroupBytes);
-                const uint64_t db = tc_desc_nosw(ta + pb * (N / 8) * kTcAugGroupBytes, 128, kTcAugGroupBytes);
-                tc_mma_tf32(d, da, db, idesc, true);
             }
+            // the half norms: one K = 8 MMA over the three-way split augmented columns
+            tc_mma_tf32(d, tc_desc_nosw(qa, 128, kTcAugGroupBytes), tc_desc_nosw(ta, 128, kTcAugGroupBytes), idesc, true);
         }
         tc_commit(&bars[1]);
         mbar_wait(&bars[1], 0);
@@ -150,29 +151,24 @@ static int run(int terms, int reps, bool check, int ts_mode = 0) {
     // make a few near-duplicates so small distances are exercised
     for (int k = 0; k < 64; ++k) t[(size_t)3 * 64 + k] = q[(size_t)5 * 64 + k];
     for (int k = 0; k < 64; ++k) t[(size_t)7 * 64 + k] = q[(size_t)9 * 64 + k] * (1.f + 1e-3f * (k & 1));
-    std::vector<uint8_t> qm(16 * kTcGroupBytes), tm((N / 8) * kTcGroupBytes);
-    std::vector<uint8_t> qa(2 * 16 * kTcAugGroupBytes), ta(2 * (N / 8) * kTcAugGroupBytes);
-    for (int r = 0; r < 128; ++r)
-        tc_pack_row_host(q.data() + (size_t)r * 64, true, true, qm.data(), qa.data(), qa.data() + 16 * kTcAugGroupBytes, r);
+    const int t_tiles = (N + 127) / 128;
+    std::vector<uint8_t> qm(kTcTileBytes), tm((size_t)t_tiles * kTcTileBytes);
+    for (int r = 0; r < 128; ++r) tc_pack_row_host(q.data() + (size_t)r * 64, true, true, qm.data(), r);
     for (int r = 0; r < N; ++r)
-        tc_pack_row_host(t.data() + (size_t)r * 64, true, false, tm.data(), ta.data(), ta.data() + (N / 8) * kTcAugGroupBytes, r);
-    uint8_t *dqm, *dtm, *dqa, *dta;
+        tc_pack_row_host(t.data() + (size_t)r * 64, true, false, tm.data() + (size_t)(r / 128) * kTcTileBytes, r % 128);
+    uint8_t *dqm, *dtm;
     float* dout;
     float* dq;
     long long* dcyc;
     CK(cudaMalloc(&dq, q.size() * 4));
     CK(cudaMemcpy(dq, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&dqm, qm.size())); CK(cudaMalloc(&dtm, tm.size()));
-    CK(cudaMalloc(&dqa, qa.size())); CK(cudaMalloc(&dta, ta.size()));
     CK(cudaMalloc(&dout, (size_t)128 * N * 4)); CK(cudaMalloc(&dcyc, 8));
     CK(cudaMemcpy(dqm, qm.data(), qm.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dtm, tm.data(), tm.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dqa, qa.data(), qa.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dta, ta.data(), ta.size(), cudaMemcpyHostToDevice));
-    const size_t smem = (16 + N / 8) * (kTcGroupBytes + 2 * kTcAugGroupBytes) + 64;
+    const size_t smem = (16 + N / 8) * (kTcGroupBytes + kTcAugGroupBytes) + 64;
     CK(cudaFuncSetAttribute(probe_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    probe_kernel<N><<<1, 192, smem>>>(dqm, dqa, dqa + 16 * kTcAugGroupBytes, dtm, dta, dta + (N / 8) * kTcAugGroupBytes, dout,
-                                     terms, reps, dcyc, dq, ts_mode);
+    probe_kernel<N><<<1, 192, smem>>>(dqm, dtm, dout, terms, reps, dcyc, dq, ts_mode);
     CK(cudaDeviceSynchronize());
     long long cyc = 0;
     CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
@@ -197,10 +193,10 @@ static int run(int terms, int reps, bool check, int ts_mode = 0) {
                 }
             }
     }
-    const int mmas = reps * terms * 9;
+    const int mmas = reps * (terms * 8 + 1);
     printf("%s N=%3d terms=%d reps=%4d: %lld cycles, %.1f cycles/MMA (floor %d)%s max|err|=%.3g bad=%d\n", ts_mode ? "A-in-TMEM" : "A-in-smem", N, terms, reps, cyc,
            (double)cyc / mmas, N / 2, check ? "" : " [timing only]", maxerr, bad);
-    cudaFree(dqm); cudaFree(dtm); cudaFree(dqa); cudaFree(dta); cudaFree(dout); cudaFree(dcyc);
+    cudaFree(dqm); cudaFree(dtm); cudaFree(dout); cudaFree(dcyc);
     return bad;
 }
 

@@ -1,18 +1,22 @@
 // tc_layout.cuh -- operand layout and PTX wrappers of the tcgen05 (5th-gen tensor core) L2 sweep.
 //
-// The SURF distance is ranked as  -1/2 d^2 = q.t - 1/2|q|^2 - 1/2|t|^2  by ONE augmented inner product
-//     q' = (q_0..q_63,  1,     hq, 0 x 6)        hq = 1/2|q|^2
-//     t' = (t_0..t_63, -ht,   -1,  0 x 6)        ht = 1/2|t|^2
-// evaluated on the tensor cores as a 3xTF32 split product: every fp32 operand x is stored as
-//     hi = x rounded to TF32 (10 explicit mantissa bits),  lo = x - hi (exact in fp32; the MMA reads its top 19 bits)
-// and  q'.t' ~= hi.hi + hi.lo + lo.hi  accumulates in fp32 in tensor memory (dropped term ~2^-24 |q||t|).
+// The SURF distance is ranked as  -1/2 d^2 = q.t - 1/2|q|^2 - 1/2|t|^2.
+//   * q.t is a 3xTF32 split product: every fp32 operand x is stored as
+//         hi = x rounded to TF32 (10 explicit mantissa bits),  lo = x - hi (exact in fp32; the MMA reads its top 19 bits)
+//     and  q.t ~= lo.hi + hi.lo + hi.hi  (24 MMAs of K = 8) accumulates in fp32 in tensor memory (dropped term ~2^-22 |q||t|).
+//   * the two half norms are added by ONE more K = 8 MMA over "augmented" columns.  A half norm h is split THREE ways,
+//         h = h_h + h_m + h_l,   h_h = tf32(h), h_m = tf32(h - h_h), h_l = h - h_h - h_m   (every part exactly a TF32 number),
+//         q' = ( 1,    1,    1,   hq_h | hq_m, hq_l, 0, 0)
+//         t' = (-ht_h, -ht_m, -ht_l, -1 |  -1,   -1,  0, 0)
+//     so q'.t' = -(ht + hq) with every product exact: 25 MMAs per 128 x 128 tile instead of the 27 of a hi/lo-split aug column.
 //
-// HBM / shared-memory image ("TC bank"), per group of 8 consecutive rows of a frame:
-//   main  4096 B : [hi k0..31][hi k32..63][lo k0..31][lo k32..63], each a 1024-byte SWIZZLE_128B K-major atom
-//                  (8 rows x 128 B; 16-byte chunk c of row r stored at chunk c ^ r) -- what tcgen05.mma's shared-memory
-//                  descriptor calls layout_type 2, stride-byte-offset 4096 between 8-row groups;
-//   aug    256 B : per (role in {query, train}) x (part in {hi, lo}), the 8 augmented columns in the no-swizzle
-//                  K-major canonical form [k-chunk 2][row 8][16 B]  (leading-byte-offset 128, stride-byte-offset 256).
+// HBM / shared-memory image ("TC bank"), per 128-row tile (kTcTileBytes = 69632 contiguous bytes = one cp.async.bulk):
+//   main  16 x 4096 B : per group of 8 rows [hi k0..31][hi k32..63][lo k0..31][lo k32..63], each a 1024-byte SWIZZLE_128B
+//                  K-major atom (8 rows x 128 B; 16-byte chunk c of row r stored at chunk c ^ r) -- what tcgen05.mma's
+//                  shared-memory descriptor calls layout_type 2, stride-byte-offset 4096 between 8-row groups;
+//   aug   16 x  256 B : per group of 8 rows the 8 augmented columns (train role) in the no-swizzle K-major canonical form
+//                  [k-chunk 2][row 8][16 B]  (leading-byte-offset 128, stride-byte-offset 256).
+// The query tile's operand is built on the fly by the sweep (fp32 rows -> hi/lo in tensor memory, aug block in shared memory).
 // Frames are padded to 128 rows; pad rows are zero with hq (resp. ht) = 1e30, so every accumulator involving them is
 // <= -1e30 and can never be selected: no index masking in the kernel.
 #pragma once
@@ -24,7 +28,10 @@
 namespace esfm {
 
 constexpr int kTcGroupBytes = 4096;      // main image of one 8-row group
-constexpr int kTcAugGroupBytes = 256;    // one (role, part) augmented block of one 8-row group
+constexpr int kTcAugGroupBytes = 256;    // augmented block of one 8-row group
+constexpr int kTcMainBytes = 16 * kTcGroupBytes;              // 65536: main image of a 128-row tile
+constexpr int kTcAugBytes = 16 * kTcAugGroupBytes;            // 4096: augmented image of a 128-row tile
+constexpr int kTcTileBytes = kTcMainBytes + kTcAugBytes;      // 69632 bytes per operand tile, contiguous in HBM
 constexpr float kTcPadNorm = 1e30f;
 
 __host__ __device__ __forceinline__ float tc_tf32_hi(float x) {
@@ -47,9 +54,17 @@ __host__ __device__ __forceinline__ int tc_sw128_off(int rr, int k) { return rr 
 // byte offset of augmented column j in [0,8) of row rr inside one 256-byte no-swizzle block
 __host__ __device__ __forceinline__ int tc_aug_off(int rr, int j) { return (j >> 2) * 128 + rr * 16 + ((j & 3) << 2); }
 
-// Host reference of the packing (used by the probe and by the CPU tests of the layout); the device pack kernel in
-// bank.cu computes exactly the same bytes.  `main` / `aug_hi` / `aug_lo` point at group 0 of the destination arrays.
-inline void tc_pack_row_host(const float* x, bool valid, bool query_role, uint8_t* main, uint8_t* aug_hi, uint8_t* aug_lo, int r) {
+// three-way TF32 split of a half norm: h == hh + hm + hl exactly, each part a TF32 number
+__host__ __device__ __forceinline__ void tc_split3(float h, float& hh, float& hm, float& hl) {
+    hh = tc_tf32_hi(h);
+    const float r = h - hh;
+    hm = tc_tf32_hi(r);
+    hl = r - hm;
+}
+
+// Host reference of the packing (used by the probe); the device pack kernel in bank.cu computes exactly the same bytes.
+// `tile` points at the image of the 128-row tile that holds row r (r = row inside the tile).
+inline void tc_pack_row_host(const float* x, bool valid, bool query_role, uint8_t* tile, int r) {
     const int g = r >> 3, rr = r & 7;
     float s = 0.f;
     for (int k = 0; k < kDim; ++k) s = fmaf(x[k], x[k], s);
@@ -58,17 +73,14 @@ inline void tc_pack_row_host(const float* x, bool valid, bool query_role, uint8_
         const float v = valid ? x[k] : 0.f;
         const float hi = tc_tf32_hi(v), lo = v - hi;
         const int off = g * kTcGroupBytes + (k >> 5) * 1024 + tc_sw128_off(rr, k & 31);
-        memcpy(main + off, &hi, 4);
-        memcpy(main + off + 2048, &lo, 4);
+        memcpy(tile + off, &hi, 4);
+        memcpy(tile + off + 2048, &lo, 4);
     }
-    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (query_role) { a[0] = 1.f; a[1] = h; } else { a[0] = -h; a[1] = -1.f; }
-    for (int j = 0; j < 8; ++j) {
-        const float hi = tc_tf32_hi(a[j]), lo = a[j] - hi;
-        const int off = g * kTcAugGroupBytes + tc_aug_off(rr, j);
-        memcpy(aug_hi + off, &hi, 4);
-        memcpy(aug_lo + off, &lo, 4);
-    }
+    float hh, hm, hl;
+    tc_split3(h, hh, hm, hl);
+    float a[8] = {1.f, 1.f, 1.f, hh, hm, hl, 0.f, 0.f};
+    if (!query_role) { a[0] = -hh; a[1] = -hm; a[2] = -hl; a[3] = -1.f; a[4] = -1.f; a[5] = -1.f; }
+    for (int j = 0; j < 8; ++j) memcpy(tile + kTcMainBytes + g * kTcAugGroupBytes + tc_aug_off(rr, j), &a[j], 4);
 }
 
 #ifdef __CUDACC__
