@@ -6,7 +6,7 @@ Workload (BASELINE.json configs[3], the config the metric is quoted on): synthet
 is 499,500 image pairs = 3.2e13 comparisons (~1.5 min on one B200), so one *step* is a fixed slice of it:
   value : `pairs_per_step` consecutive pairs of this rank's block-cyclic shard of the triangle, descriptor bank
           already resident in HBM (device-resident throughput; only per-pair counts come back to the host);
-  e2e   : the public call a user makes -- esfm_bank_set_frame x M + esfm_bank_commit + esfm_match_all_pairs on M
+  e2e   : the public call a user makes -- esfm_bank_set_frame_pinned x M + esfm_bank_commit + esfm_match_all_pairs on M
           host frames (M(M-1)/2 ~ pairs_per_step), host->device upload of the frames from pinned memory and
           device->host copy of the compacted matches inside the timed region.
 Both are reported as descriptor comparisons/s (rows_q * rows_t per pair, counted once even with cross-check).
@@ -291,7 +291,7 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
         f0 = (s * e2e_frames) % max(1, n_host - e2e_frames + 1)
         b = ctx.bank(kind_id, e2e_frames)
         for k in range(e2e_frames):
-            b.set_frame(k, host_bank[f0 + k])
+            b.set_frame_pinned(k, host_bank[f0 + k])     # the step's inputs live in pinned host memory: no staging copy
         t.append(time.perf_counter())
         b.commit()
         t.append(time.perf_counter())

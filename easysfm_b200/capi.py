@@ -61,6 +61,7 @@ SIGNATURES = {
     "esfm_get_l2_engine": (c_int, [c_void_p, POINTER(c_int)]),
     "esfm_bank_create": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
     "esfm_bank_set_frame": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_size_t]),
+    "esfm_bank_set_frame_pinned": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_size_t]),
     "esfm_bank_set_frame_rows": (c_int, [c_void_p, c_int, c_int]),
     "esfm_bank_commit": (c_int, [c_void_p]),
     "esfm_bank_alloc_device": (c_int, [c_void_p]),
@@ -245,11 +246,24 @@ class Bank:
         _check(self._lib.esfm_bank_set_frame(self._h, int(frame_id), a.ctypes.data, a.shape[0], a.shape[1],
                                              a.strides[0] if a.shape[0] else a.shape[1] * a.itemsize))
 
+    def set_frame_pinned(self, frame_id: int, desc):
+        """No host-side copy: `desc` must be a C-contiguous array in page-locked memory (e.g. a view of a torch
+        pin_memory tensor) and must stay alive and unmodified until commit() returns."""
+        a = np.asarray(desc)
+        b, _ = _as_desc(a, self.kind)
+        if b is not a or (a.shape[0] and not a.flags.c_contiguous):
+            raise ValueError("set_frame_pinned needs a C-contiguous array (no implicit copy)")
+        self._pinned_refs = getattr(self, "_pinned_refs", [])
+        self._pinned_refs.append(a)
+        _check(self._lib.esfm_bank_set_frame_pinned(self._h, int(frame_id), a.ctypes.data, a.shape[0], a.shape[1],
+                                                    a.shape[1] * a.itemsize))
+
     def set_frame_rows(self, frame_id: int, rows: int):
         _check(self._lib.esfm_bank_set_frame_rows(self._h, int(frame_id), int(rows)))
 
     def commit(self):
         _check(self._lib.esfm_bank_commit(self._h))
+        self._pinned_refs = []
 
     def alloc_device(self):
         _check(self._lib.esfm_bank_alloc_device(self._h))

@@ -48,6 +48,7 @@ struct esfm_ctx {
     bool own_stream = false;
     int sm_count = 0;
     bool profiling = true;
+    int tc_qtiles = 1;                     // TC sweep geometry: query tiles per block (1 or 2; $ESFM_TC_QT)
     int l2_engine = ESFM_L2_ENGINE_TC;     // which sweep kernel serves ESFM_KIND_F32X64 (esfm_set_l2_engine / $ESFM_L2_ENGINE)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     esfm_stats_t stats{};
@@ -106,6 +107,7 @@ struct esfm_bank {
     uint8_t* h_up = nullptr;                  // pinned upload staging (borrowed from the ctx pool until commit)
     size_t h_up_cap = 0, h_up_used = 0;
     std::vector<size_t> host_off;             // per frame offset into h_up ((size_t)-1 = no host data)
+    std::vector<const void*> host_ext;        // per frame caller-owned pinned source (esfm_bank_set_frame_pinned), else nullptr
     bool committed = false;
     bool device_allocated = false;
     // device
@@ -191,6 +193,7 @@ extern "C" int esfm_init(int device, void* cuda_stream, esfm_ctx_t** out) {
     if (!ctx) return fail(ESFM_ERR_NOMEM, "esfm_init: out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* qt = getenv("ESFM_TC_QT")) ctx->tc_qtiles = atoi(qt) == 2 ? 2 : 1;
     if (const char* eng = getenv("ESFM_L2_ENGINE")) {
         if (!strcmp(eng, "tc") || !strcmp(eng, "tensor")) ctx->l2_engine = ESFM_L2_ENGINE_TC;
         else if (!strcmp(eng, "ffma")) ctx->l2_engine = ESFM_L2_ENGINE_FFMA;
@@ -288,6 +291,7 @@ extern "C" int esfm_bank_create(esfm_ctx_t* ctx, esfm_kind kind, int n_frames, e
     b->n_frames = n_frames;
     b->rows.assign(n_frames, -1);
     b->host_off.assign(n_frames, (size_t)-1);
+    b->host_ext.assign(n_frames, nullptr);
     *out = b;
     return ESFM_OK;
 }
@@ -329,7 +333,35 @@ extern "C" int esfm_bank_set_frame(esfm_bank_t* b, int frame_id, const void* dat
         for (int r = 0; r < rows; ++r) memcpy(dst + (size_t)r * rb, (const uint8_t*)data + (size_t)r * step_bytes, rb);
     }
     b->host_off[frame_id] = b->h_up_used;
+    b->host_ext[frame_id] = nullptr;
     b->h_up_used += need;
+    b->rows[frame_id] = rows;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_bank_set_frame_pinned(esfm_bank_t* b, int frame_id, const void* data, int rows, int cols, size_t step_bytes) {
+    if (!b) return fail(ESFM_ERR_INVALID, "bank is NULL");
+    if (b->committed || b->device_allocated) return fail(ESFM_ERR_STATE, "esfm_bank_set_frame_pinned: bank already committed");
+    if (frame_id < 0 || frame_id >= b->n_frames) return fail(ESFM_ERR_INVALID, "frame_id %d out of range [0,%d)", frame_id, b->n_frames);
+    if (rows < 0) return fail(ESFM_ERR_INVALID, "rows < 0");
+    const int want_cols = b->kind == ESFM_KIND_F32X64 ? kDim : 32;
+    if (rows > 0 && cols != want_cols)
+        return fail(ESFM_ERR_INVALID, "kind %d needs %d columns per descriptor, got %d", b->kind, want_cols, cols);
+    if (rows > 0 && !data) return fail(ESFM_ERR_INVALID, "data is NULL with rows > 0");
+    if (rows > 0 && step_bytes != b->row_bytes())
+        return fail(ESFM_ERR_INVALID, "esfm_bank_set_frame_pinned needs densely packed rows (step_bytes %zu != %zu)", step_bytes, b->row_bytes());
+    if (int rc = check_frame_limits(b, rows)) return rc;
+    if (rows > 0) {
+        if (int rc = set_device(b->ctx)) return rc;
+        cudaPointerAttributes at{};
+        const cudaError_t e = cudaPointerGetAttributes(&at, data);
+        if (e != cudaSuccess || at.type != cudaMemoryTypeHost) {
+            cudaGetLastError();
+            return fail(ESFM_ERR_INVALID, "esfm_bank_set_frame_pinned: frame %d is not in page-locked host memory", frame_id);
+        }
+    }
+    b->host_off[frame_id] = (size_t)-1;
+    b->host_ext[frame_id] = rows > 0 ? data : nullptr;
     b->rows[frame_id] = rows;
     return ESFM_OK;
 }
@@ -342,6 +374,7 @@ extern "C" int esfm_bank_set_frame_rows(esfm_bank_t* b, int frame_id, int rows) 
     if (int rc = check_frame_limits(b, rows)) return rc;
     b->rows[frame_id] = rows;
     b->host_off[frame_id] = (size_t)-1;
+    b->host_ext[frame_id] = nullptr;
     return ESFM_OK;
 }
 
@@ -409,7 +442,7 @@ extern "C" int esfm_bank_commit(esfm_bank_t* b) {
     if (b->committed) return fail(ESFM_ERR_STATE, "bank already committed");
     if (!b->device_allocated) {
         for (int f = 0; f < b->n_frames; ++f)
-            if (b->rows[f] > 0 && b->host_off[f] == (size_t)-1)
+            if (b->rows[f] > 0 && b->host_off[f] == (size_t)-1 && !b->host_ext[f])
                 return fail(ESFM_ERR_STATE, "frame %d has rows declared but no host data; use esfm_bank_alloc_device + esfm_bank_commit_device", f);
         if (int rc = bank_alloc_layout(b)) return rc;
     }
@@ -419,13 +452,14 @@ extern "C" int esfm_bank_commit(esfm_bank_t* b) {
     if (total > 0) {
         bool in_order = b->h_up_used == total;
         for (int f = 0; f < b->n_frames && in_order; ++f)
-            if (b->rows[f] > 0 && b->host_off[f] != (size_t)b->row_off[f] * rb) in_order = false;
+            if (b->rows[f] > 0 && (b->host_ext[f] || b->host_off[f] != (size_t)b->row_off[f] * rb)) in_order = false;
         if (in_order) {   // one pinned -> device copy
             CUDA_TRY(cudaMemcpyAsync(b->d_rows, b->h_up, total, cudaMemcpyHostToDevice, ctx->stream));
         } else {          // frames were set out of order (or re-set): one copy per frame
             for (int f = 0; f < b->n_frames; ++f)
-                if (b->rows[f] > 0)
-                    CUDA_TRY(cudaMemcpyAsync((uint8_t*)b->d_rows + (size_t)b->row_off[f] * rb, b->h_up + b->host_off[f],
+                if (b->rows[f] > 0)     // caller-owned pinned source (no staging copy was made) or the staging buffer
+                    CUDA_TRY(cudaMemcpyAsync((uint8_t*)b->d_rows + (size_t)b->row_off[f] * rb,
+                                             b->host_ext[f] ? (const uint8_t*)b->host_ext[f] : b->h_up + b->host_off[f],
                                              (size_t)b->rows[f] * rb, cudaMemcpyHostToDevice, ctx->stream));
         }
         ctx->stats.h2d_bytes += total;
@@ -586,6 +620,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     sp.stride = pl.stride;
     sp.col_cap = pl.col_cap;
     if (const char* dbg = getenv("ESFM_TC_DEBUG")) sp.debug_flags = atoi(dbg);
+    sp.tc_qtiles = ctx->tc_qtiles;
     if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
     cudaError_t e = b->kind == ESFM_KIND_F32X64 ? (tc ? launch_sweep_l2_tc(sp, ctx->sm_count, ctx->stream)
                                                       : launch_sweep_l2(sp, ctx->sm_count, ctx->stream))

@@ -53,9 +53,10 @@ struct SweepParams {
     int units_per_pair;         // query-range split factor S (>= 1)
     // scratch
     u64* keys;                  // [n_pairs][4][stride]
-    uint32_t* col_thr;          // [n_pairs][stride] running column thresholds (float bits), L2 sweep only
+    uint32_t* col_thr;          // [n_pairs][stride] running column thresholds (float bits), L2 sweeps only
     int stride;                 // keys per array (>= padded rows of the largest frame in the chunk)
     int col_cap;                // Hamming sweep: smem column-minimum capacity in entries
+    int tc_qtiles;              // TC sweep geometry: query tiles per block, 1 or 2 ($ESFM_TC_QT)
     int debug_flags;            // TC sweep pipeline probes ($ESFM_TC_DEBUG; results are WRONG when set): 1 = epilogue only drains,
                                 // 2 = no MMAs issued, 4 = no train-tile loads
 };

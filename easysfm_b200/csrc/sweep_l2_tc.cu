@@ -34,13 +34,25 @@ namespace {
 constexpr int kTcColParts = 4;                          // column quarters of a train tile, one per epilogue warp of a lane quarter
 constexpr int kTcEpiWarps = 4 * kTcColParts;            // 16 epilogue warps: enough to hide the epilogue's dependent-issue latency
 constexpr int kTcEpiThreads = kTcEpiWarps * 32;
-constexpr int kTcThreads = kTcEpiThreads + 64 + 128;    // + TMA producer warp + MMA issuer warp + 4 query-writer warps
-constexpr int kTcWriterWarp0 = kTcEpiWarps + 2;         // warps 18..21: warp % 4 covers the four TMEM lane quarters
-constexpr int kTcQTiles = 2;                            // query tiles per block: each train tile in shared memory is used twice
-constexpr uint32_t kTcACol0 = 256;                      // tensor-memory columns of query tile h: 256 + 128 h (hi 64 | lo 64)
+constexpr int kTcThreads = kTcEpiThreads + 256;         // + 2 service warpgroups: TMA producer, MMA issuer, (2 idle), 4 query writers
+constexpr int kTcWriterWarp0 = kTcEpiWarps + 4;         // warps 20..23: warp % 4 covers the four TMEM lane quarters
+// setmaxnreg works on whole warpgroups: the kernel launches at 80 registers/thread (768 threads), the two service
+// warpgroups shrink to 40 and the four epilogue warpgroups grow to 96 (32 accumulator columns + 8 group maxima + thresholds
+// live at once).  setmaxnreg.inc can only take what setmaxnreg.dec of the SAME CTA released (the unallocated rest of the
+// register file is not in the pool -- asking for more blocks forever), hence the balance check.
+constexpr int kTcLaunchRegs = 80, kTcEpiRegs = 96, kTcServiceRegs = 40;
+static_assert(256 * (kTcLaunchRegs - kTcServiceRegs) >= kTcEpiThreads * (kTcEpiRegs - kTcLaunchRegs), "setmaxnreg pool would deadlock");
+static_assert(kTcThreads * kTcLaunchRegs <= 65536 && (65536 / kTcThreads) / 8 * 8 == kTcLaunchRegs, "launch register count drifted");
 constexpr int kTcPartCols = kTile / kTcColParts;        // 32 columns per epilogue thread and stage
 constexpr int kTcStages = 3;                 // shared-memory train stages (68 KB each)
-constexpr int kTcAccStages = 2;              // tensor-memory accumulator stages (128 columns each; columns 256..511 hold the query operands)
+// Geometry variants (template parameter QT = query tiles per block): tensor memory has 512 columns = QT x 128 of query
+// operand (hi 64 | lo 64 per tile) + the accumulator stages (128 columns each).
+//   QT = 1: 3 accumulator stages; every train tile in shared memory feeds one accumulator.
+//   QT = 2: 2 accumulator stages; every train tile feeds two accumulators (half the L2 -> shared-memory traffic and power).
+template <int QT> struct TcGeom {
+    static constexpr int kAccStages = 4 - QT;
+    static constexpr uint32_t kACol0 = 128u * (4 - QT);     // tensor-memory column of query tile 0's operand
+};
 constexpr int kTcThrBytes = kTile * 4;                  // 512: column thresholds riding with a train tile
 constexpr int kTcThrStages = 4;                         // threshold snapshots have their own (deeper) ring
 constexpr uint32_t kTcBoundBits = 0x6f6f6f6fu;          // 7.4e28f: "no bound yet" (what memset(0x6f) writes); pads are 1e30
@@ -66,48 +78,59 @@ __device__ __forceinline__ TcUnit tc_decode_unit(const SweepParams& p, int unit)
     return u;
 }
 
+// Watchdog of every barrier wait: 4 s on one barrier is certainly a pipeline deadlock; trap, so that it surfaces as a launch
+// failure instead of a hung GPU (the wall clock is only read every 1024 polls).
+__device__ __forceinline__ void tc_watchdog(uint32_t& polls, unsigned long long& t0) {
+    if ((++polls & 0x3ffu) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000ull) __trap();
+    }
+}
+
 struct RowTop2 {
     float v1, v2;        // 1/2 d^2 of the best / second best so far
     uint32_t i1, i2;
 };
 
-// Wait of the single producer / MMA-issuing lanes: each shares an SM sub-partition with four epilogue warps, so a tight
-// try_wait loop (measured: 3 issue slots every ~7 cycles) steals a large part of their issue bandwidth, while the 2 us
-// back-off of the FFMA sweep's producer is longer than a whole tile here (~1 us) and starves the tensor pipe.  Poll every
-// few tens of nanoseconds instead.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
+// Barrier waits.  Every waiting warp shares an SM sub-partition with four epilogue warps, and a polling loop is not free:
+// with try_wait + 40 ns sleeps the six service warps and the parked epilogue warps together executed > 40 % of all
+// instructions of the kernel (ncu source page), taken from the issue slots of the warps that had work.  (The suspend-time
+// hint of try_wait does not park a warp for anything near the hinted time.)  So every role sleeps between polls for as long
+// as its place in the pipeline tolerates: SLEEP_NS is a template argument.
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+template <int SLEEP_NS>
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0, polls = 0;
+    unsigned long long t0 = 0;
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (ok) break;
-        __nanosleep(40);
+        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+        tc_watchdog(polls, t0);
     }
 }
-
-// Wait of the epilogue warps: let the hardware park the warp (suspend-time hint) instead of spinning on try_wait -- the
-// spin loop was 21 % of all executed instructions, taken from the issue slots of the warps that had work.
-__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(100000u)
-            : "memory");
-    } while (!ok);
-}
+// Measured: sleeping 60-200 ns in the producer / issuer / epilogue waits costs 3 % (wake-up latency sits on the pipeline's
+// critical path), so those keep polling; the four writer warps do not poll at all (named barrier, see below).
+constexpr int kTcSleepProducer = 40;
+constexpr int kTcSleepIssuer = 40;
+constexpr int kTcSleepEpilogue = 0;
 
 }  // namespace
 
+template <int kTcQTiles>
 __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepParams p) {
+    constexpr int kTcAccStages = TcGeom<kTcQTiles>::kAccStages;
+    constexpr uint32_t kTcACol0 = TcGeom<kTcQTiles>::kACol0;
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -118,8 +141,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     uint32_t* sbound = reinterpret_cast<uint32_t*>(mkey + kTcQTiles * 2 * kTile);  // [tile h][128] row bound shared by a row's parts
     uint64_t* bars = reinterpret_cast<uint64_t*>(sbound + kTcQTiles * kTile);
     uint64_t* fullQ = bars;                      // [kTcQTiles]
-    uint64_t* emptyQ = fullQ + kTcQTiles;        // [kTcQTiles]
-    uint64_t* fullT = emptyQ + kTcQTiles;
+    uint64_t* fullT = fullQ + kTcQTiles;
     uint64_t* emptyT = fullT + kTcStages;
     uint64_t* accFull = emptyT + kTcStages;
     uint64_t* accEmpty = accFull + kTcAccStages;
@@ -133,7 +155,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     if (threadIdx.x == 0) {
         for (int h = 0; h < kTcQTiles; ++h) {
             mbar_init(&fullQ[h], 4);                  // the 4 query-writer warps
-            mbar_init(&emptyQ[h], 1);                 // MMA commit
         }
         for (int s = 0; s < kTcStages; ++s) {
             mbar_init(&fullT[s], 1);
@@ -155,6 +176,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    if (warp >= kTcEpiWarps) {
+    reg_dealloc<kTcServiceRegs>();
     if (warp == kTcEpiWarps) {
         // ======================= TMA producer =======================
         if (lane == 0) {
@@ -166,7 +189,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                 for (int qt = u.qb0; qt < u.qb1; qt += kTcQTiles) {
                     for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                         const uint32_t st = g % kTcStages, ph = (g / kTcStages) & 1;
-                        mbar_wait_relaxed(&emptyT[st], ph ^ 1);
+                        mbar_wait_sleep<kTcSleepProducer>(&emptyT[st], ph ^ 1);
                         mbar_arrive_expect_tx(&fullT[st], kTcTileBytes);
                         if (p.debug_flags & 4)
                             asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&fullT[st])), "r"(kTcTileBytes) : "memory");
@@ -175,7 +198,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                         // the running column thresholds of this tile ride along in their own ring (a snapshot a few tiles
                         // old is fine: a stale threshold is only looser, never wrong)
                         const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
-                        mbar_wait_relaxed(&thrEmpty[ts], tph ^ 1);
+                        mbar_wait_sleep<kTcSleepProducer>(&thrEmpty[ts], tph ^ 1);
                         mbar_arrive_expect_tx(&thrFull[ts], kTcThrBytes);
                         bulk_g2s(Thr + ts * kTcThrBytes, tauc + (size_t)tt * kTile, kTcThrBytes, &thrFull[ts]);
                     }
@@ -200,15 +223,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                 const int nh = min(kTcQTiles, u.qb1 - qt);
                 for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                     const uint32_t st = g % kTcStages, ph = (g / kTcStages) & 1;
-                    mbar_wait_relaxed(&fullT[st], ph);
+                    mbar_wait_sleep<kTcSleepIssuer>(&fullT[st], ph);
                     // descriptor start addresses are in 16-byte units: adding (bytes >> 4) to the low word moves the window
                     const uint64_t td = td0 + (uint64_t)(st * (kTcTileBytes >> 4));
                     const uint64_t tad = tad0 + (uint64_t)(st * (kTcTileBytes >> 4));
 #pragma unroll 1
                     for (int h = 0; h < nh; ++h, ++a) {
                         const uint32_t as = a % kTcAccStages, aph = (a / kTcAccStages) & 1;
-                        if (tt == 0) mbar_wait_relaxed(&fullQ[h], (h == 0 ? qn0 : qn1) & 1);   // the writers have filled slot h for this block
-                        mbar_wait_relaxed(&accEmpty[as], aph ^ 1);
+                        if (tt == 0) mbar_wait_sleep<kTcSleepIssuer>(&fullQ[h], (h == 0 ? qn0 : qn1) & 1);   // the writers have filled slot h for this block
+                        mbar_wait_sleep<kTcSleepIssuer>(&accEmpty[as], aph ^ 1);
                         tc_fence_after();
                         const uint32_t d = tmem + as * 128;
                         const uint32_t acol = tmem + kTcACol0 + h * 128;
@@ -234,7 +257,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                         __syncwarp();
                         if (elect_one()) {
                             tc_commit(&accFull[as]);                        // accumulator stage ready for the epilogue
-                            if (tt == u.ntt - 1) tc_commit(&emptyQ[h]);     // query tile h may be overwritten once these MMAs retire
                             if (h == nh - 1) tc_commit(&emptyT[st]);        // shared-memory stage consumed
                         }
                         __syncwarp();
@@ -249,7 +271,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
         const int quarter = warp & 3;
         const int trow = quarter * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        uint32_t quse[kTcQTiles] = {0, 0};
+        uint32_t quse[2] = {0, 0};
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const TcUnit u = tc_decode_unit(p, unit);
             const int fq = p.frame_rows[u.q_frame];
@@ -257,20 +279,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
             for (int qt = u.qb0; qt < u.qb1; ++qt) {
                 const int h = (qt - u.qb0) & (kTcQTiles - 1);
                 const int r = qt * kTile + trow;
-                float4 x[16];
-#pragma unroll
-                for (int m = 0; m < 16; ++m) x[m] = r < fq ? __ldg(qrows + (size_t)r * 16 + m) : make_float4(0.f, 0.f, 0.f, 0.f);
-                float hs = 0.f;     // 1/2|q|^2 in the summation order of bank.cu's pack kernels
-#pragma unroll
+                const bool valid = r < fq;
+                const float4* xr = qrows + (size_t)(valid ? r : 0) * 16;
+                // pass 1: 1/2|q|^2 in the summation order of bank.cu's pack kernels (few live registers: this warpgroup runs at 40)
+                float hs = 0.f;
+#pragma unroll 4
                 for (int m = 0; m < 16; ++m) {
-                    hs = __fmaf_rn(x[m].x, x[m].x, hs); hs = __fmaf_rn(x[m].y, x[m].y, hs);
-                    hs = __fmaf_rn(x[m].z, x[m].z, hs); hs = __fmaf_rn(x[m].w, x[m].w, hs);
+                    const float4 x = __ldg(xr + m);
+                    hs = __fmaf_rn(x.x, x.x, hs); hs = __fmaf_rn(x.y, x.y, hs);
+                    hs = __fmaf_rn(x.z, x.z, hs); hs = __fmaf_rn(x.w, x.w, hs);
                 }
-                const float hq = r < fq ? 0.5f * hs : kTcPadNorm;   // pad rows can never win a column
+                const float hq = valid ? 0.5f * hs : kTcPadNorm;   // pad rows can never win a column
                 float hqh, hqm, hql;
                 tc_split3(hq, hqh, hqm, hql);
                 const uint32_t use = h == 0 ? quse[0] : quse[1];
-                mbar_wait(&emptyQ[h], (use & 1) ^ 1);      // every MMA reading the previous tile in this slot has retired
+                // Slot h is free once every MMA that read its previous tile has retired.  The writers do not poll for that (four
+                // warps polling an mbarrier for a whole query block were 20 % of all executed instructions; __nanosleep does not
+                // sleep anywhere near the requested time): they block on NAMED BARRIER 2 + h, which epilogue warp 0 arrives at
+                // as soon as it has seen the accumulator of the block's last (train tile, slot h) job complete.
+                if (use > 0) named_bar_sync(2 + h, 128 + 32);
                 if (h == 0) ++quse[0]; else ++quse[1];
                 tc_fence_after();
                 unsigned char* qa = Qa + h * kTcAugBytes + (trow >> 3) * kTcAugGroupBytes + (trow & 7) * 16;
@@ -278,9 +305,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                 *reinterpret_cast<float4*>(qa + 128) = make_float4(hqm, hql, 0.f, 0.f);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async reads
                 const uint32_t acol = tmem + lane_addr + kTcACol0 + h * 128;
-#pragma unroll
+                // pass 2: the row again (L1/L2 hit), 8 dims at a time -> hi / lo columns of tensor memory
+#pragma unroll 2
                 for (int m = 0; m < 8; ++m) {
-                    const float xs[8] = {x[2 * m].x, x[2 * m].y, x[2 * m].z, x[2 * m].w, x[2 * m + 1].x, x[2 * m + 1].y, x[2 * m + 1].z, x[2 * m + 1].w};
+                    float4 x0 = __ldg(xr + 2 * m), x1 = __ldg(xr + 2 * m + 1);
+                    if (!valid) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }
+                    const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                     uint32_t hi[8], lo[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -297,8 +327,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                 if (lane == 0) mbar_arrive(&fullQ[h]);
             }
         }
+        // the epilogue arrives once per (block, slot); the last arrival of each slot has no refill waiting for it
+        if (quse[0] > 0) named_bar_sync(2, 128 + 32);
+        if (kTcQTiles == 2 && quse[1] > 0) named_bar_sync(3, 128 + 32);
+    }
     } else {
         // ======================= epilogue warps =======================
+        reg_alloc<kTcEpiRegs>();
         const int quarter = warp & 3, part = warp >> 2;
         const int trow = quarter * 32 + lane;               // row inside a 128-row query tile (= TMEM lane)
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -323,21 +358,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                 t.i1 = t.i2 = to.i1 = to.i2 = 0xffffffffu;
                 for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                     const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
-                    mbar_wait_parked(&thrFull[ts], tph);
+                    mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);
                     const float4* tp = reinterpret_cast<const float4*>(Thr + ts * kTcThrBytes) + part * (kTcPartCols / 4);
 #pragma unroll 1
                     for (int h = 0; h < nh; ++h, ++a) {
                         const uint32_t as = a % kTcAccStages, aph = (a / kTcAccStages) & 1;
                         const uint32_t qrow = (uint32_t)((qt + h) * kTile + trow);     // frame row of this thread
                         uint32_t* sb = &sbound[h * kTile + trow];
-                        mbar_wait_parked(&accFull[as], aph);
+                        mbar_wait_sleep<kTcSleepEpilogue>(&accFull[as], aph);
+                        if (warp == 0 && tt == u.ntt - 1) named_bar_arrive(2 + h, 128 + 32);   // slot h may be refilled (see the writers)
                         tc_fence_after();
-                        const uint32_t taddr = tmem + lane_addr + as * 128 + part * kTcPartCols;
                         // All 32 columns of this thread go to registers at once and the accumulator stage is released right
-                        // away: with only two stages the tensor pipe must never wait for the selection logic below.
-                        uint32_t vb[16], vn[16];
-                        tmem_ld16(taddr, vb);
-                        tmem_ld16(taddr + 16, vn);
+                        // away: the tensor pipe never waits for the selection logic below.
+                        uint32_t vb[32];
+                        tmem_ld32(tmem + lane_addr + as * 128 + part * kTcPartCols, vb);
                         // The row's running second best over ALL column parts (each part keeps a private top-2; the shared
                         // bound only filters, with '>=' so equal values still reach the private strict-'<' insertion).
                         float nb = -__uint_as_float(*reinterpret_cast<volatile uint32_t*>(sb));
@@ -345,100 +379,101 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&accEmpty[as]);
-                        // columns in chunks of 16: a real loop, so the epilogue body stays small enough for the instruction
-                        // cache (a fully unrolled 64-column body was 64 KB of SASS and stalled on instruction fetch)
-#pragma unroll 1
-                        for (int ch = 0; ch < kTcPartCols / 16; ++ch) {
-                            if (ch > 0) {
+                        if (p.debug_flags & 1) continue;
+                        float v[32];
 #pragma unroll
-                                for (int c = 0; c < 16; ++c) vb[c] = vn[c];     // second half of the columns
-                            }
-                            float thr[16];
+                        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(vb[c]);   // v = -1/2 d^2
+                        // ---- fast path: maxima of 8 groups of 4 columns -> one row test; 4 chains of 8 column tests; ONE vote ----
+                        float gm[8];
 #pragma unroll
-                            for (int m = 0; m < 4; ++m) {
-                                const float4 x = tp[ch * 4 + m];
-                                thr[4 * m] = x.x; thr[4 * m + 1] = x.y; thr[4 * m + 2] = x.z; thr[4 * m + 3] = x.w;
-                            }
-                            if (ch == kTcPartCols / 16 - 1 && h == nh - 1) {      // last read of this threshold snapshot
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(&thrEmpty[ts]);
-                            }
-                            float v[16];
+                        for (int gq = 0; gq < 8; ++gq)
+                            gm[gq] = fmaxf(fmaxf(fmaxf(v[4 * gq], v[4 * gq + 1]), v[4 * gq + 2]), v[4 * gq + 3]);
+                        const float rmax = fmaxf(fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), fmaxf(fmaxf(gm[3], gm[4]), gm[5])), fmaxf(gm[6], gm[7]));
+                        const bool rflag = rmax >= nb;
+                        // (A pre-test on one threshold per group of 4 columns -- 8 compares and 2 loads instead of 32 and 8 -- was
+                        // tried and lost 15 %: the loosest of four thresholds lets far too many rows through to the slow path.)
+                        bool cf[4];
 #pragma unroll
-                            for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(vb[c]);   // v = -1/2 d^2
-                            if (p.debug_flags & 1) continue;
-                            // ---- fast path (~40 instructions): one row test + 16 column tests + ONE vote ----
-                            float gmx[4];
-#pragma unroll
-                            for (int gq = 0; gq < 4; ++gq)
-                                gmx[gq] = fmaxf(fmaxf(fmaxf(v[4 * gq], v[4 * gq + 1]), v[4 * gq + 2]), v[4 * gq + 3]);
-                            const bool rflag = fmaxf(fmaxf(fmaxf(gmx[0], gmx[1]), gmx[2]), gmx[3]) >= nb;
-                            bool cflag = false;
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) cflag |= (v[j] >= -thr[j]);
-                            if (!__any_sync(0xffffffffu, rflag || cflag)) continue;
-
+                        for (int cq = 0; cq < 4; ++cq) {
+                            const float4 x0 = tp[2 * cq], x1 = tp[2 * cq + 1];
+                            cf[cq] = (v[8 * cq] >= -x0.x) | (v[8 * cq + 1] >= -x0.y) | (v[8 * cq + 2] >= -x0.z) | (v[8 * cq + 3] >= -x0.w) |
+                                     (v[8 * cq + 4] >= -x1.x) | (v[8 * cq + 5] >= -x1.y) | (v[8 * cq + 6] >= -x1.z) | (v[8 * cq + 7] >= -x1.w);
+                        }
+                        const bool cflag = cf[0] | cf[1] | cf[2] | cf[3];
+                        if (__any_sync(0xffffffffu, rflag || cflag)) {
                             // ---- slow path: ~2 ln F hits per row and ~ln F per column over a whole sweep ----
-                            const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols + ch * 16);
-                            if (rflag) {
-                                bool ins = false;
-#pragma unroll
-                                for (int gq = 0; gq < 4; ++gq) {
-                                    if (gmx[gq] >= nb) {
-#pragma unroll
-                                        for (int j = 0; j < 4; ++j) {
-                                            const float d = -v[4 * gq + j];
-                                            if (d < t.v2) {     // ascending column order + strict '<' keeps the lowest index on ties
-                                                const uint32_t idx = col0 + 4 * gq + j;
-                                                if (d < t.v1) {
-                                                    t.v2 = t.v1; t.i2 = t.i1;
-                                                    t.v1 = d;    t.i1 = idx;
-                                                } else {
-                                                    t.v2 = d;    t.i2 = idx;
-                                                }
-                                                ins = true;
-                                            }
-                                        }
-                                    }
-                                }
-                                if (ins) {
-                                    atomicMin(sb, __float_as_uint(fmaxf(t.v2, 0.f)));
-                                    nb = fmaxf(nb, -t.v2);
-                                }
-                            }
+                            const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols);
+                            // columns first (the row insertion below retires elements of v[])
                             if (__any_sync(0xffffffffu, cflag)) {
 #pragma unroll
-                                for (int gq = 0; gq < 2; ++gq) {
-                                    bool any = false;
+                                for (int cq = 0; cq < 4; ++cq) {
+                                    if (__any_sync(0xffffffffu, cf[cq])) {
+                                        // which of the chain's 8 columns have a hit in some lane (warp-uniform mask), then ONE shared
+                                        // event body in a loop: 32 unrolled copies of it were 19 KB of rarely executed code
+                                        const float* thp = reinterpret_cast<const float*>(tp) + 8 * cq;
+                                        uint32_t pend = 0;
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) any |= (v[8 * gq + j] >= -thr[8 * gq + j]);
-                                    if (__any_sync(0xffffffffu, any)) {
-#pragma unroll
-                                        for (int j = 0; j < 8; ++j) {
-                                            const bool hit = v[8 * gq + j] >= -thr[8 * gq + j];
-                                            const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-                                            if (bal) {     // warp-uniform
-                                                const uint32_t bits = hit ? __float_as_uint(fmaxf(-v[8 * gq + j], 0.f)) : 0xffffffffu;
-                                                const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
-                                                const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
-                                                if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
-                                                    uint32_t gcol = col0 + 8 * gq + j;
-                                                    asm volatile("" : "+r"(gcol));   // keep the 64-bit address arithmetic inside this (rare) branch
-                                                    atomicMin(ck1 + gcol, make_key(mn, qrow));
-                                                    atomicMin(tauc + gcol, mn);
-                                                }
+                                        for (int j = 0; j < 8; ++j)
+                                            if (__any_sync(0xffffffffu, v[8 * cq + j] >= -thp[j])) pend |= 1u << j;
+#pragma unroll 1
+                                        while (pend) {
+                                            const int j = __ffs(pend) - 1;
+                                            pend &= pend - 1;
+                                            // v[8 cq + j] for a warp-uniform j: three levels of selects
+                                            const bool s0 = j & 1, s1 = j & 2, s2 = j & 4;
+                                            const float a0 = s0 ? v[8 * cq + 1] : v[8 * cq], a1 = s0 ? v[8 * cq + 3] : v[8 * cq + 2];
+                                            const float a2 = s0 ? v[8 * cq + 5] : v[8 * cq + 4], a3 = s0 ? v[8 * cq + 7] : v[8 * cq + 6];
+                                            const float b0 = s1 ? a1 : a0, b1 = s1 ? a3 : a2;
+                                            const float x = s2 ? b1 : b0;
+                                            const bool hit = x >= -thp[j];
+                                            const uint32_t bits = hit ? __float_as_uint(fmaxf(-x, 0.f)) : 0xffffffffu;
+                                            const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
+                                            const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
+                                            if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
+                                                const uint32_t gcol = col0 + 8 * cq + j;
+                                                atomicMin(ck1 + gcol, make_key(mn, qrow));
+                                                atomicMin(tauc + gcol, mn);
                                             }
                                         }
                                     }
                                 }
                             }
+                            if (rflag) {
+                                // Per group of 4 columns a LOOP (a real branch, never if-converted) that takes the group's maximum while it
+                                // still beats the bound: insert it, retire it, recompute the group maximum.  Typically one trip in
+                                // one group.  Equal values leave the group lowest column first, so ascending-index ties hold.
+                                bool ins = false;
+#pragma unroll
+                                for (int gq = 0; gq < 8; ++gq) {
+                                    while (gm[gq] >= nb) {
+                                        const float m = gm[gq], d = -m;
+                                        if (!(d < t.v2)) break;     // let through by another part's bound or an equal value: nothing here can enter
+                                        const int j = v[4 * gq] == m ? 0 : (v[4 * gq + 1] == m ? 1 : (v[4 * gq + 2] == m ? 2 : 3));
+                                        const uint32_t idx = col0 + 4 * gq + j;
+                                        if (d < t.v1) {
+                                            t.v2 = t.v1; t.i2 = t.i1;
+                                            t.v1 = d;    t.i1 = idx;
+                                        } else {
+                                            t.v2 = d;    t.i2 = idx;
+                                        }
+                                        ins = true;
+                                        nb = fmaxf(nb, -t.v2);
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) v[4 * gq + e] = (e == j) ? -3.0e38f : v[4 * gq + e];
+                                        gm[gq] = fmaxf(fmaxf(fmaxf(v[4 * gq], v[4 * gq + 1]), v[4 * gq + 2]), v[4 * gq + 3]);
+                                    }
+                                }
+                                if (ins) atomicMin(sb, __float_as_uint(fmaxf(t.v2, 0.f)));
+                            }
                         }
-                        if (nh == kTcQTiles) {      // next accumulator belongs to the other query tile
+                        if (kTcQTiles == 2 && nh == 2) {      // next accumulator belongs to the other query tile
                             const RowTop2 x = t;
                             t = to;
                             to = x;
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&thrEmpty[ts]);      // last read of this threshold snapshot
                 }
                 // ---- end of the sweep for this query block: merge the column parts of every row, publish ----
                 // 64-bit shared-memory atomics on packed keys: the smallest key ends in mkey[.][0], the smallest of all the
@@ -479,20 +514,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     if (warp == kTcEpiWarps + 1) tmem_free(tmem, 512);
 }
 
-size_t sweep_l2_tc_smem_bytes() {
-    return 1024 + (size_t)kTcStages * kTcTileBytes + (size_t)kTcQTiles * kTcAugBytes + (size_t)kTcThrStages * kTcThrBytes +
-           (size_t)kTcQTiles * 2 * kTile * sizeof(u64) + (size_t)kTcQTiles * kTile * 4 +
-           (2 * kTcQTiles + 2 * kTcStages + 2 * kTcAccStages + 2 * kTcThrStages) * 8 + 16;
+size_t sweep_l2_tc_smem_bytes(int qt) {
+    return 1024 + (size_t)kTcStages * kTcTileBytes + (size_t)qt * kTcAugBytes + (size_t)kTcThrStages * kTcThrBytes +
+           (size_t)qt * 2 * kTile * sizeof(u64) + (size_t)qt * kTile * 4 +
+           (qt + 2 * kTcStages + 2 * (4 - qt) + 2 * kTcThrStages) * 8 + 16;
 }
 
 cudaError_t launch_sweep_l2_tc(const SweepParams& p, int sm_count, cudaStream_t s) {
     const int n_units = p.n_pairs * p.units_per_pair;
     if (n_units <= 0) return cudaSuccess;
     const int grid = n_units < sm_count ? n_units : sm_count;
-    const size_t smem = sweep_l2_tc_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(sweep_l2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int qt = p.tc_qtiles == 2 ? 2 : 1;
+    const size_t smem = sweep_l2_tc_smem_bytes(qt);
+    auto kern = qt == 2 ? sweep_l2_tc_kernel<2> : sweep_l2_tc_kernel<1>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    sweep_l2_tc_kernel<<<grid, kTcThreads, smem, s>>>(p);
+    kern<<<grid, kTcThreads, smem, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -121,6 +121,12 @@ int esfm_bank_create(esfm_ctx_t* ctx, esfm_kind kind, int n_frames, esfm_bank_t*
  * (F32X64, elements are float) or 32 (B256, elements are uint8).  rows may be 0.  The host pointer
  * need not outlive the call.  `frame_id` in [0, n_frames).  May be called again before commit. */
 int esfm_bank_set_frame(esfm_bank_t* bank, int frame_id, const void* data, int rows, int cols, size_t step_bytes);
+/* Same, without the host-side copy: `data` must be page-locked (cudaMallocHost / cudaHostRegister) with
+ * step_bytes == the row size, and must stay valid and unmodified until esfm_bank_commit returns; commit copies
+ * straight from it (one async host->device copy per frame).  For callers that already hold their descriptors in
+ * pinned memory (a feature extractor writing into a pinned arena); cv::Mat data is pageable: use esfm_bank_set_frame.
+ * ESFM_ERR_INVALID if the memory is not page-locked or the rows are not densely packed. */
+int esfm_bank_set_frame_pinned(esfm_bank_t* bank, int frame_id, const void* data, int rows, int cols, size_t step_bytes);
 /* Declare a frame's row count without host data: for banks whose rows arrive on the device
  * (esfm_bank_device_rows + an NCCL broadcast driven by the host process). */
 int esfm_bank_set_frame_rows(esfm_bank_t* bank, int frame_id, int rows);

@@ -162,3 +162,27 @@ def test_error_behaviour(ctx):
     b.set_frame(0, np.zeros((4, 64), np.float32))
     with pytest.raises(esfm.EsfmError):
         b.commit()                                                     # frame 1 never set
+
+
+def test_set_frame_pinned_equals_set_frame(ctx):
+    """esfm_bank_set_frame_pinned (no host-side copy, commit reads the caller's page-locked memory) gives the same bank as
+    esfm_bank_set_frame, for both kinds and with a mix of the two calls; pageable memory is refused."""
+    import torch
+    import easysfm_b200 as esfm
+    for frames in (synth.orb_like(3, [300, 129, 512], seed=11), synth.surf_like(3, [300, 129, 512], seed=11)):
+        kind = esfm.KIND_B256 if frames[0].dtype == np.uint8 else esfm.KIND_F32X64
+        ref_bank = ctx.bank_from_frames(frames)
+        ref = ref_bank.match_all_pairs(0.8, True)
+        pinned = [torch.from_numpy(f.copy()).pin_memory() for f in frames]
+        b = ctx.bank(kind, 3)
+        b.set_frame_pinned(0, pinned[0].numpy())
+        b.set_frame(1, frames[1])                      # mixing the two calls is allowed
+        b.set_frame_pinned(2, pinned[2].numpy())
+        b.commit()
+        got = b.match_all_pairs(0.8, True)
+        for k in range(ref.n_pairs):
+            i, j, m = ref.pair_at(k)
+            assert_matches_equal(got.pair(i, j), m)
+        b2 = ctx.bank(kind, 1)
+        with pytest.raises(esfm.EsfmError):
+            b2.set_frame_pinned(0, frames[0])          # pageable numpy memory
