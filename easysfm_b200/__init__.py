@@ -21,6 +21,9 @@ from .capi import (  # noqa: F401
     Results,
     library_path,
     load_library,
+    load_results,
+    read_match_file,
+    write_match_file,
 )
 from .feature_matching import FeatureMatching, Frame, pairwise_match_descriptors  # noqa: F401
 from .scheduler import all_pairs, match_all_pairs, shard_pairs  # noqa: F401

@@ -84,6 +84,9 @@ SIGNATURES = {
     "esfm_results_pair": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p), POINTER(c_int)]),
     "esfm_results_pair_counts": (c_int, [c_void_p, POINTER(c_int32)]),
     "esfm_results_destroy": (c_int, [c_void_p]),
+    "esfm_results_save": (c_int, [c_void_p, c_char_p]),
+    "esfm_results_load": (c_int, [c_char_p, POINTER(c_void_p)]),
+    "esfm_results_params": (c_int, [c_void_p, POINTER(c_int), POINTER(ctypes.c_double), POINTER(c_int)]),
 }
 
 _LIB = None
@@ -317,6 +320,45 @@ class Bank:
         return idx, dist
 
 
+MATCH_FILE_HEADER = np.dtype([("magic", "S8"), ("version", "<u4"), ("dmatch_bytes", "<u4"), ("n_pairs", "<i8"), ("n_matches", "<i8"),
+                              ("kind", "<i4"), ("cross_check", "<i4"), ("ratio", "<f8")])
+
+
+def load_results(path: str) -> "Results":
+    """esfm_results_load: a saved batch back as a Results object; needs no device."""
+    lib = load_library()
+    h = c_void_p()
+    _check(lib.esfm_results_load(os.fsencode(path), ctypes.byref(h)))
+    return Results(lib, h)
+
+
+def write_match_file(path: str, pairs, matches_per_pair, kind: int, ratio: float, cross_check: bool):
+    """The match-file format written with numpy (tools and tests; the library's writer is esfm_results_save)."""
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    counts = np.array([len(m) for m in matches_per_pair], np.int32)
+    hdr = np.zeros(1, MATCH_FILE_HEADER)
+    hdr["magic"], hdr["version"], hdr["dmatch_bytes"] = b"ESFMMTCH", 1, DMATCH_DTYPE.itemsize
+    hdr["n_pairs"], hdr["n_matches"] = len(pairs), int(counts.sum())
+    hdr["kind"], hdr["cross_check"], hdr["ratio"] = kind, int(bool(cross_check)), ratio
+    with open(path, "wb") as f:
+        f.write(hdr.tobytes())
+        f.write(pairs.tobytes())
+        f.write(counts.tobytes())
+        for m in matches_per_pair:
+            f.write(np.ascontiguousarray(m, dtype=DMATCH_DTYPE).tobytes())
+
+
+def read_match_file(path: str):
+    """-> (header record, pairs [n,2] int32, counts [n] int32, matches [n_matches] DMATCH_DTYPE)."""
+    with open(path, "rb") as f:
+        hdr = np.frombuffer(f.read(MATCH_FILE_HEADER.itemsize), MATCH_FILE_HEADER)[0]
+        n = int(hdr["n_pairs"])
+        pairs = np.frombuffer(f.read(8 * n), np.int32).reshape(n, 2)
+        counts = np.frombuffer(f.read(4 * n), np.int32)
+        matches = np.frombuffer(f.read(), DMATCH_DTYPE)
+    return hdr, pairs, counts, matches
+
+
 class Results:
     """Host-resident compacted matches of a batch of pairs (esfm_results_t)."""
 
@@ -347,6 +389,16 @@ class Results:
         if self.n_pairs:
             _check(self._lib.esfm_results_pair_counts(self._h, out.ctypes.data_as(POINTER(c_int32))))
         return out
+
+    def save(self, path: str):
+        """Write the (fetched) batch to a match file (include/esfm_match.h: persistence)."""
+        _check(self._lib.esfm_results_save(self._h, os.fsencode(path)))
+
+    def params(self):
+        """(kind, ratio, cross_check) the batch was matched with."""
+        k, r, c = c_int(), ctypes.c_double(), c_int()
+        _check(self._lib.esfm_results_params(self._h, ctypes.byref(k), ctypes.byref(r), ctypes.byref(c)))
+        return k.value, r.value, bool(c.value)
 
     def _view(self, ptr, n):
         if n == 0 or not ptr:

@@ -130,6 +130,9 @@ struct esfm_results {
     std::vector<uint64_t> offsets;          // segment index << 40 | offset (in matches) inside that segment
     struct Segment { esfm_dmatch_t* ptr; size_t count; };
     std::vector<Segment> segments;          // one pinned buffer per chunk, borrowed from the ctx pool
+    int kind = -1, cross_check = 0;         // what the batch was matched with (kept in the match file)
+    double ratio = 0.0;
+    bool heap_segments = false;             // esfm_results_load: segments are plain malloc memory, there is no ctx
     std::unordered_map<uint64_t, int64_t> index;
     bool fetched = true;
     // device-resident variant (single chunk only)
@@ -683,6 +686,9 @@ int match_pairs_impl(esfm_bank* b, const esfm_pair_t* pairs, int64_t n_pairs, do
     esfm_results* res = new (std::nothrow) esfm_results();
     if (!res) return fail(ESFM_ERR_NOMEM, "out of host memory");
     res->ctx = ctx;
+    res->kind = b->kind;
+    res->ratio = ratio;
+    res->cross_check = cross_check ? 1 : 0;
     res->pairs.resize((size_t)n_pairs);
     res->counts.assign((size_t)n_pairs, 0);
     res->offsets.assign((size_t)n_pairs, 0);
@@ -934,7 +940,115 @@ extern "C" int esfm_results_pair_counts(esfm_results_t* r, int32_t* counts) {
 
 extern "C" int esfm_results_destroy(esfm_results_t* r) {
     if (!r) return ESFM_OK;
-    for (auto& s : r->segments) pool_release(r->ctx, s.ptr);
+    for (auto& s : r->segments) {
+        if (r->heap_segments) free(s.ptr);
+        else pool_release(r->ctx, s.ptr);
+    }
     delete r;
+    return ESFM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistence of a fetched batch (host only)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct MatchFileHeader {
+    char magic[8];
+    uint32_t version, dmatch_bytes;
+    int64_t n_pairs, n_matches;
+    int32_t kind, cross_check;
+    double ratio;
+};
+static_assert(sizeof(MatchFileHeader) == 48, "match file header layout");
+const char kMatchMagic[8] = {'E', 'S', 'F', 'M', 'M', 'T', 'C', 'H'};
+}  // namespace
+
+extern "C" int esfm_results_save(esfm_results_t* r, const char* path) {
+    if (!r || !path) return fail(ESFM_ERR_INVALID, "esfm_results_save: NULL argument");
+    if (!r->fetched) return fail(ESFM_ERR_STATE, "matches are device-resident; call esfm_results_fetch first");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(ESFM_ERR_INVALID, "esfm_results_save: cannot open %s for writing", path);
+    MatchFileHeader h{};
+    memcpy(h.magic, kMatchMagic, 8);
+    h.version = 1;
+    h.dmatch_bytes = (uint32_t)sizeof(esfm_dmatch_t);
+    h.n_pairs = (int64_t)r->pairs.size();
+    h.n_matches = 0;
+    for (int32_t c : r->counts) h.n_matches += c;
+    h.kind = r->kind;
+    h.cross_check = r->cross_check;
+    h.ratio = r->ratio;
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    static_assert(sizeof(PairDesc) == sizeof(esfm_pair_t), "pair layout");
+    if (ok && h.n_pairs) ok = fwrite(r->pairs.data(), sizeof(PairDesc), r->pairs.size(), f) == r->pairs.size();
+    if (ok && h.n_pairs) ok = fwrite(r->counts.data(), sizeof(int32_t), r->counts.size(), f) == r->counts.size();
+    for (size_t k = 0; ok && k < r->pairs.size(); ++k) {
+        const int32_t n = r->counts[k];
+        if (n <= 0) continue;
+        const uint64_t o = r->offsets[k];
+        const esfm_dmatch_t* m = r->segments[(size_t)(o >> 40)].ptr + (o & (((uint64_t)1 << 40) - 1));
+        ok = fwrite(m, sizeof(esfm_dmatch_t), (size_t)n, f) == (size_t)n;
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(ESFM_ERR_INVALID, "esfm_results_save: short write to %s", path);
+    return ESFM_OK;
+}
+
+extern "C" int esfm_results_params(esfm_results_t* r, int* kind, double* ratio, int* cross_check) {
+    if (!r) return fail(ESFM_ERR_INVALID, "results is NULL");
+    if (kind) *kind = r->kind;
+    if (ratio) *ratio = r->ratio;
+    if (cross_check) *cross_check = r->cross_check;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_results_load(const char* path, esfm_results_t** out) {
+    if (!path || !out) return fail(ESFM_ERR_INVALID, "esfm_results_load: NULL argument");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(ESFM_ERR_INVALID, "esfm_results_load: cannot open %s", path);
+    MatchFileHeader h{};
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, kMatchMagic, 8) != 0 || h.version != 1 ||
+        h.dmatch_bytes != sizeof(esfm_dmatch_t) || h.n_pairs < 0 || h.n_matches < 0) {
+        fclose(f);
+        return fail(ESFM_ERR_INVALID, "esfm_results_load: %s is not an esfm match file (version 1)", path);
+    }
+    esfm_results* r = new (std::nothrow) esfm_results();
+    if (!r) { fclose(f); return fail(ESFM_ERR_NOMEM, "out of host memory"); }
+    r->heap_segments = true;
+    r->fetched = true;
+    r->kind = h.kind;
+    r->cross_check = h.cross_check;
+    r->ratio = h.ratio;
+    bool ok = true;
+    try {
+        r->pairs.resize((size_t)h.n_pairs);
+        r->counts.resize((size_t)h.n_pairs);
+        r->offsets.resize((size_t)h.n_pairs);
+    } catch (...) { ok = false; }
+    if (ok && h.n_pairs) ok = fread(r->pairs.data(), sizeof(PairDesc), r->pairs.size(), f) == r->pairs.size();
+    if (ok && h.n_pairs) ok = fread(r->counts.data(), sizeof(int32_t), r->counts.size(), f) == r->counts.size();
+    int64_t total = 0;
+    for (size_t k = 0; ok && k < r->pairs.size(); ++k) {
+        if (r->counts[k] < 0) { ok = false; break; }
+        r->offsets[k] = (uint64_t)total;      // segment 0
+        total += r->counts[k];
+    }
+    if (ok && total != h.n_matches) ok = false;
+    if (ok) {
+        esfm_results::Segment sg{nullptr, (size_t)total};
+        if (total > 0) {
+            sg.ptr = (esfm_dmatch_t*)malloc((size_t)total * sizeof(esfm_dmatch_t));
+            ok = sg.ptr && fread(sg.ptr, sizeof(esfm_dmatch_t), (size_t)total, f) == (size_t)total;
+        }
+        r->segments.push_back(sg);
+        r->total_matches = total;
+    }
+    fclose(f);
+    if (!ok) {
+        esfm_results_destroy(r);
+        return fail(ESFM_ERR_INVALID, "esfm_results_load: %s is truncated or inconsistent", path);
+    }
+    *out = r;
     return ESFM_OK;
 }

@@ -10,6 +10,9 @@
 //   * all-pairs path: call p3dv::esfm_prepare_all_pairs(frames, 'S'|'O', ratio, cross_check) once before the
 //     pair loop (a one-line hook at sfm.cpp:131); every later matchFeatures* call on those frames with the same
 //     ratio is a lookup into the precomputed result (esfm_results_pair).
+//   * resume: p3dv::esfm_save_matches(path) after the prepare step writes the whole batch to a match file;
+//     p3dv::esfm_load_matches(frames, 'S'|'O', ratio, path) in a later run makes the same lookups work without
+//     matching again (and without touching the GPU).
 //
 // Semantics kept from the reference: matches are APPENDED (push_back, :90/:135), ascending queryIdx, imgIdx = 0,
 // returns true; ratio test in double (:88/:133); the stdout summary lines (:81,96-97 / :126,141-142).
@@ -78,7 +81,6 @@ bool match_common(esfm_kind kind, const char* tag, frame_t& f1, frame_t& f2, std
     static_assert(sizeof(cv::DMatch) == sizeof(esfm_dmatch_t), "esfm_dmatch_t must be layout-identical to cv::DMatch");
     GpuState& s = state();
     std::chrono::steady_clock::time_point tic = std::chrono::steady_clock::now();
-    if (!ensure_ctx()) return false;
     const cv::Mat& q = f1.descriptors;  // cur_frame_1 is the query side (knnMatch(cur_frame_1, cur_frame_2), :80/:125)
     const cv::Mat& t = f2.descriptors;
     if (!check_mat(q, kind) || !check_mat(t, kind)) {
@@ -100,6 +102,7 @@ bool match_common(esfm_kind kind, const char* tag, frame_t& f1, frame_t& f2, std
         }
     }
     if (!done) {  // per-call path
+        if (!ensure_ctx()) return false;
         std::vector<esfm_dmatch_t> buf((size_t)std::max(q.rows, 1));
         int n = 0;
         const int rc = esfm_match_descriptors(s.ctx, kind, q.data, q.rows, (size_t)q.step, t.data, t.rows, (size_t)t.step,
@@ -146,6 +149,39 @@ bool esfm_prepare_all_pairs(std::vector<frame_t>& frames, char feature, double r
         std::cerr << "esfm_prepare_all_pairs failed: " << esfm_last_error() << std::endl;
         return false;
     }
+    return true;
+}
+
+// Persist the batch computed by esfm_prepare_all_pairs (the reference keeps matches in RAM only, sfm.cpp:130-197).
+bool esfm_save_matches(const char* path) {
+    GpuState& s = state();
+    if (!s.results) { std::cerr << "esfm_save_matches: nothing prepared" << std::endl; return false; }
+    if (esfm_results_save(s.results, path) != ESFM_OK) { std::cerr << "esfm_save_matches failed: " << esfm_last_error() << std::endl; return false; }
+    return true;
+}
+
+// Resume: load a match file written for the same frame list (same order), feature kind and ratio.  No device is needed;
+// every later matchFeatures* call on those frames with that ratio is a lookup.
+bool esfm_load_matches(std::vector<frame_t>& frames, char feature, double ratio_thre, const char* path) {
+    GpuState& s = state();
+    esfm_results_t* r = nullptr;
+    if (esfm_results_load(path, &r) != ESFM_OK) { std::cerr << "esfm_load_matches failed: " << esfm_last_error() << std::endl; return false; }
+    int kind = -1, cc = 0;
+    double ratio = 0.0;
+    esfm_results_params(r, &kind, &ratio, &cc);
+    const esfm_kind want = feature == 'O' ? ESFM_KIND_B256 : ESFM_KIND_F32X64;
+    if (kind != (int)want || ratio != ratio_thre) {
+        std::cerr << "esfm_load_matches: " << path << " was matched with kind " << kind << ", ratio " << ratio << std::endl;
+        esfm_results_destroy(r);
+        return false;
+    }
+    if (s.results) esfm_results_destroy(s.results);
+    s.results = r;
+    s.kind = want;
+    s.ratio = ratio_thre;
+    s.cross_check = cc != 0;
+    s.frame_index.clear();
+    for (size_t i = 0; i < frames.size(); ++i) s.frame_index[frames[i].frame_id] = (int)i;
     return true;
 }
 

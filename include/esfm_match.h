@@ -184,6 +184,20 @@ int esfm_results_pair(esfm_results_t* results, int query_frame, int train_frame,
 int esfm_results_pair_counts(esfm_results_t* results, int32_t* counts);
 int esfm_results_destroy(esfm_results_t* results);
 
+/* ---- persistence (restart the SfM pipeline after matching) --------------------
+ * The reference keeps every pair's matches in RAM only (img_match_graph, sfm.cpp:130-197) and re-matches on
+ * every run.  esfm_results_save writes a fetched batch to one little-endian file:
+ *   "ESFMMTCH" | u32 version = 1 | u32 sizeof(esfm_dmatch_t) = 16 | i64 n_pairs | i64 n_matches |
+ *   i32 kind | i32 cross_check | f64 ratio |
+ *   n_pairs x esfm_pair_t {query, train} | n_pairs x i32 counts | n_matches x esfm_dmatch_t (pairs in batch order)
+ * esfm_results_load needs no device and no context: the loaded batch answers esfm_results_counts / _pair_at /
+ * _pair / _pair_counts exactly like the one that was saved.  ESFM_ERR_INVALID on a missing, truncated or
+ * foreign file. */
+int esfm_results_save(esfm_results_t* results, const char* path);
+/* The parameters the batch was matched with (also stored in the file, so a resumed run can check them). */
+int esfm_results_params(esfm_results_t* results, int* kind, double* ratio, int* cross_check);
+int esfm_results_load(const char* path, esfm_results_t** results);
+
 #ifdef __cplusplus
 }
 #endif

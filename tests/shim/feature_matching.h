@@ -47,5 +47,7 @@ public:
                            double ratio_thre = 0.5, bool show = false);
 };
 bool esfm_prepare_all_pairs(std::vector<frame_t>& frames, char feature, double ratio_thre, bool cross_check);
+bool esfm_save_matches(const char* path);
+bool esfm_load_matches(std::vector<frame_t>& frames, char feature, double ratio_thre, const char* path);
 }  // namespace p3dv
 #endif

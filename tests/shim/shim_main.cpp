@@ -1,7 +1,10 @@
 // Drives the C++ shim the way cpp_code/test/sfm.cpp:140-161 drives the reference: for i, for j < i: matchFeaturesX(frames[i], frames[j], out).
-// usage: shim_main <O|S> <n_frames> <rows_0> ... <rows_{n-1}> <descriptor file (raw, frames back to back)> <prepare 0|1> <out file>
+// usage: shim_main <O|S> <n_frames> <rows_0> ... <rows_{n-1}> <descriptor file (raw, frames back to back)> <mode> <out file>
+//   mode 0: per-call path   1: esfm_prepare_all_pairs first   2: prepare + esfm_save_matches(<out file>.matches)
+//   mode 3: esfm_load_matches(<out file>.matches) instead of matching (no device needed)
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "feature_matching.h"
@@ -13,7 +16,8 @@ int main(int argc, char** argv) {
     std::vector<int> rows(n);
     for (int i = 0; i < n; ++i) rows[i] = std::atoi(argv[3 + i]);
     const char* path = argv[3 + n];
-    const bool prepare = std::atoi(argv[4 + n]) != 0;
+    const int mode = std::atoi(argv[4 + n]);
+    const bool prepare = mode == 1 || mode == 2;
     const char* out_path = argv[5 + n];
     const size_t rb = feature == 'O' ? 32 : 256;
     size_t total = 0;
@@ -35,6 +39,9 @@ int main(int argc, char** argv) {
     }
     p3dv::FeatureMatching fm;
     if (prepare && !p3dv::esfm_prepare_all_pairs(frames, feature, feature == 'O' ? 0.8 : 0.5, false)) return 4;
+    const std::string match_file = std::string(out_path) + ".matches";
+    if (mode == 2 && !p3dv::esfm_save_matches(match_file.c_str())) return 6;
+    if (mode == 3 && !p3dv::esfm_load_matches(frames, feature, feature == 'O' ? 0.8 : 0.5, match_file.c_str())) return 7;
     FILE* o = std::fopen(out_path, "wb");
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < i; ++j) {
