@@ -55,7 +55,6 @@ template <int QT> struct TcGeom {
 };
 constexpr int kTcThrBytes = kTile * 4;                  // 512: column thresholds riding with a train tile
 constexpr int kTcThrStages = 4;                         // threshold snapshots have their own (deeper) ring
-constexpr int kTcDenseLanes = 8;                        // >= this many lanes with row candidates -> dense (branch-free) row update
 constexpr uint32_t kTcBoundBits = 0x6f6f6f6fu;          // 7.4e28f: "no bound yet" (what memset(0x6f) writes); pads are 1e30
 
 struct TcUnit {
@@ -127,57 +126,6 @@ constexpr int kTcSleepIssuer = 40;
 constexpr int kTcSleepEpilogue = 0;
 
 }  // namespace
-
-// x[g] for a per-thread (non-uniform) g in [0, 8): three levels of selects
-__device__ __forceinline__ float tc_mux8(float x0, float x1, float x2, float x3, float x4, float x5, float x6, float x7, bool b0, bool b1, bool b2) {
-    const float a0 = b0 ? x1 : x0, a1 = b0 ? x3 : x2, a2 = b0 ? x5 : x4, a3 = b0 ? x7 : x6;
-    const float c0 = b1 ? a1 : a0, c1 = b1 ? a3 : a2;
-    return b2 ? c1 : c0;
-}
-
-// Dense row update: the exact top-2 (largest value first, lowest column on ties) of a thread's 32 accumulator values, merged
-// into its running top-2 -- branch-free, ~170 instructions whatever the number of candidates.  Used instead of the per-group
-// insertion loops when many lanes of the warp have candidates, i.e. in the first tiles of every query block, when the
-// bounds are still cold: there the loops need 300-600 dependent instructions per accumulator, several MMA periods, and
-// the three accumulator stages cannot hide that (it was ~19 % of the sweep's time).
-__device__ __forceinline__ bool tc_row_top2_dense(const float (&v)[32], const float (&gm)[8], float m1, uint32_t col0, RowTop2& t) {
-    int g1 = 7;
-#pragma unroll
-    for (int g = 6; g >= 0; --g) g1 = (gm[g] == m1) ? g : g1;            // first group holding the maximum
-    const bool p0 = g1 & 1, p1 = g1 & 2, p2 = g1 & 4;
-    float a[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) a[e] = tc_mux8(v[e], v[4 + e], v[8 + e], v[12 + e], v[16 + e], v[20 + e], v[24 + e], v[28 + e], p0, p1, p2);
-    const int j1 = a[0] == m1 ? 0 : (a[1] == m1 ? 1 : (a[2] == m1 ? 2 : 3));
-#pragma unroll
-    for (int e = 0; e < 4; ++e) a[e] = (e == j1) ? -3.0e38f : a[e];     // retire it
-    const float s_in = fmaxf(fmaxf(fmaxf(a[0], a[1]), a[2]), a[3]);
-    float gm2[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) gm2[g] = (g == g1) ? s_in : gm[g];
-    const float m2 = fmaxf(fmaxf(fmaxf(fmaxf(gm2[0], gm2[1]), gm2[2]), fmaxf(fmaxf(gm2[3], gm2[4]), gm2[5])), fmaxf(gm2[6], gm2[7]));
-    int g2 = 7;
-#pragma unroll
-    for (int g = 6; g >= 0; --g) g2 = (gm2[g] == m2) ? g : g2;
-    const bool q0 = g2 & 1, q1 = g2 & 2, q2 = g2 & 4;
-    float c[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        c[e] = tc_mux8(v[e], v[4 + e], v[8 + e], v[12 + e], v[16 + e], v[20 + e], v[24 + e], v[28 + e], q0, q1, q2);
-        c[e] = (g2 == g1) ? a[e] : c[e];                                  // same group: without the retired element
-    }
-    const int j2 = c[0] == m2 ? 0 : (c[1] == m2 ? 1 : (c[2] == m2 ? 2 : 3));
-    const float d1 = -m1, d2 = -m2;                                      // d1 <= d2; equal values: d1 has the lower column
-    const uint32_t i1 = col0 + 4 * g1 + j1, i2 = col0 + 4 * g2 + j2;
-    bool ins = false;
-    if (d1 < t.v2) {
-        if (d1 < t.v1) { t.v2 = t.v1; t.i2 = t.i1; t.v1 = d1; t.i1 = i1; }
-        else           { t.v2 = d1;   t.i2 = i1; }
-        ins = true;
-    }
-    if (d2 < t.v2) { t.v2 = d2; t.i2 = i2; ins = true; }                 // d2 >= d1 >= t.v1 now: it can only be the second
-    return ins;
-}
 
 template <int kTcQTiles>
 __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepParams p) {
@@ -490,12 +438,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                                     }
                                 }
                             }
-                            const uint32_t rlanes = __ballot_sync(0xffffffffu, rflag);
-                            if (__popc(rlanes) >= kTcDenseLanes) {
-                                // many rows of this warp have candidates (cold bounds): branch-free exact top-2 of all 32 columns
-                                const bool ins = tc_row_top2_dense(v, gm, rmax, col0, t);
-                                if (ins) atomicMin(sb, __float_as_uint(fmaxf(t.v2, 0.f)));
-                            } else if (rflag) {
+                            if (rflag) {
                                 // Per group of 4 columns a LOOP (a real branch, never if-converted) that takes the group's maximum while it
                                 // still beats the bound: insert it, retire it, recompute the group maximum.  Typically one trip in
                                 // one group.  Equal values leave the group lowest column first, so ascending-index ties hold.

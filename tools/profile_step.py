@@ -37,6 +37,6 @@ for r in range(repeats):
     dt = time.perf_counter() - t0
     st = ctx.stats()
     print(f"{kind} engine={ctx.l2_engine() if kind == 'surf' else '-'} {len(pairs)} pairs of {n_feat}x{n_feat}: {n} matches, {dt * 1e3:.1f} ms wall, "
-          f"sweep {st['last_sweep_ms']:.2f} ms -> {len(pairs) * n_feat * n_feat / (st['last_sweep_ms'] * 1e-3):.3e} cmp/s", flush=True)
+          f"finalize {st['last_finalize_ms']:.2f} ms, sweep {st['last_sweep_ms']:.2f} ms -> {len(pairs) * n_feat * n_feat / (st['last_sweep_ms'] * 1e-3):.3e} cmp/s", flush=True)
 bank.close()
 ctx.close()
