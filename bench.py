@@ -37,6 +37,7 @@ SM_LANES_FP32 = 128      # FFMA lanes per SM per clock (verified: profiles/pipes
 POPC_LANES = 16          # POPC lanes per SM per clock (verified: profiles/pipes_r1.txt)
 
 
+TC8_FLOP_PER_CMP = (256 + 32) * 2       # ORB on the tensor cores: 256 FP8 MACs + one K=32 augmented step, x 2
 TC_FLOP_PER_CMP = (3 * 64 + 8) * 2   # 3xTF32 split over 64 dims + one K=8 augmented step (norms), x 2: tensor FLOPs executed per comparison
 
 
@@ -181,13 +182,14 @@ def workload_config(kind, pairs_per_step, e2e_frames):
 
 def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budget_s, engine=None, e2e_arm=True):
     """Returns the result dict for one descriptor kind (device-resident value, e2e, roofline, cpu baseline).
-    `engine` selects the SURF sweep kernel ('tc' = tcgen05 3xTF32, 'ffma' = exact-FP32 FMA pipe); None = library default."""
+    `engine` selects the sweep kernel: SURF 'tc' (tcgen05 3xTF32) | 'ffma' (exact-FP32 FMA pipe); ORB 'tc' (tcgen05 FP8 +-1 dot
+    product) | 'popc' (XOR + POPC); None = library default."""
     import torch
     from easysfm_b200 import scheduler
     import easysfm_b200 as esfm
-    if kind == "surf" and engine:
-        ctx.set_l2_engine(engine)
-    engine = ctx.l2_engine() if kind == "surf" else None
+    if engine:
+        (ctx.set_l2_engine if kind == "surf" else ctx.set_hamming_engine)(engine)
+    engine = ctx.l2_engine() if kind == "surf" else ctx.hamming_engine()
 
     n_images, n_feat = N_IMAGES[kind], N_FEAT[kind]
     if args.images:
@@ -350,6 +352,11 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
         peak = fp32_pipe_peak
         bound = "fp32-fma-pipe"
         kern = "sweep_l2_kernel"
+    elif engine == "tc":
+        unit_ops, unit = 8.0, "TPOPC/s"                        # algorithmic: 8 x 32-bit POPC per comparison (north_star)
+        peak = sms * POPC_LANES * sm_max * 1e6 / 1e12          # ... against the pipe the XOR+POPC design is bound by
+        bound = "tensor"
+        kern = "sweep_l2_tc_kernel<1, B256>"
     else:
         unit_ops, unit = 8.0, "TPOPC/s"                        # 8 x 32-bit POPC per comparison (algorithmic, north_star)
         peak = sms * POPC_LANES * sm_max * 1e6 / 1e12
@@ -363,7 +370,18 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
                                f"(sm_max_mhz {peak_src}; lanes/clk measured by csrc/microbench/pipes.cu, profiles/pipes_r1.txt)",
                 "kernel_ms": sweep_ms, "comparisons_per_launch": comps_per_launch,
                 "hbm_gbs_algorithmic": None, "traffic": None}
-    if bound == "tensor":
+    if bound == "tensor" and kind == "orb":
+        # ORB on the tensor cores: Hamming = (256 - dot) / 2 of FP8 +-1 vectors, exact.  `achieved`/`frac` stay in the north
+        # star's algorithmic unit (8 POPC per comparison against the POPC-pipe peak: > 1 means faster than any XOR+POPC kernel
+        # can be); `executed_tflops` / `frac_executed` are the FP8 tensor FLOPs actually issued over the dense FP8 peak
+        # (= 2 x the measured dense bf16 rate).  The kernel is bound by its selection epilogue, not by the tensor pipe.
+        fp8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        roofline["executed_tflops"] = (comps_per_launch / (sweep_ms * 1e-3)) * TC8_FLOP_PER_CMP / 1e12
+        roofline["frac_executed"] = roofline["executed_tflops"] / fp8_peak
+        roofline["tensor_peak_tflops"] = fp8_peak
+        roofline["note"] = ("Hamming as an exact FP8 (+-1) dot product on tcgen05 (kind::f8f6f4): 576 tensor FLOP per comparison; "
+                            "frac is the algorithmic 8-POPC rate over the POPC-pipe peak")
+    if bound == "tensor" and kind == "surf":
         # `achieved`/`frac` use the ALGORITHMIC 128 FLOP per comparison.  The tensor cores execute 3.125x that
         # (3xTF32 split over 64 dims + 8 augmented columns); `frac_executed` is that executed rate over the same peak (= tensor-pipe utilisation),
         # and `frac_of_fp32_pipe_roofline` compares the algorithmic rate with the FP32-FFMA pipe peak the FFMA engine is bound by.
@@ -372,7 +390,7 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
         roofline["frac_of_fp32_pipe_roofline"] = achieved / fp32_pipe_peak
         roofline["note"] = ("3xTF32 split product (lo.hi + hi.lo + hi.hi over 64 dims, + one K=8 step adding the norms) on tcgen05; "
                             f"{TC_FLOP_PER_CMP} tensor FLOP executed per 128 algorithmic FLOP")
-    if kind == "orb":
+    if kind == "orb" and engine != "tc":
         # The kernel compresses the 8 xor words with carry-save adders and issues only 4 POPC per comparison, so it can
         # exceed the algorithmic 8-POPC roofline; what binds it is instruction issue (~36 warp-instructions per 32
         # comparisons, 4 issue slots per clock per SM; profiles/sass_hamming_loop_r1.txt).
@@ -384,7 +402,7 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
     # algorithmic HBM bytes: every pair reads both frames once + writes its matches
     # (SURF rows: 260 B in the FFMA engine's k-major bank; tensor-core engine: 544 B per train row = hi + lo images + augmented
     #  columns, 256 B per query row = the fp32 rows the sweep converts on the fly)
-    bytes_per_pair = n_feat * (((544 + 256) if engine == "tc" else 520) if kind == "surf" else 64)
+    bytes_per_pair = n_feat * (((544 + 256) if engine == "tc" else 520) if kind == "surf" else ((288 + 32) if engine == "tc" else 64))
     roofline["hbm_gbs_algorithmic"] = (comps_per_launch / (n_feat * n_feat)) * bytes_per_pair / (sweep_ms * 1e-3) / 1e9
     roofline["hbm_peak_gbs"] = peaks.get("hbm_gbs")
     # measured DRAM traffic of this kernel on this command (one ncu pass, committed under profiles/): far BELOW the per-pair
@@ -392,7 +410,7 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            tr = json.load(f).get("surf_tc" if engine == "tc" else kind)
+            tr = json.load(f).get({"surf": "surf_tc", "orb": "orb_tc"}[kind] if engine == "tc" else kind)
         if tr:
             per_pair = (tr["dram_read_bytes_per_launch"] + tr["dram_write_bytes_per_launch"]) / tr["pairs_per_launch"]
             roofline["traffic"] = per_pair * (comps_per_launch / (n_feat * n_feat))
@@ -438,7 +456,9 @@ def main():
     ap.add_argument("--ref-pairs-per-step", type=int, default=4)
     ap.add_argument("--l2-engine", default=None, choices=["tc", "ffma"],
                     help="SURF sweep kernel: tcgen05 3xTF32 ('tc', library default) or exact-FP32 FMA pipe ('ffma')")
-    ap.add_argument("--no-alt-engine", action="store_true", help="skip the short run of the other SURF engine")
+    ap.add_argument("--hamming-engine", default=None, choices=["tc", "popc"],
+                    help="ORB sweep kernel: tcgen05 FP8 +-1 dot product ('tc') or XOR + POPC ('popc'); default = library default")
+    ap.add_argument("--no-alt-engine", action="store_true", help="skip the short run of the other engine of each kind")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -470,27 +490,27 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = esfm.Context(local_rank, stream=stream.cuda_stream)
 
-    surf_engine = args.l2_engine or ctx.l2_engine()
+    engines = {"surf": args.l2_engine or ctx.l2_engine(), "orb": args.hamming_engine or ctx.hamming_engine()}
+    other_engine = {"surf": {"tc": "ffma", "ffma": "tc"}, "orb": {"tc": "popc", "popc": "tc"}}
+
+    def alt_run(kind):
+        # the other engine of this kind on the same workload, device-resident arm only (short: it is context, not the headline)
+        a = bench_kind(args, kind, ctx, dev, rank, world, dist, 3, 3, 0.0, engine=other_engine[kind][engines[kind]], e2e_arm=False)
+        (ctx.set_l2_engine if kind == "surf" else ctx.set_hamming_engine)(engines[kind])
+        return {k: a[k] for k in ("engine", "value", "unit", "ms_per_step", "roofline", "clocks")}
+
     primary = bench_kind(args, args.kind, ctx, dev, rank, world, dist, args.steps, args.warmup, args.cpu_budget_s,
-                         engine=surf_engine)
+                         engine=engines[args.kind])
     if not args.no_alt_engine and world == 1:
-        # the other SURF engine on the same workload, device-resident arm only (short: it is context, not the headline)
-        alt = "ffma" if surf_engine == "tc" else "tc"
-        a = bench_kind(args, "surf", ctx, dev, rank, world, dist, 3, 3, 0.0, engine=alt, e2e_arm=False)
-        alt_obj = {k: a[k] for k in ("engine", "value", "unit", "ms_per_step", "roofline", "clocks")}
-        if args.kind == "surf":
-            primary["alt_engine"] = alt_obj
-        ctx.set_l2_engine(surf_engine)
-    else:
-        alt_obj = None
+        primary["alt_engine"] = alt_run(args.kind)
     if not args.no_secondary:
         other = "orb" if args.kind == "surf" else "surf"
         sec = bench_kind(args, other, ctx, dev, rank, world, dist, max(3, args.steps // 2), args.warmup, args.cpu_budget_s / 2,
-                         engine=surf_engine)
+                         engine=engines[other])
         primary["secondary"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "dtype", "config", "pairs_per_s", "e2e", "engine",
                                                     "roofline", "cpu_baseline", "gpu_launches", "clocks", "full_job_estimate_s")}
-        if args.kind != "surf" and alt_obj:
-            primary["secondary"]["alt_engine"] = alt_obj
+        if not args.no_alt_engine and world == 1:
+            primary["secondary"]["alt_engine"] = alt_run(other)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

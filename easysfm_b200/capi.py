@@ -22,6 +22,8 @@ PAIR_DTYPE = np.dtype([("query", "<i4"), ("train", "<i4")])
 
 L2_ENGINE_FFMA = 0
 L2_ENGINE_TC = 1
+HAMMING_ENGINE_POPC = 0
+HAMMING_ENGINE_TC = 1
 
 
 class EsfmError(RuntimeError):
@@ -59,6 +61,8 @@ SIGNATURES = {
     "esfm_device_sm_count": (c_int, [c_void_p, POINTER(c_int)]),
     "esfm_set_l2_engine": (c_int, [c_void_p, c_int]),
     "esfm_get_l2_engine": (c_int, [c_void_p, POINTER(c_int)]),
+    "esfm_set_hamming_engine": (c_int, [c_void_p, c_int]),
+    "esfm_get_hamming_engine": (c_int, [c_void_p, POINTER(c_int)]),
     "esfm_bank_create": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
     "esfm_bank_set_frame": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_size_t]),
     "esfm_bank_set_frame_pinned": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_size_t]),
@@ -191,6 +195,16 @@ class Context:
         e = c_int(0)
         _check(self._lib.esfm_get_l2_engine(self._h, ctypes.byref(e)))
         return {L2_ENGINE_FFMA: "ffma", L2_ENGINE_TC: "tc"}[e.value]
+
+    def set_hamming_engine(self, engine):
+        """'popc' (XOR + POPC on the integer pipes) or 'tc' (exact FP8 +-1 dot product on the tensor cores) for the ORB sweep."""
+        code = {"popc": HAMMING_ENGINE_POPC, "tc": HAMMING_ENGINE_TC}.get(engine, engine)
+        _check(self._lib.esfm_set_hamming_engine(self._h, int(code)))
+
+    def hamming_engine(self) -> str:
+        e = c_int(0)
+        _check(self._lib.esfm_get_hamming_engine(self._h, ctypes.byref(e)))
+        return {HAMMING_ENGINE_POPC: "popc", HAMMING_ENGINE_TC: "tc"}[e.value]
 
     def bank(self, kind: int, n_frames: int) -> "Bank":
         return Bank(self, kind, n_frames)

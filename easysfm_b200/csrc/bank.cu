@@ -111,4 +111,51 @@ cudaError_t launch_pack_tc(const float* rows, const int* frame_rows, const int* 
     return cudaGetLastError();
 }
 
+// B256 -> the FP8 tile images of tc_layout.cuh (Hamming on the tensor cores): one block per 128-row tile, one thread per
+// (row, 32-bit word): 32 bits -> 32 bytes of +-1.0 (E4M3), written as two 16-byte chunks into the SWIZZLE_128B atoms.
+__global__ void __launch_bounds__(256) pack_tc8_kernel(const uint32_t* __restrict__ rows, const int* __restrict__ frame_rows,
+                                                       const int* __restrict__ frame_row_off,
+                                                       const int* __restrict__ frame_tile_off, int n_frames,
+                                                       unsigned char* __restrict__ tc_main) {
+    const int t = blockIdx.x;
+    int lo = 0, hi = n_frames - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (frame_tile_off[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const int f = lo;
+    const int row0 = (t - frame_tile_off[f]) * kTile;
+    int valid = frame_rows[f] - row0;
+    valid = valid < 0 ? 0 : (valid > kTile ? kTile : valid);
+    const uint32_t* src = rows + ((size_t)frame_row_off[f] + row0) * 8;
+    unsigned char* out = tc_main + (size_t)t * kTc8TileBytes;
+    for (int idx = threadIdx.x; idx < kTile * 8; idx += blockDim.x) {
+        const int r = idx >> 3, w = idx & 7;                   // row, word: bits 32 w .. 32 w + 31 = elements k
+        uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = c0;          // pad rows: all-zero operands (+0.0)
+        if (r < valid) {
+            const uint32_t x = src[(size_t)r * 8 + w];
+            c0 = make_uint4(tc8_expand4(x), tc8_expand4(x >> 4), tc8_expand4(x >> 8), tc8_expand4(x >> 12));
+            c1 = make_uint4(tc8_expand4(x >> 16), tc8_expand4(x >> 20), tc8_expand4(x >> 24), tc8_expand4(x >> 28));
+        }
+        const int k = w * 32;                                   // first element of this word
+        unsigned char* atom = out + (r >> 3) * kTc8GroupBytes + (k >> 7) * 1024;
+        *reinterpret_cast<uint4*>(atom + tc8_sw128_off(r & 7, k & 127)) = c0;
+        *reinterpret_cast<uint4*>(atom + tc8_sw128_off(r & 7, (k & 127) + 16)) = c1;
+    }
+    if (threadIdx.x < kTile) {
+        const int r = threadIdx.x;
+        // train role: (-448, tpad ? -448 : 0, -16, 0 ...) against the query's (qpad ? 448 : 0, 448, 16, 0 ...)
+        unsigned char* a = out + kTc8MainBytes + (r >> 3) * kTcAugGroupBytes + (r & 7) * 16;
+        *reinterpret_cast<uint4*>(a) = make_uint4(kFp8Neg448 | ((r < valid ? 0u : kFp8Neg448) << 8) | (kFp8Neg16 << 16), 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(a + 128) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+cudaError_t launch_pack_tc8(const uint32_t* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
+                            int n_frames, int n_tiles_total, unsigned char* tc_main, cudaStream_t s) {
+    if (n_tiles_total <= 0) return cudaSuccess;
+    pack_tc8_kernel<<<n_tiles_total, 256, 0, s>>>(rows, frame_rows, frame_row_off, frame_tile_off, n_frames, tc_main);
+    return cudaGetLastError();
+}
+
 }  // namespace esfm

@@ -49,6 +49,7 @@ struct esfm_ctx {
     int sm_count = 0;
     bool profiling = true;
     int tc_qtiles = 1;                     // TC sweep geometry: query tiles per block (1 or 2; $ESFM_TC_QT)
+    int hamming_engine = ESFM_HAMMING_ENGINE_TC;     // which sweep kernel serves ESFM_KIND_B256 (esfm_set_hamming_engine / $ESFM_HAMMING_ENGINE)
     int l2_engine = ESFM_L2_ENGINE_TC;     // which sweep kernel serves ESFM_KIND_F32X64 (esfm_set_l2_engine / $ESFM_L2_ENGINE)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     esfm_stats_t stats{};
@@ -197,6 +198,11 @@ extern "C" int esfm_init(int device, void* cuda_stream, esfm_ctx_t** out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* qt = getenv("ESFM_TC_QT")) ctx->tc_qtiles = atoi(qt) == 2 ? 2 : 1;
+    if (const char* eng = getenv("ESFM_HAMMING_ENGINE")) {
+        if (!strcmp(eng, "tc") || !strcmp(eng, "tensor")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_TC;
+        else if (!strcmp(eng, "popc")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_POPC;
+        else { delete ctx; return fail(ESFM_ERR_INVALID, "ESFM_HAMMING_ENGINE=%s: expected 'popc' or 'tc'", eng); }
+    }
     if (const char* eng = getenv("ESFM_L2_ENGINE")) {
         if (!strcmp(eng, "tc") || !strcmp(eng, "tensor")) ctx->l2_engine = ESFM_L2_ENGINE_TC;
         else if (!strcmp(eng, "ffma")) ctx->l2_engine = ESFM_L2_ENGINE_FFMA;
@@ -264,6 +270,19 @@ extern "C" int esfm_set_l2_engine(esfm_ctx_t* ctx, int engine) {
     if (!ctx) return fail(ESFM_ERR_INVALID, "ctx is NULL");
     if (engine != ESFM_L2_ENGINE_FFMA && engine != ESFM_L2_ENGINE_TC) return fail(ESFM_ERR_INVALID, "unknown L2 engine %d", engine);
     ctx->l2_engine = engine;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_set_hamming_engine(esfm_ctx_t* ctx, int engine) {
+    if (!ctx) return fail(ESFM_ERR_INVALID, "ctx is NULL");
+    if (engine != ESFM_HAMMING_ENGINE_POPC && engine != ESFM_HAMMING_ENGINE_TC) return fail(ESFM_ERR_INVALID, "unknown Hamming engine %d", engine);
+    ctx->hamming_engine = engine;
+    return ESFM_OK;
+}
+
+extern "C" int esfm_get_hamming_engine(esfm_ctx_t* ctx, int* engine) {
+    if (!ctx || !engine) return fail(ESFM_ERR_INVALID, "esfm_get_hamming_engine: NULL argument");
+    *engine = ctx->hamming_engine;
     return ESFM_OK;
 }
 
@@ -536,6 +555,8 @@ struct ChunkPlan {
     size_t chunk_pairs;
 };
 
+bool use_tc(const esfm_ctx* ctx, const esfm_bank* b);
+
 ChunkPlan plan_chunks(const esfm_bank* b, int64_t n_pairs) {
     ChunkPlan pl;
     const int padded = ((b->max_rows + kTile - 1) / kTile) * kTile;
@@ -555,7 +576,7 @@ int ensure_scratch(esfm_ctx* ctx, const esfm_bank* b, const ChunkPlan& pl) {
     size_t cap = ctx->keys_bytes / sizeof(u64);
     if (int rc = grow(&ctx->keys, &cap, key_elems)) return rc;
     ctx->keys_bytes = cap * sizeof(u64);
-    if (b->kind == ESFM_KIND_F32X64)
+    if (b->kind == ESFM_KIND_F32X64 || use_tc(ctx, b))
         if (int rc = grow(&ctx->col_thr, &ctx->col_thr_elems, pl.chunk_pairs * (size_t)pl.stride)) return rc;
     size_t arena_need = pl.chunk_pairs * (size_t)std::max(b->max_rows, 1);
     if (int rc = grow(&ctx->arena, &ctx->arena_cap, arena_need)) return rc;
@@ -569,11 +590,12 @@ int ensure_scratch(esfm_ctx* ctx, const esfm_bank* b, const ChunkPlan& pl) {
     return ESFM_OK;
 }
 
-// Tensor-core operand images of an F32X64 bank, built the first time the TC engine sweeps it.
+// Tensor-core operand images of a bank (tc_layout.cuh: 3xTF32 hi/lo images for F32X64, FP8 +-1 images for B256), built the
+// first time a tensor-core engine sweeps it.
 int ensure_tc_layout(esfm_ctx* ctx, esfm_bank* b) {
-    if (b->d_tc || b->kind != ESFM_KIND_F32X64) return ESFM_OK;
+    if (b->d_tc) return ESFM_OK;
     const int n_tiles = b->tile_off[b->n_frames];
-    b->tc_bytes = ((size_t)n_tiles + 1) * kTcTileBytes;
+    b->tc_bytes = ((size_t)n_tiles + 1) * (b->kind == ESFM_KIND_F32X64 ? (size_t)kTcTileBytes : (size_t)kTc8TileBytes);
     cudaError_t e = cudaMallocAsync((void**)&b->d_tc, b->tc_bytes, ctx->stream);
     if (e != cudaSuccess) {
         const size_t want = b->tc_bytes;
@@ -581,17 +603,21 @@ int ensure_tc_layout(esfm_ctx* ctx, esfm_bank* b) {
         b->tc_bytes = 0;
         return fail(ESFM_ERR_NOMEM, "cudaMallocAsync(%zu) for the tensor-core bank failed: %s", want, cudaGetErrorString(e));
     }
-    e = launch_pack_tc((const float*)b->d_rows, b->d_frame_rows, b->d_row_off, b->d_tile_off, b->n_frames, n_tiles, b->d_tc, ctx->stream);
-    if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "pack_tc kernel launch failed: %s", cudaGetErrorString(e));
+    e = b->kind == ESFM_KIND_F32X64
+            ? launch_pack_tc((const float*)b->d_rows, b->d_frame_rows, b->d_row_off, b->d_tile_off, b->n_frames, n_tiles, b->d_tc, ctx->stream)
+            : launch_pack_tc8((const uint32_t*)b->d_rows, b->d_frame_rows, b->d_row_off, b->d_tile_off, b->n_frames, n_tiles, b->d_tc, ctx->stream);
+    if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "tensor-core pack kernel launch failed: %s", cudaGetErrorString(e));
     if (n_tiles > 0) ctx->stats.kernel_launches += 1;
     return ESFM_OK;
 }
 
-bool use_tc(const esfm_ctx* ctx, const esfm_bank* b) { return b->kind == ESFM_KIND_F32X64 && ctx->l2_engine == ESFM_L2_ENGINE_TC; }
+bool use_tc(const esfm_ctx* ctx, const esfm_bank* b) {
+    return b->kind == ESFM_KIND_F32X64 ? ctx->l2_engine == ESFM_L2_ENGINE_TC : ctx->hamming_engine == ESFM_HAMMING_ENGINE_TC;
+}
 
 int units_per_pair(const esfm_ctx* ctx, const esfm_bank* b, size_t n_chunk_pairs) {
     if (n_chunk_pairs >= (size_t)4 * ctx->sm_count) return 1;
-    const int qblock_rows = b->kind == ESFM_KIND_F32X64 ? (use_tc(ctx, b) ? kTile : kQTiles * kTile) : kConsumerThreads * kHamRQ;
+    const int qblock_rows = use_tc(ctx, b) ? kTile : (b->kind == ESFM_KIND_F32X64 ? kQTiles * kTile : kConsumerThreads * kHamRQ);
     const int max_blocks = std::max(1, (b->max_rows + qblock_rows - 1) / qblock_rows);
     const int want = (int)((4 * (size_t)ctx->sm_count + n_chunk_pairs - 1) / std::max<size_t>(n_chunk_pairs, 1));
     return std::max(1, std::min(want, max_blocks));
@@ -604,9 +630,11 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     CUDA_TRY(cudaMemsetAsync(ctx->d_cursor, 0, 2 * sizeof(unsigned long long), ctx->stream));
     const bool tc = use_tc(ctx, b);
     if (tc) if (int rc = ensure_tc_layout(ctx, b)) return rc;
-    if (b->kind == ESFM_KIND_F32X64)  // column thresholds start at "no bound yet": 0x7f7f7f7f = 3.39e38f (FFMA engine),
+    if (b->kind == ESFM_KIND_F32X64 || tc)  // column thresholds start at "no bound yet": 0x7f7f7f7f = 3.39e38f (FFMA engine),
                                       // 0x6f6f6f6f = 7.4e28f (TC engine: below its 1e30 pad-row norm)
-        CUDA_TRY(cudaMemsetAsync(ctx->col_thr, tc ? 0x6F : 0x7F, n * (size_t)pl.stride * sizeof(uint32_t), ctx->stream));
+        // (TC engine: 0x6f6f6f6f = 7.4e28f for SURF, 0x47474747 = 51015f for ORB -- above every real value, below the pad rows)
+        CUDA_TRY(cudaMemsetAsync(ctx->col_thr, tc ? (b->kind == ESFM_KIND_F32X64 ? 0x6F : 0x47) : 0x7F,
+                                 n * (size_t)pl.stride * sizeof(uint32_t), ctx->stream));
     SweepParams sp{};
     sp.kmajor = b->d_kmajor;
     sp.rows_f32 = (const float*)b->d_rows;
@@ -624,10 +652,11 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     sp.col_cap = pl.col_cap;
     if (const char* dbg = getenv("ESFM_TC_DEBUG")) sp.debug_flags = atoi(dbg);
     sp.tc_qtiles = ctx->tc_qtiles;
+    sp.tc_kind = b->kind;
     if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
-    cudaError_t e = b->kind == ESFM_KIND_F32X64 ? (tc ? launch_sweep_l2_tc(sp, ctx->sm_count, ctx->stream)
-                                                      : launch_sweep_l2(sp, ctx->sm_count, ctx->stream))
-                                                : launch_sweep_hamming(sp, ctx->sm_count, ctx->stream);
+    cudaError_t e = tc ? launch_sweep_l2_tc(sp, ctx->sm_count, ctx->stream)
+                       : (b->kind == ESFM_KIND_F32X64 ? launch_sweep_l2(sp, ctx->sm_count, ctx->stream)
+                                                      : launch_sweep_hamming(sp, ctx->sm_count, ctx->stream));
     if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(e));
     if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
     FinalizeParams fp{};
@@ -642,6 +671,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     fp.stride = pl.stride;
     fp.ratio = ratio;
     fp.cross_check = cross_check ? 1 : 0;
+    fp.b256_float_keys = (tc && b->kind == ESFM_KIND_B256) ? 1 : 0;
     fp.arena = ctx->arena;
     fp.arena_cap = ctx->arena_cap;
     fp.cursor = ctx->d_cursor;

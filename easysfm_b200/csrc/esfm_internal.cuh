@@ -56,6 +56,7 @@ struct SweepParams {
     uint32_t* col_thr;          // [n_pairs][stride] running column thresholds (float bits), L2 sweeps only
     int stride;                 // keys per array (>= padded rows of the largest frame in the chunk)
     int col_cap;                // Hamming sweep: smem column-minimum capacity in entries
+    int tc_kind;                // TC sweep: ESFM_KIND_F32X64 (3xTF32 L2) or ESFM_KIND_B256 (FP8 Hamming); tc_main holds that kind's images
     int tc_qtiles;              // TC sweep geometry: query tiles per block, 1 or 2 ($ESFM_TC_QT)
     int debug_flags;            // TC sweep pipeline probes ($ESFM_TC_DEBUG; results are WRONG when set): 1 = epilogue only drains,
                                 // 2 = no MMAs issued, 4 = no train-tile loads
@@ -79,6 +80,7 @@ struct FinalizeParams {
     unsigned long long* pair_off;  // [n_pairs] offset of each pair's matches in the arena
     int32_t* pair_cnt;          // [n_pairs]
     int* overflow;              // set to 1 if the arena was too small
+    int b256_float_keys;        // B256 keys come from the tensor-core sweep: high word = float bits of 2 * hamming (else the integer)
     // optional raw knn output for one pair (esfm_knn2_pair)
     int32_t* knn_idx;
     float* knn_dist;
@@ -87,6 +89,8 @@ struct FinalizeParams {
 // ---- host-side launchers (defined in the .cu files) -------------------------------------------
 cudaError_t launch_pack_f32(const float* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
                             int n_frames, int n_tiles_total, float* kmajor, cudaStream_t s);
+cudaError_t launch_pack_tc8(const uint32_t* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
+                            int n_frames, int n_tiles_total, unsigned char* tc_main, cudaStream_t s);
 cudaError_t launch_pack_tc(const float* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
                            int n_frames, int n_tiles_total, unsigned char* tc_main, cudaStream_t s);
 cudaError_t launch_sweep_l2(const SweepParams& p, int sm_count, cudaStream_t s);

@@ -48,7 +48,7 @@ __device__ __forceinline__ RowResult eval_row(const FinalizeParams& p, const u64
     if (k1 != kKeyInit) {
         i1 = (int)(uint32_t)k1;
         if (KIND == ESFM_KIND_F32X64) d1 = l2_direct(qrows + (size_t)q * kDim, trows + (size_t)i1 * kDim);
-        else d1 = (float)(uint32_t)(k1 >> 32);
+        else d1 = p.b256_float_keys ? 0.5f * __uint_as_float((uint32_t)(k1 >> 32)) : (float)(uint32_t)(k1 >> 32);
     }
     if (k2 != kKeyInit) {
         i2 = (int)(uint32_t)k2;
@@ -56,7 +56,7 @@ __device__ __forceinline__ RowResult eval_row(const FinalizeParams& p, const u64
             d2 = l2_direct(qrows + (size_t)q * kDim, trows + (size_t)i2 * kDim);
             order2(d1, i1, d2, i2);
         } else {
-            d2 = (float)(uint32_t)(k2 >> 32);
+            d2 = p.b256_float_keys ? 0.5f * __uint_as_float((uint32_t)(k2 >> 32)) : (float)(uint32_t)(k2 >> 32);
         }
     }
     if (knn_idx) {

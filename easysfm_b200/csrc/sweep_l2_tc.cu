@@ -49,13 +49,21 @@ constexpr int kTcStages = 3;                 // shared-memory train stages (68 K
 // operand (hi 64 | lo 64 per tile) + the accumulator stages (128 columns each).
 //   QT = 1: 3 accumulator stages; every train tile in shared memory feeds one accumulator.
 //   QT = 2: 2 accumulator stages; every train tile feeds two accumulators (half the L2 -> shared-memory traffic and power).
-template <int QT> struct TcGeom {
-    static constexpr int kAccStages = 4 - QT;
-    static constexpr uint32_t kACol0 = 128u * (4 - QT);     // tensor-memory column of query tile 0's operand
+// KIND = ESFM_KIND_F32X64: 3xTF32, query operand = 128 columns (hi 64 | lo 64), train tile image 68 KB;
+// KIND = ESFM_KIND_B256:   Hamming as an FP8 +-1 dot product (tc_layout.cuh), query operand = 64 columns, image 36 KB.
+template <int QT, int KIND> struct TcGeom {
+    static constexpr int kACols = KIND == ESFM_KIND_F32X64 ? 128 : 64;
+    static constexpr int kAccStages = (512 - QT * kACols) / 128;
+    static constexpr uint32_t kACol0 = 128u * kAccStages;   // tensor-memory column of query tile 0's operand
+    static constexpr int kMainBytes = KIND == ESFM_KIND_F32X64 ? kTcMainBytes : kTc8MainBytes;
+    static constexpr int kGroupBytes = KIND == ESFM_KIND_F32X64 ? kTcGroupBytes : kTc8GroupBytes;
+    static constexpr int kTileBytes = kMainBytes + kTcAugBytes;
 };
 constexpr int kTcThrBytes = kTile * 4;                  // 512: column thresholds riding with a train tile
 constexpr int kTcThrStages = 4;                         // threshold snapshots have their own (deeper) ring
-constexpr uint32_t kTcBoundBits = 0x6f6f6f6fu;          // 7.4e28f: "no bound yet" (what memset(0x6f) writes); pads are 1e30
+// "no bound yet" (also what cudaMemsetAsync writes into the column thresholds, hence a repeated byte): above every real value,
+// below the pad rows.  SURF: 7.4e28 (pads: 1e30).  ORB: 51015 (real 2 * hamming <= 512, pads >= 200704).
+constexpr uint32_t kTcBoundBitsF32 = 0x6f6f6f6fu, kTcBoundBitsB256 = 0x47474747u;
 
 struct TcUnit {
     int pair, q_frame, t_frame;
@@ -127,10 +135,16 @@ constexpr int kTcSleepEpilogue = 0;
 
 }  // namespace
 
-template <int kTcQTiles>
+template <int kTcQTiles, int KIND>
 __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepParams p) {
-    constexpr int kTcAccStages = TcGeom<kTcQTiles>::kAccStages;
-    constexpr uint32_t kTcACol0 = TcGeom<kTcQTiles>::kACol0;
+    using G = TcGeom<kTcQTiles, KIND>;
+    constexpr int kTcAccStages = G::kAccStages;
+    constexpr uint32_t kTcACol0 = G::kACol0;
+    constexpr int kACols = G::kACols;
+    constexpr int kTcTileBytes = G::kTileBytes;       // (shadows the SURF constant of tc_layout.cuh)
+    constexpr int kTcMainBytes = G::kMainBytes;
+    constexpr int kTcGroupBytes = G::kGroupBytes;
+    constexpr uint32_t kTcBoundBits = KIND == ESFM_KIND_F32X64 ? kTcBoundBitsF32 : kTcBoundBitsB256;
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -211,7 +225,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
         // descriptors live in uniform registers); one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
         // (Issuing from inside `if (lane == 0)` made the compiler wrap every MMA in an ELECT / R2UR.BROADCAST waterfall
         // loop: 16 dependent instructions and ~90 cycles per MMA, longer than the MMA itself.)
-        constexpr uint32_t idesc = tc_idesc_tf32(128, 128);
+        constexpr uint32_t idesc = KIND == ESFM_KIND_F32X64 ? tc_idesc_tf32(128, 128) : tc_idesc_e4m3(128, 128);
         const uint64_t qad0 = tc_desc_nosw(smem_u32(Qa), 128, kTcAugGroupBytes);
         const uint64_t td0 = tc_desc_sw128(smem_u32(Ts), kTcGroupBytes);
         const uint64_t tad0 = tc_desc_nosw(smem_u32(Ts) + kTcMainBytes, 128, kTcAugGroupBytes);
@@ -234,7 +248,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                         mbar_wait_sleep<kTcSleepIssuer>(&accEmpty[as], aph ^ 1);
                         tc_fence_after();
                         const uint32_t d = tmem + as * 128;
-                        const uint32_t acol = tmem + kTcACol0 + h * 128;
+                        const uint32_t acol = tmem + kTcACol0 + h * kACols;
+                        if (KIND == ESFM_KIND_B256) {
+                            if (!(p.debug_flags & 2) && elect_one()) {
+                                // 256 FP8 values per row = 8 k-steps of K = 32 (32 bytes: the same descriptor arithmetic as TF32's K = 8)
+#pragma unroll
+                                for (int ks = 0; ks < 8; ++ks) {
+                                    const uint32_t off = ((ks >> 2) * 1024 + (ks & 3) * 32) >> 4;
+                                    tc_mma_f8_ts(d, acol + ks * 8, td + (uint64_t)off, idesc, ks > 0);
+                                }
+                                // - 256 and the pad-row penalties (tc_layout.cuh)
+                                tc_mma_f8(d, qad0 + (uint64_t)(h * (kTcAugBytes >> 4)), tad, idesc, true);
+                            }
+                        } else
                         if (!(p.debug_flags & 2) && elect_one()) {
                             bool first = true;
 #pragma unroll
@@ -275,6 +301,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const TcUnit u = tc_decode_unit(p, unit);
             const int fq = p.frame_rows[u.q_frame];
+            if (KIND == ESFM_KIND_B256) {
+                // ---- ORB: 256 bits -> 256 FP8 values +-1.0, 4 per tensor-memory column ----
+                const uint4* qbits = p.rows_b256 + (size_t)p.frame_row_off[u.q_frame] * 2;
+                for (int qt = u.qb0; qt < u.qb1; ++qt) {
+                    const int h = (qt - u.qb0) & (kTcQTiles - 1);
+                    const int r = qt * kTile + trow;
+                    const bool valid = r < fq;
+                    uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
+                    if (valid) { w0 = __ldg(qbits + (size_t)r * 2); w1 = __ldg(qbits + (size_t)r * 2 + 1); }
+                    const uint32_t use = h == 0 ? quse[0] : quse[1];
+                    if (use > 0) named_bar_sync(2 + h, 128 + 32);      // slot h free (see the SURF branch below)
+                    if (h == 0) ++quse[0]; else ++quse[1];
+                    tc_fence_after();
+                    // augmented columns: (qpad ? 448 : 0, 448, 16, 0 ...) in FP8
+                    unsigned char* qa = Qa + h * kTcAugBytes + (trow >> 3) * kTcAugGroupBytes + (trow & 7) * 16;
+                    *reinterpret_cast<uint4*>(qa) = make_uint4((valid ? 0u : kFp8Pos448) | (kFp8Pos448 << 8) | (kFp8Pos16 << 16), 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(qa + 128) = make_uint4(0u, 0u, 0u, 0u);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    const uint32_t acol = tmem + lane_addr + kTcACol0 + h * kACols;
+                    const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {       // word m = elements 32 m .. 32 m + 31 = 8 columns
+                        uint32_t c[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) c[j] = valid ? tc8_expand4(ws[m] >> (4 * j)) : 0u;
+                        tmem_st8(acol + m * 8, c);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&fullQ[h]);
+                }
+                continue;
+            }
             const float4* qrows = reinterpret_cast<const float4*>(p.rows_f32 + (size_t)p.frame_row_off[u.q_frame] * kDim);
             for (int qt = u.qb0; qt < u.qb1; ++qt) {
                 const int h = (qt - u.qb0) & (kTcQTiles - 1);
@@ -304,7 +364,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                 *reinterpret_cast<float4*>(qa) = make_float4(1.f, 1.f, 1.f, hqh);
                 *reinterpret_cast<float4*>(qa + 128) = make_float4(hqm, hql, 0.f, 0.f);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async reads
-                const uint32_t acol = tmem + lane_addr + kTcACol0 + h * 128;
+                const uint32_t acol = tmem + lane_addr + kTcACol0 + h * kACols;
                 // pass 2: the row again (L1/L2 hit), 8 dims at a time -> hi / lo columns of tensor memory
 #pragma unroll 2
                 for (int m = 0; m < 8; ++m) {
@@ -514,19 +574,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     if (warp == kTcEpiWarps + 1) tmem_free(tmem, 512);
 }
 
-size_t sweep_l2_tc_smem_bytes(int qt) {
-    return 1024 + (size_t)kTcStages * kTcTileBytes + (size_t)qt * kTcAugBytes + (size_t)kTcThrStages * kTcThrBytes +
+size_t sweep_tc_smem_bytes(int qt, int kind) {
+    const size_t tile = kind == ESFM_KIND_F32X64 ? (size_t)kTcTileBytes : (size_t)kTc8TileBytes;
+    const int acc = (512 - qt * (kind == ESFM_KIND_F32X64 ? 128 : 64)) / 128;
+    return 1024 + (size_t)kTcStages * tile + (size_t)qt * kTcAugBytes + (size_t)kTcThrStages * kTcThrBytes +
            (size_t)qt * 2 * kTile * sizeof(u64) + (size_t)qt * kTile * 4 +
-           (qt + 2 * kTcStages + 2 * (4 - qt) + 2 * kTcThrStages) * 8 + 16;
+           (qt + 2 * kTcStages + 2 * acc + 2 * kTcThrStages) * 8 + 16;
 }
 
+// kind = p.tc_kind: ESFM_KIND_F32X64 (3xTF32 L2 sweep) or ESFM_KIND_B256 (FP8 Hamming sweep)
 cudaError_t launch_sweep_l2_tc(const SweepParams& p, int sm_count, cudaStream_t s) {
     const int n_units = p.n_pairs * p.units_per_pair;
     if (n_units <= 0) return cudaSuccess;
     const int grid = n_units < sm_count ? n_units : sm_count;
     const int qt = p.tc_qtiles == 2 ? 2 : 1;
-    const size_t smem = sweep_l2_tc_smem_bytes(qt);
-    auto kern = qt == 2 ? sweep_l2_tc_kernel<2> : sweep_l2_tc_kernel<1>;
+    const int kind = p.tc_kind == ESFM_KIND_B256 ? ESFM_KIND_B256 : ESFM_KIND_F32X64;
+    const size_t smem = sweep_tc_smem_bytes(qt, kind);
+    void (*kern)(const SweepParams) =
+        kind == ESFM_KIND_B256 ? (qt == 2 ? sweep_l2_tc_kernel<2, ESFM_KIND_B256> : sweep_l2_tc_kernel<1, ESFM_KIND_B256>)
+                               : (qt == 2 ? sweep_l2_tc_kernel<2, ESFM_KIND_F32X64> : sweep_l2_tc_kernel<1, ESFM_KIND_F32X64>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kTcThreads, smem, s>>>(p);

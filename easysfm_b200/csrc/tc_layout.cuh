@@ -83,6 +83,26 @@ inline void tc_pack_row_host(const float* x, bool valid, bool query_role, uint8_
     for (int j = 0; j < 8; ++j) memcpy(tile + kTcMainBytes + g * kTcAugGroupBytes + tc_aug_off(rr, j), &a[j], 4);
 }
 
+// ---- ORB / Hamming on the tensor cores: 256 bits -> 256 FP8 (E4M3) values +-1 ----------------------------------------
+// bit 0 -> +1.0 (0x38), bit 1 -> -1.0 (0xB8): the dot product of two such rows is 256 - 2 * hamming, an exact small integer in
+// the fp32 accumulator.  One more K = 32 MMA over augmented columns adds -256 and pushes pad rows out of reach:
+//     q' = (qpad ? 448 : 0,  448,               16, 0 x 29)
+//     t' = (-448,            tpad ? -448 : 0,  -16, 0 x 29)         =>  accumulator = -2 * hamming   (pads: < -200000)
+// so the selection epilogue is the SURF one unchanged (it ranks "- 1/2 d^2").
+// Image per 128-row tile (kTc8TileBytes = 36864): 16 groups x 2048 B = [k 0..127][k 128..255] SWIZZLE_128B atoms of 8 rows x
+// 128 B, then 16 x 256 B augmented columns in the same no-swizzle form as the SURF image (K = 32 bytes = 2 chunks of 16).
+constexpr int kTc8GroupBytes = 2048;
+constexpr int kTc8MainBytes = 16 * kTc8GroupBytes;            // 32768
+constexpr int kTc8TileBytes = kTc8MainBytes + kTcAugBytes;    // 36864
+constexpr unsigned kFp8Pos448 = 0x7e, kFp8Neg448 = 0xfe, kFp8Pos16 = 0x58, kFp8Neg16 = 0xd8;
+
+// 4 descriptor bits (low nibble of n) -> 4 FP8 bytes, bit i in byte i
+__host__ __device__ __forceinline__ uint32_t tc8_expand4(uint32_t n) {
+    return ((((n & 0xfu) * 0x00204081u) & 0x01010101u) << 7) | 0x38383838u;
+}
+// byte offset of element (row rr in [0,8), k in [0,128)) inside one 1024-byte SWIZZLE_128B atom of bytes
+__host__ __device__ __forceinline__ int tc8_sw128_off(int rr, int k) { return rr * 128 + ((((k >> 4) ^ rr) & 7) << 4) + (k & 15); }
+
 #ifdef __CUDACC__
 // ---- shared-memory matrix descriptors (tcgen05.mma operand A / B), K-major ---------------------------------------
 // bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
@@ -97,6 +117,27 @@ __device__ __forceinline__ uint64_t tc_desc_nosw(uint32_t saddr, uint32_t lbo_by
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28.
 __host__ __device__ constexpr uint32_t tc_idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// kind::f8f6f4 with A = B = E4M3 (format code 0), D = F32
+__host__ __device__ constexpr uint32_t tc_idesc_e4m3(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_f8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
 }
 
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {

@@ -113,6 +113,14 @@ int esfm_device_sm_count(esfm_ctx_t* ctx, int* sms);
 #define ESFM_L2_ENGINE_TC 1
 int esfm_set_l2_engine(esfm_ctx_t* ctx, int engine);
 int esfm_get_l2_engine(esfm_ctx_t* ctx, int* engine);
+/* Which kernel serves ESFM_KIND_B256: XOR + POPC on the integer pipes (the north-star design), or the same Hamming
+ * distance as an exact FP8 (+-1) dot product on the tcgen05 tensor cores (256 - 2 * hamming accumulates as a small integer
+ * in fp32; 1.8x faster).  Both are bit-exact against OpenCV and against each other; default: $ESFM_HAMMING_ENGINE
+ * ("popc" | "tc") at esfm_init, else ESFM_HAMMING_ENGINE_TC. */
+#define ESFM_HAMMING_ENGINE_POPC 0
+#define ESFM_HAMMING_ENGINE_TC 1
+int esfm_set_hamming_engine(esfm_ctx_t* ctx, int engine);
+int esfm_get_hamming_engine(esfm_ctx_t* ctx, int* engine);
 
 /* ---- descriptor bank (replaces the per-call cv::Mat arguments; utility.h:31) ---------------- */
 

@@ -14,12 +14,13 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session", params=["ffma", "tc"])
 def ctx(request):
-    """One CUDA context per L2 engine for the whole GPU session (every test that takes `ctx` runs once on the
-    exact-FP32 FFMA sweep and once on the tcgen05 3xTF32 sweep; the Hamming path is the same kernel in both);
-    fails loudly if the library or the device is missing."""
+    """One CUDA context per engine family for the whole GPU session: every test that takes `ctx` runs once on the CUDA-core
+    sweeps (exact-FP32 FFMA for SURF, XOR + POPC for ORB) and once on the tcgen05 sweeps (3xTF32 for SURF, FP8 +-1 dot product
+    for ORB); fails loudly if the library or the device is missing."""
     import easysfm_b200 as esfm
     c = esfm.Context(0)
     c.set_l2_engine(request.param)
-    assert c.l2_engine() == request.param
+    c.set_hamming_engine({"ffma": "popc", "tc": "tc"}[request.param])
+    assert c.l2_engine() == request.param and c.hamming_engine() == {"ffma": "popc", "tc": "tc"}[request.param]
     yield c
     c.close()

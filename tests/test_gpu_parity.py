@@ -186,3 +186,53 @@ def test_set_frame_pinned_equals_set_frame(ctx):
         b2 = ctx.bank(kind, 1)
         with pytest.raises(esfm.EsfmError):
             b2.set_frame_pinned(0, frames[0])          # pageable numpy memory
+
+
+@pytest.mark.parametrize("nq,nt,levels", [(300, 700, 3), (129, 1025, 2), (515, 260, 5)])
+def test_l2_exact_ties_on_quantised_descriptors(ctx, nq, nt, levels):
+    """Descriptors quantised to a few levels (k/8): every distance is exact in fp32 in every implementation (OpenCV, the C
+    oracle, the FP32-FMA sweep, the 3xTF32 tensor-core sweep), so the data is full of EXACT ties at rank 1 and 2 and the
+    lowest-index rule must hold index for index -- forward knn-2, ratio test and mutual cross-check."""
+    rng = np.random.default_rng(nq * 31 + nt)
+    Q = (rng.integers(-levels, levels + 1, (nq, 64)) / 8.0).astype(np.float32)
+    T = (rng.integers(-levels, levels + 1, (nt, 64)) / 8.0).astype(np.float32)
+    T[7] = T[3]; T[nt - 1] = T[3]; Q[11] = T[3]; Q[12] = T[3]
+    bank = ctx.bank_from_frames([Q, T])
+    idx, dist = bank.knn2_pair(0, 1)
+    ridx, rdist = oracle.knn2(Q, T)
+    np.testing.assert_array_equal(idx, ridx)
+    np.testing.assert_array_equal(dist, rdist)
+    cidx, cdist = cv2_oracle.knn2(Q, T)
+    np.testing.assert_array_equal(idx, cidx)
+    np.testing.assert_array_equal(dist, cdist)
+    for ratio in (0.8, 1.0, float("inf")):
+        for cc in (False, True):
+            if ratio == float("inf") and not cc:
+                continue
+            assert_matches_equal(ctx.match_descriptors(Q, T, ratio, cc), oracle.match(Q, T, ratio, cc))
+
+
+def test_hamming_engines_are_byte_identical(ctx):
+    """XOR + POPC and the FP8 +-1 tensor-core dot product give the same bytes: matches (ratio / cross-check / mutual-NN mode)
+    and raw knn-2, on a ragged bank with empty, 1-row, non-multiple-of-128 frames and exact duplicates."""
+    rows = [700, 0, 1, 129, 1025, 2, 512, 300]
+    frames = synth.orb_like(len(rows), rows, seed=9)
+    frames[4][10] = frames[4][3]; frames[6][5] = frames[4][3]; frames[6][7] = frames[4][3]
+    keep = ctx.hamming_engine()
+    out = {}
+    try:
+        for eng in ("popc", "tc"):
+            ctx.set_hamming_engine(eng)
+            bank = ctx.bank_from_frames(frames)
+            per = []
+            for ratio, cc in ((0.8, True), (0.8, False), (float("inf"), True)):
+                res = bank.match_all_pairs(ratio, cc)
+                per += [res.pair_at(k)[2].tobytes() for k in range(res.n_pairs)]
+            for (i, j) in ((4, 6), (6, 4), (0, 7), (3, 2), (0, 5), (2, 0)):
+                idx, dist = bank.knn2_pair(i, j)
+                per += [idx.tobytes(), dist.tobytes()]
+            out[eng] = per
+            bank.close()
+    finally:
+        ctx.set_hamming_engine(keep)
+    assert out["popc"] == out["tc"]
