@@ -48,7 +48,8 @@ struct esfm_ctx {
     bool own_stream = false;
     int sm_count = 0;
     bool profiling = true;
-    int tc_qtiles = 1;                     // TC sweep geometry: query tiles per block (1 or 2; $ESFM_TC_QT)
+    int tc_qtiles = 1;                     // TC sweep geometry, SURF: query tiles per block (1 or 2; $ESFM_TC_QT)
+    int tc_qtiles_orb = 1;                 // TC sweep geometry, ORB (1 or 2; $ESFM_TC_QT_ORB): 3 accumulator stages either way
     int hamming_engine = ESFM_HAMMING_ENGINE_TC;     // which sweep kernel serves ESFM_KIND_B256 (esfm_set_hamming_engine / $ESFM_HAMMING_ENGINE)
     int l2_engine = ESFM_L2_ENGINE_TC;     // which sweep kernel serves ESFM_KIND_F32X64 (esfm_set_l2_engine / $ESFM_L2_ENGINE)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -198,6 +199,7 @@ extern "C" int esfm_init(int device, void* cuda_stream, esfm_ctx_t** out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* qt = getenv("ESFM_TC_QT")) ctx->tc_qtiles = atoi(qt) == 2 ? 2 : 1;
+    if (const char* qt = getenv("ESFM_TC_QT_ORB")) ctx->tc_qtiles_orb = atoi(qt) == 2 ? 2 : 1;
     if (const char* eng = getenv("ESFM_HAMMING_ENGINE")) {
         if (!strcmp(eng, "tc") || !strcmp(eng, "tensor")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_TC;
         else if (!strcmp(eng, "popc")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_POPC;
@@ -651,7 +653,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     sp.stride = pl.stride;
     sp.col_cap = pl.col_cap;
     if (const char* dbg = getenv("ESFM_TC_DEBUG")) sp.debug_flags = atoi(dbg);
-    sp.tc_qtiles = ctx->tc_qtiles;
+    sp.tc_qtiles = b->kind == ESFM_KIND_B256 ? ctx->tc_qtiles_orb : ctx->tc_qtiles;
     sp.tc_kind = b->kind;
     if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
     cudaError_t e = tc ? launch_sweep_l2_tc(sp, ctx->sm_count, ctx->stream)

@@ -57,7 +57,7 @@ struct SweepParams {
     int stride;                 // keys per array (>= padded rows of the largest frame in the chunk)
     int col_cap;                // Hamming sweep: smem column-minimum capacity in entries
     int tc_kind;                // TC sweep: ESFM_KIND_F32X64 (3xTF32 L2) or ESFM_KIND_B256 (FP8 Hamming); tc_main holds that kind's images
-    int tc_qtiles;              // TC sweep geometry: query tiles per block, 1 or 2 ($ESFM_TC_QT)
+    int tc_qtiles;              // TC sweep geometry: query tiles per block, 1 or 2 ($ESFM_TC_QT, $ESFM_TC_QT_ORB)
     int debug_flags;            // TC sweep pipeline probes ($ESFM_TC_DEBUG; results are WRONG when set): 1 = epilogue only drains,
                                 // 2 = no MMAs issued, 4 = no train-tile loads
 };
