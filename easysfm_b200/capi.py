@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 import numpy as np
@@ -151,9 +152,13 @@ class Context:
         _check(self._lib.esfm_init(int(device), c_void_p(stream) if stream else None, ctypes.byref(h)))
         self._h = h
         self.device = int(device)
+        # banks and result batches borrow the context's stream, scratch and pinned pool: they must go first
+        self._children = weakref.WeakSet()
 
     def close(self):
         if getattr(self, "_h", None):
+            for child in list(getattr(self, "_children", ())):
+                child.close()
             self._lib.esfm_destroy(self._h)
             self._h = None
 
@@ -246,6 +251,7 @@ class Bank:
         _check(self._lib.esfm_bank_create(ctx._h, int(kind), int(n_frames), ctypes.byref(h)))
         self._h = h
         self.n_frames = int(n_frames)
+        ctx._children.add(self)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -308,14 +314,14 @@ class Bank:
     def match_all_pairs(self, ratio: float, cross_check: bool = False) -> "Results":
         h = c_void_p()
         _check(self._lib.esfm_match_all_pairs(self._h, float(ratio), int(bool(cross_check)), ctypes.byref(h)))
-        return Results(self._lib, h)
+        return Results(self._lib, h, self.ctx)
 
     def match_pairs(self, pairs, ratio: float, cross_check: bool = False, device_resident: bool = False) -> "Results":
         p = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
         h = c_void_p()
         fn = self._lib.esfm_match_pairs_device if device_resident else self._lib.esfm_match_pairs
         _check(fn(self._h, p.ctypes.data, p.shape[0], float(ratio), int(bool(cross_check)), ctypes.byref(h)))
-        return Results(self._lib, h)
+        return Results(self._lib, h, self.ctx)
 
     def match_pair(self, query_frame: int, train_frame: int, ratio: float, cross_check: bool = False) -> np.ndarray:
         cap = max(self.frame_rows(query_frame), 1)
@@ -376,9 +382,11 @@ def read_match_file(path: str):
 class Results:
     """Host-resident compacted matches of a batch of pairs (esfm_results_t)."""
 
-    def __init__(self, lib, handle):
+    def __init__(self, lib, handle, ctx=None):
         self._lib = lib
         self._h = handle
+        if ctx is not None:      # (a batch loaded from a match file has no context)
+            ctx._children.add(self)
         n_pairs, n_matches = c_int64(), c_int64()
         _check(lib.esfm_results_counts(handle, ctypes.byref(n_pairs), ctypes.byref(n_matches)))
         self.n_pairs = n_pairs.value

@@ -46,22 +46,25 @@ def match(Q, T, ratio: float, cross_check: bool):
     import cv2
     out = []
     nq, nt = Q.shape[0], T.shape[0]
-    if nq == 0 or nt < 2:
+    # ratio = +inf: no ratio test (include/esfm_match.h) -- one neighbour is enough and `d1 < inf * d2` is NOT evaluated
+    # (inf * 0 is NaN and would drop the exact duplicates that BFMatcher(crossCheck=True).match keeps)
+    no_ratio = ratio == float("inf")
+    if nq == 0 or nt < (1 if no_ratio else 2):
         return np.zeros(0, DMATCH_DTYPE)
     Q = np.ascontiguousarray(Q)
     T = np.ascontiguousarray(T)
     norm = _norm(Q)
-    fwd = cv2.BFMatcher(norm, crossCheck=False).knnMatch(Q, T, k=2)
+    fwd = cv2.BFMatcher(norm, crossCheck=False).knnMatch(Q, T, k=1 if no_ratio else 2)
     rev = None
     if cross_check:
         r = cv2.BFMatcher(norm, crossCheck=False).knnMatch(T, Q, k=1)
         rev = np.array([lst[0].trainIdx if lst else -1 for lst in r], np.int64)
     for q, lst in enumerate(fwd):
-        if len(lst) < 2:
+        if len(lst) < (1 if no_ratio else 2):
             continue
-        m, n = lst[0], lst[1]
+        m = lst[0]
         # Python floats are doubles: the same arithmetic as `float < double * float` in C++.
-        if not (float(m.distance) < float(ratio) * float(n.distance)):
+        if not no_ratio and not (float(m.distance) < float(ratio) * float(lst[1].distance)):
             continue
         if rev is not None and rev[m.trainIdx] != q:
             continue

@@ -205,11 +205,13 @@ def test_l2_exact_ties_on_quantised_descriptors(ctx, nq, nt, levels):
     cidx, cdist = cv2_oracle.knn2(Q, T)
     np.testing.assert_array_equal(idx, cidx)
     np.testing.assert_array_equal(dist, cdist)
-    for ratio in (0.8, 1.0, float("inf")):
+    for ratio in (0.8, 1.0, float("inf")):       # +inf = no ratio test: the duplicates (d2 = 0) must survive it
         for cc in (False, True):
-            if ratio == float("inf") and not cc:
-                continue
             assert_matches_equal(ctx.match_descriptors(Q, T, ratio, cc), oracle.match(Q, T, ratio, cc))
+    import cv2
+    want = sorted((m.queryIdx, m.trainIdx, m.distance) for m in cv2.BFMatcher(cv2.NORM_L2, crossCheck=True).match(Q, T))
+    got = ctx.match_descriptors(Q, T, float("inf"), True)
+    assert [(int(m["queryIdx"]), int(m["trainIdx"]), float(m["distance"])) for m in got] == want    # feature_match.py:26-27 itself
 
 
 def test_hamming_engines_are_byte_identical(ctx):

@@ -101,3 +101,40 @@ def test_oracle_thread_count_does_not_change_results():
     oracle.set_threads(0)
     b = oracle.match(Q, T, 0.8, True)
     assert_matches_equal(a, b)
+
+
+def _cv2_cross_check_call(Q, T):
+    """The reference's own mutual-NN call, python_code/feature_match.py:26-27, issued directly."""
+    import cv2
+    norm = cv2.NORM_L2 if Q.dtype == np.float32 else cv2.NORM_HAMMING
+    m = cv2.BFMatcher(norm, crossCheck=True).match(np.ascontiguousarray(Q), np.ascontiguousarray(T))
+    return sorted((x.queryIdx, x.trainIdx, x.distance) for x in m)
+
+
+def _as_tuples(m):
+    return [(int(x["queryIdx"]), int(x["trainIdx"]), float(x["distance"])) for x in m]
+
+
+@pytest.mark.parametrize("kind", ["surf", "orb"])
+def test_ratio_inf_is_no_ratio_test_even_for_exact_duplicates(kind):
+    """ratio = +inf means NO ratio test (include/esfm_match.h), not `d1 < inf * d2`: that product is NaN when the second
+    neighbour is an exact duplicate (d2 = 0) and would drop matches that BFMatcher(crossCheck=True).match keeps.  Both
+    oracles in this mode must equal that cv2 call, duplicates on both sides included; one train row is enough."""
+    if kind == "surf":
+        rng = np.random.default_rng(5)
+        Q = (rng.integers(-3, 4, (90, 64)) / 8.0).astype(np.float32)
+        T = (rng.integers(-3, 4, (140, 64)) / 8.0).astype(np.float32)
+    else:
+        Q, T = synth.orb_like(2, [90, 140], seed=6)
+    T[7] = T[3]; T[139] = T[3]; Q[11] = T[3]; Q[12] = T[3]
+    want = _cv2_cross_check_call(Q, T)
+    assert (11, 3, 0.0) in want and not any(q == 12 for q, _, _ in want)
+    for mod in (oracle, cv2_oracle):
+        assert _as_tuples(mod.match(Q, T, float("inf"), True)) == want
+        assert _as_tuples(mod.mutual_nn(Q, T)) == want
+        fwd = mod.match(Q, T, float("inf"), False)          # every query keeps its nearest neighbour
+        idx, dist = mod.knn2(Q, T)
+        assert len(fwd) == len(Q) and (fwd["trainIdx"] == idx[:, 0]).all() and (fwd["distance"] == dist[:, 0]).all()
+        one = mod.match(Q, T[:1], float("inf"), True)        # a single train row: its nearest query, nothing else
+        assert _as_tuples(one) == _cv2_cross_check_call(Q, T[:1])
+        assert len(mod.match(Q, T[:1], 1e30, True)) == 0     # a finite ratio still needs two neighbours (SURVEY F7)
