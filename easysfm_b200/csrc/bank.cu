@@ -116,7 +116,7 @@ cudaError_t launch_pack_tc(const float* rows, const int* frame_rows, const int* 
 __global__ void __launch_bounds__(256) pack_tc8_kernel(const uint32_t* __restrict__ rows, const int* __restrict__ frame_rows,
                                                        const int* __restrict__ frame_row_off,
                                                        const int* __restrict__ frame_tile_off, int n_frames,
-                                                       unsigned char* __restrict__ tc_main) {
+                                                       unsigned char* __restrict__ tc_main, int z_mode) {
     const int t = blockIdx.x;
     int lo = 0, hi = n_frames - 1;
     while (lo < hi) {
@@ -134,8 +134,13 @@ __global__ void __launch_bounds__(256) pack_tc8_kernel(const uint32_t* __restric
         uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = c0;          // pad rows: all-zero operands (+0.0)
         if (r < valid) {
             const uint32_t x = src[(size_t)r * 8 + w];
-            c0 = make_uint4(tc8_expand4(x), tc8_expand4(x >> 4), tc8_expand4(x >> 8), tc8_expand4(x >> 12));
-            c1 = make_uint4(tc8_expand4(x >> 16), tc8_expand4(x >> 20), tc8_expand4(x >> 24), tc8_expand4(x >> 28));
+            if (z_mode) {     // "Z" encoding (tc_layout.cuh): bit 0 -> -64, bit 1 -> +64
+                c0 = make_uint4(tcz_expand4_t(x), tcz_expand4_t(x >> 4), tcz_expand4_t(x >> 8), tcz_expand4_t(x >> 12));
+                c1 = make_uint4(tcz_expand4_t(x >> 16), tcz_expand4_t(x >> 20), tcz_expand4_t(x >> 24), tcz_expand4_t(x >> 28));
+            } else {
+                c0 = make_uint4(tc8_expand4(x), tc8_expand4(x >> 4), tc8_expand4(x >> 8), tc8_expand4(x >> 12));
+                c1 = make_uint4(tc8_expand4(x >> 16), tc8_expand4(x >> 20), tc8_expand4(x >> 24), tc8_expand4(x >> 28));
+            }
         }
         const int k = w * 32;                                   // first element of this word
         unsigned char* atom = out + (r >> 3) * kTc8GroupBytes + (k >> 7) * 1024;
@@ -146,15 +151,23 @@ __global__ void __launch_bounds__(256) pack_tc8_kernel(const uint32_t* __restric
         const int r = threadIdx.x;
         // train role: (-448, tpad ? -448 : 0, -16, 0 ...) against the query's (qpad ? 448 : 0, 448, 16, 0 ...)
         unsigned char* a = out + kTc8MainBytes + (r >> 3) * kTcAugGroupBytes + (r & 7) * 16;
+        if (z_mode) {
+            // offset slots + the row's index inside its frame, digit by digit; pad rows stay all-zero (masked by index in the sweep)
+            uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (r < valid) tcz_train_aug((uint32_t)(row0 + r), w);
+            *reinterpret_cast<uint4*>(a) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(a + 128) = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
         *reinterpret_cast<uint4*>(a) = make_uint4(kFp8Neg448 | ((r < valid ? 0u : kFp8Neg448) << 8) | (kFp8Neg16 << 16), 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(a + 128) = make_uint4(0u, 0u, 0u, 0u);
+        }
     }
 }
 
 cudaError_t launch_pack_tc8(const uint32_t* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
-                            int n_frames, int n_tiles_total, unsigned char* tc_main, cudaStream_t s) {
+                            int n_frames, int n_tiles_total, unsigned char* tc_main, int z_mode, cudaStream_t s) {
     if (n_tiles_total <= 0) return cudaSuccess;
-    pack_tc8_kernel<<<n_tiles_total, 256, 0, s>>>(rows, frame_rows, frame_row_off, frame_tile_off, n_frames, tc_main);
+    pack_tc8_kernel<<<n_tiles_total, 256, 0, s>>>(rows, frame_rows, frame_row_off, frame_tile_off, n_frames, tc_main, z_mode);
     return cudaGetLastError();
 }
 

@@ -50,6 +50,8 @@ struct esfm_ctx {
     bool profiling = true;
     int tc_qtiles = 1;                     // TC sweep geometry, SURF: query tiles per block (1 or 2; $ESFM_TC_QT)
     int tc_qtiles_orb = 1;                 // TC sweep geometry, ORB (1 or 2; $ESFM_TC_QT_ORB): 3 accumulator stages either way
+    int orb_z = 1;                         // ORB tensor-core sweep with the "Z" operand encoding (packed keys from the MMA): default;
+                                           // $ESFM_ORB_Z=0 selects the +-1 encoding with the generic epilogue, 2 the experimental epilogue
     int hamming_engine = ESFM_HAMMING_ENGINE_TC;     // which sweep kernel serves ESFM_KIND_B256 (esfm_set_hamming_engine / $ESFM_HAMMING_ENGINE)
     int l2_engine = ESFM_L2_ENGINE_TC;     // which sweep kernel serves ESFM_KIND_F32X64 (esfm_set_l2_engine / $ESFM_L2_ENGINE)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -116,6 +118,7 @@ struct esfm_bank {
     void* d_rows = nullptr;  size_t rows_bytes = 0;
     float* d_kmajor = nullptr; size_t kmajor_bytes = 0;
     unsigned char* d_tc = nullptr; size_t tc_bytes = 0;   // tensor-core operand images (built on first use), main then aug
+    int tc_z = 0;                                         // ... of a B256 bank: 0 = +-1 encoding, 1 = "Z" encoding (tc_layout.cuh)
     int* d_frame_rows = nullptr;
     int* d_row_off = nullptr;
     int* d_tile_off = nullptr;
@@ -200,6 +203,7 @@ extern "C" int esfm_init(int device, void* cuda_stream, esfm_ctx_t** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* qt = getenv("ESFM_TC_QT")) ctx->tc_qtiles = atoi(qt) == 2 ? 2 : 1;
     if (const char* qt = getenv("ESFM_TC_QT_ORB")) ctx->tc_qtiles_orb = atoi(qt) == 2 ? 2 : 1;
+    if (const char* z = getenv("ESFM_ORB_Z")) ctx->orb_z = atoi(z) == 2 ? 2 : (atoi(z) != 0);
     if (const char* eng = getenv("ESFM_HAMMING_ENGINE")) {
         if (!strcmp(eng, "tc") || !strcmp(eng, "tensor")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_TC;
         else if (!strcmp(eng, "popc")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_POPC;
@@ -594,8 +598,13 @@ int ensure_scratch(esfm_ctx* ctx, const esfm_bank* b, const ChunkPlan& pl) {
 
 // Tensor-core operand images of a bank (tc_layout.cuh: 3xTF32 hi/lo images for F32X64, FP8 +-1 images for B256), built the
 // first time a tensor-core engine sweeps it.
-int ensure_tc_layout(esfm_ctx* ctx, esfm_bank* b) {
-    if (b->d_tc) return ESFM_OK;
+int ensure_tc_layout(esfm_ctx* ctx, esfm_bank* b, int z_mode) {
+    if (b->d_tc && b->tc_z == z_mode) return ESFM_OK;
+    if (b->d_tc) {      // built for the other ORB encoding: rebuild (stream-ordered, earlier sweeps have been enqueued before)
+        cudaFreeAsync(b->d_tc, ctx->stream);
+        b->d_tc = nullptr;
+    }
+    b->tc_z = z_mode;
     const int n_tiles = b->tile_off[b->n_frames];
     b->tc_bytes = ((size_t)n_tiles + 1) * (b->kind == ESFM_KIND_F32X64 ? (size_t)kTcTileBytes : (size_t)kTc8TileBytes);
     cudaError_t e = cudaMallocAsync((void**)&b->d_tc, b->tc_bytes, ctx->stream);
@@ -607,7 +616,7 @@ int ensure_tc_layout(esfm_ctx* ctx, esfm_bank* b) {
     }
     e = b->kind == ESFM_KIND_F32X64
             ? launch_pack_tc((const float*)b->d_rows, b->d_frame_rows, b->d_row_off, b->d_tile_off, b->n_frames, n_tiles, b->d_tc, ctx->stream)
-            : launch_pack_tc8((const uint32_t*)b->d_rows, b->d_frame_rows, b->d_row_off, b->d_tile_off, b->n_frames, n_tiles, b->d_tc, ctx->stream);
+            : launch_pack_tc8((const uint32_t*)b->d_rows, b->d_frame_rows, b->d_row_off, b->d_tile_off, b->n_frames, n_tiles, b->d_tc, z_mode, ctx->stream);
     if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "tensor-core pack kernel launch failed: %s", cudaGetErrorString(e));
     if (n_tiles > 0) ctx->stats.kernel_launches += 1;
     return ESFM_OK;
@@ -631,11 +640,14 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     CUDA_TRY(cudaMemsetAsync(ctx->keys, 0xFF, n * 4 * (size_t)pl.stride * sizeof(u64), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_cursor, 0, 2 * sizeof(unsigned long long), ctx->stream));
     const bool tc = use_tc(ctx, b);
-    if (tc) if (int rc = ensure_tc_layout(ctx, b)) return rc;
+    // ORB "Z" encoding: the column index rides in the key, so every frame must have at most 2^15 rows; else the +-1 encoding
+    const int zmode = (tc && b->kind == ESFM_KIND_B256 && ctx->orb_z && b->max_rows <= kTcZMaxRows) ? ctx->orb_z : 0;
+    if (tc) if (int rc = ensure_tc_layout(ctx, b, zmode ? 1 : 0)) return rc;
     if (b->kind == ESFM_KIND_F32X64 || tc)  // column thresholds start at "no bound yet": 0x7f7f7f7f = 3.39e38f (FFMA engine),
                                       // 0x6f6f6f6f = 7.4e28f (TC engine: below its 1e30 pad-row norm)
         // (TC engine: 0x6f6f6f6f = 7.4e28f for SURF, 0x47474747 = 51015f for ORB -- above every real value, below the pad rows)
-        CUDA_TRY(cudaMemsetAsync(ctx->col_thr, tc ? (b->kind == ESFM_KIND_F32X64 ? 0x6F : 0x47) : 0x7F,
+        // (ORB "Z" encoding: 0x4b4b4b4b = 1.33e7f, above every key)
+        CUDA_TRY(cudaMemsetAsync(ctx->col_thr, tc ? (b->kind == ESFM_KIND_F32X64 ? 0x6F : (zmode ? 0x4B : 0x47)) : 0x7F,
                                  n * (size_t)pl.stride * sizeof(uint32_t), ctx->stream));
     SweepParams sp{};
     sp.kmajor = b->d_kmajor;
@@ -654,7 +666,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     sp.col_cap = pl.col_cap;
     if (const char* dbg = getenv("ESFM_TC_DEBUG")) sp.debug_flags = atoi(dbg);
     sp.tc_qtiles = b->kind == ESFM_KIND_B256 ? ctx->tc_qtiles_orb : ctx->tc_qtiles;
-    sp.tc_kind = b->kind;
+    sp.tc_kind = zmode == 2 ? kTcKindB256Z2 : (zmode ? kTcKindB256Z : b->kind);
     if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
     cudaError_t e = tc ? launch_sweep_l2_tc(sp, ctx->sm_count, ctx->stream)
                        : (b->kind == ESFM_KIND_F32X64 ? launch_sweep_l2(sp, ctx->sm_count, ctx->stream)
@@ -673,7 +685,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     fp.stride = pl.stride;
     fp.ratio = ratio;
     fp.cross_check = cross_check ? 1 : 0;
-    fp.b256_float_keys = (tc && b->kind == ESFM_KIND_B256) ? 1 : 0;
+    fp.b256_float_keys = (tc && b->kind == ESFM_KIND_B256) ? (zmode ? 2 : 1) : 0;
     fp.arena = ctx->arena;
     fp.arena_cap = ctx->arena_cap;
     fp.cursor = ctx->d_cursor;

@@ -32,6 +32,11 @@ constexpr uint32_t kFltMaxBits = 0x7f7fffffu;
 constexpr int kHamTile = 256;                        // train rows per smem stage (8 KB)
 constexpr int kHamStages = 4;
 constexpr int kHamRQ = 4;                            // query rows held in registers per thread
+constexpr int kTcKindB256Z = 2;                      // internal sweep kind: B256 with the "Z" operand encoding (tc_layout.cuh)
+constexpr int kTcKindB256Z2 = 3;                     // ... with the experimental epilogue variant ($ESFM_ORB_Z=2)
+constexpr int kTcZShift = 15;                        // Z key = kTcZ0i + (hamming << kTcZShift) + train row index inside its frame
+constexpr int kTcZMaxRows = 1 << kTcZShift;          // frames with more rows use the generic tensor-core epilogue
+constexpr int kTcZ0i = 21 * 448 * 448 - (1 << 22);   // 20480: what the 21 offset slots leave after cancelling -2^22
 constexpr int kHamIdxBits = 20;                      // packed 32-bit key = dist << 20 | index  (rows per frame < 2^20)
 
 struct PairDesc {
@@ -56,7 +61,8 @@ struct SweepParams {
     uint32_t* col_thr;          // [n_pairs][stride] running column thresholds (float bits), L2 sweeps only
     int stride;                 // keys per array (>= padded rows of the largest frame in the chunk)
     int col_cap;                // Hamming sweep: smem column-minimum capacity in entries
-    int tc_kind;                // TC sweep: ESFM_KIND_F32X64 (3xTF32 L2) or ESFM_KIND_B256 (FP8 Hamming); tc_main holds that kind's images
+    int tc_kind;                // TC sweep: ESFM_KIND_F32X64 (3xTF32 L2), ESFM_KIND_B256 (FP8 Hamming) or kTcKindB256Z (FP8 Hamming, packed
+                                // (distance, column) keys from the MMA); tc_main holds that kind's images
     int tc_qtiles;              // TC sweep geometry: query tiles per block, 1 or 2 ($ESFM_TC_QT, $ESFM_TC_QT_ORB)
     int debug_flags;            // TC sweep pipeline probes ($ESFM_TC_DEBUG; results are WRONG when set): 1 = epilogue only drains,
                                 // 2 = no MMAs issued, 4 = no train-tile loads
@@ -80,7 +86,8 @@ struct FinalizeParams {
     unsigned long long* pair_off;  // [n_pairs] offset of each pair's matches in the arena
     int32_t* pair_cnt;          // [n_pairs]
     int* overflow;              // set to 1 if the arena was too small
-    int b256_float_keys;        // B256 keys come from the tensor-core sweep: high word = float bits of 2 * hamming (else the integer)
+    int b256_float_keys;        // B256 keys from the tensor-core sweeps: 1 = high word is the float bits of 2 * hamming, 2 = of the packed key
+                                // z = kTcZ0 + 2^15 * hamming + column (tc_layout.cuh); 0 = the integer distance (XOR + POPC sweep)
     // optional raw knn output for one pair (esfm_knn2_pair)
     int32_t* knn_idx;
     float* knn_dist;
@@ -90,7 +97,7 @@ struct FinalizeParams {
 cudaError_t launch_pack_f32(const float* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
                             int n_frames, int n_tiles_total, float* kmajor, cudaStream_t s);
 cudaError_t launch_pack_tc8(const uint32_t* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
-                            int n_frames, int n_tiles_total, unsigned char* tc_main, cudaStream_t s);
+                            int n_frames, int n_tiles_total, unsigned char* tc_main, int z_mode, cudaStream_t s);
 cudaError_t launch_pack_tc(const float* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
                            int n_frames, int n_tiles_total, unsigned char* tc_main, cudaStream_t s);
 cudaError_t launch_sweep_l2(const SweepParams& p, int sm_count, cudaStream_t s);

@@ -34,6 +34,15 @@ __device__ __forceinline__ void order2(float& da, int& ia, float& db, int& ib) {
     }
 }
 
+// Hamming distance out of the high word of a sweep key: the integer itself (XOR + POPC sweep), the float 2 * hamming (tensor-core
+// sweep), or the packed float key z = kTcZ0i + 2^15 * hamming + column (tensor-core sweep, "Z" encoding)
+__device__ __forceinline__ float b256_key_distance(const FinalizeParams& p, u64 k) {
+    const uint32_t hi = (uint32_t)(k >> 32);
+    if (p.b256_float_keys == 2) return (float)(((int)__uint_as_float(hi) - kTcZ0i) >> kTcZShift);
+    if (p.b256_float_keys == 1) return 0.5f * __uint_as_float(hi);
+    return (float)hi;
+}
+
 template <int KIND>
 __device__ __forceinline__ RowResult eval_row(const FinalizeParams& p, const u64* rk1, const u64* rk2, const u64* ck1,
                                               const u64* ck2, const float* qrows, const float* trows, int q, int fq,
@@ -48,7 +57,7 @@ __device__ __forceinline__ RowResult eval_row(const FinalizeParams& p, const u64
     if (k1 != kKeyInit) {
         i1 = (int)(uint32_t)k1;
         if (KIND == ESFM_KIND_F32X64) d1 = l2_direct(qrows + (size_t)q * kDim, trows + (size_t)i1 * kDim);
-        else d1 = p.b256_float_keys ? 0.5f * __uint_as_float((uint32_t)(k1 >> 32)) : (float)(uint32_t)(k1 >> 32);
+        else d1 = b256_key_distance(p, k1);
     }
     if (k2 != kKeyInit) {
         i2 = (int)(uint32_t)k2;
@@ -56,7 +65,7 @@ __device__ __forceinline__ RowResult eval_row(const FinalizeParams& p, const u64
             d2 = l2_direct(qrows + (size_t)q * kDim, trows + (size_t)i2 * kDim);
             order2(d1, i1, d2, i2);
         } else {
-            d2 = p.b256_float_keys ? 0.5f * __uint_as_float((uint32_t)(k2 >> 32)) : (float)(uint32_t)(k2 >> 32);
+            d2 = b256_key_distance(p, k2);
         }
     }
     if (knn_idx) {

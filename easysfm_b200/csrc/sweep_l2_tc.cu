@@ -51,6 +51,8 @@ constexpr int kTcStages = 3;                 // shared-memory train stages (68 K
 //   QT = 2: 2 accumulator stages; every train tile feeds two accumulators (half the L2 -> shared-memory traffic and power).
 // KIND = ESFM_KIND_F32X64: 3xTF32, query operand = 128 columns (hi 64 | lo 64), train tile image 68 KB;
 // KIND = ESFM_KIND_B256:   Hamming as an FP8 +-1 dot product (tc_layout.cuh), query operand = 64 columns, image 36 KB.
+// KIND = kTcKindB256Z:     the same with scaled operands whose accumulator is the packed key z = Z0 + 2^15 hamming + column
+//                          (tc_layout.cuh "Z" encoding): branch-free row selection, QT = 1 only.
 template <int QT, int KIND> struct TcGeom {
     static constexpr int kACols = KIND == ESFM_KIND_F32X64 ? 128 : 64;
     static constexpr int kAccStages = (512 - QT * kACols) / 128;
@@ -62,8 +64,8 @@ template <int QT, int KIND> struct TcGeom {
 constexpr int kTcThrBytes = kTile * 4;                  // 512: column thresholds riding with a train tile
 constexpr int kTcThrStages = 4;                         // threshold snapshots have their own (deeper) ring
 // "no bound yet" (also what cudaMemsetAsync writes into the column thresholds, hence a repeated byte): above every real value,
-// below the pad rows.  SURF: 7.4e28 (pads: 1e30).  ORB: 51015 (real 2 * hamming <= 512, pads >= 200704).
-constexpr uint32_t kTcBoundBitsF32 = 0x6f6f6f6fu, kTcBoundBitsB256 = 0x47474747u;
+// below the pad rows.  SURF: 7.4e28 (pads: 1e30).  ORB: 51015 (real 2 * hamming <= 512, pads >= 200704).  ORB "Z": 1.33e7 (keys < 2^24).
+constexpr uint32_t kTcBoundBitsF32 = 0x6f6f6f6fu, kTcBoundBitsB256 = 0x47474747u, kTcBoundBitsZ = 0x4b4b4b4bu;
 
 struct TcUnit {
     int pair, q_frame, t_frame;
@@ -144,7 +146,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     constexpr int kTcTileBytes = G::kTileBytes;       // (shadows the SURF constant of tc_layout.cuh)
     constexpr int kTcMainBytes = G::kMainBytes;
     constexpr int kTcGroupBytes = G::kGroupBytes;
-    constexpr uint32_t kTcBoundBits = KIND == ESFM_KIND_F32X64 ? kTcBoundBitsF32 : kTcBoundBitsB256;
+    constexpr uint32_t kTcBoundBits = KIND == ESFM_KIND_F32X64 ? kTcBoundBitsF32 : ((KIND == kTcKindB256Z || KIND == kTcKindB256Z2) ? kTcBoundBitsZ : kTcBoundBitsB256);
+    constexpr bool kOrb = KIND != ESFM_KIND_F32X64;       // FP8 operands (both ORB encodings share the MMA sequence and the tile geometry)
+    constexpr bool kZ = KIND == kTcKindB256Z || KIND == kTcKindB256Z2;
+    constexpr bool kZ2 = KIND == kTcKindB256Z2;      // experimental: independent row chains, per-lane column atomics
+    static_assert(!kZ || kTcQTiles == 1, "the Z epilogue keeps one row state per thread");
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
         // descriptors live in uniform registers); one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
         // (Issuing from inside `if (lane == 0)` made the compiler wrap every MMA in an ELECT / R2UR.BROADCAST waterfall
         // loop: 16 dependent instructions and ~90 cycles per MMA, longer than the MMA itself.)
-        constexpr uint32_t idesc = KIND == ESFM_KIND_F32X64 ? tc_idesc_tf32(128, 128) : tc_idesc_e4m3(128, 128);
+        constexpr uint32_t idesc = kOrb ? tc_idesc_e4m3(128, 128) : tc_idesc_tf32(128, 128);
         const uint64_t qad0 = tc_desc_nosw(smem_u32(Qa), 128, kTcAugGroupBytes);
         const uint64_t td0 = tc_desc_sw128(smem_u32(Ts), kTcGroupBytes);
         const uint64_t tad0 = tc_desc_nosw(smem_u32(Ts) + kTcMainBytes, 128, kTcAugGroupBytes);
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                         tc_fence_after();
                         const uint32_t d = tmem + as * 128;
                         const uint32_t acol = tmem + kTcACol0 + h * kACols;
-                        if (KIND == ESFM_KIND_B256) {
+                        if (kOrb) {
                             if (!(p.debug_flags & 2) && elect_one()) {
                                 // 256 FP8 values per row = 8 k-steps of K = 32 (32 bytes: the same descriptor arithmetic as TF32's K = 8)
 #pragma unroll
@@ -301,8 +307,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const TcUnit u = tc_decode_unit(p, unit);
             const int fq = p.frame_rows[u.q_frame];
-            if (KIND == ESFM_KIND_B256) {
-                // ---- ORB: 256 bits -> 256 FP8 values +-1.0, 4 per tensor-memory column ----
+            if (kOrb) {
+                // ---- ORB: 256 bits -> 256 FP8 values +-1.0 (Z encoding: +-256), 4 per tensor-memory column ----
                 const uint4* qbits = p.rows_b256 + (size_t)p.frame_row_off[u.q_frame] * 2;
                 for (int qt = u.qb0; qt < u.qb1; ++qt) {
                     const int h = (qt - u.qb0) & (kTcQTiles - 1);
@@ -314,10 +320,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                     if (use > 0) named_bar_sync(2 + h, 128 + 32);      // slot h free (see the SURF branch below)
                     if (h == 0) ++quse[0]; else ++quse[1];
                     tc_fence_after();
-                    // augmented columns: (qpad ? 448 : 0, 448, 16, 0 ...) in FP8
+                    // augmented columns: (qpad ? 448 : 0, 448, 16, 0 ...) in FP8; Z encoding: the offset slots and digit multipliers
                     unsigned char* qa = Qa + h * kTcAugBytes + (trow >> 3) * kTcAugGroupBytes + (trow & 7) * 16;
-                    *reinterpret_cast<uint4*>(qa) = make_uint4((valid ? 0u : kFp8Pos448) | (kFp8Pos448 << 8) | (kFp8Pos16 << 16), 0u, 0u, 0u);
-                    *reinterpret_cast<uint4*>(qa + 128) = make_uint4(0u, 0u, 0u, 0u);
+                    if (kZ) {
+                        uint32_t aw[8];
+                        tcz_query_aug(aw);
+                        *reinterpret_cast<uint4*>(qa) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+                        *reinterpret_cast<uint4*>(qa + 128) = make_uint4(aw[4], aw[5], aw[6], aw[7]);
+                    } else {
+                        *reinterpret_cast<uint4*>(qa) = make_uint4((valid ? 0u : kFp8Pos448) | (kFp8Pos448 << 8) | (kFp8Pos16 << 16), 0u, 0u, 0u);
+                        *reinterpret_cast<uint4*>(qa + 128) = make_uint4(0u, 0u, 0u, 0u);
+                    }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     const uint32_t acol = tmem + lane_addr + kTcACol0 + h * kACols;
                     const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -325,7 +338,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                     for (int m = 0; m < 8; ++m) {       // word m = elements 32 m .. 32 m + 31 = 8 columns
                         uint32_t c[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) c[j] = valid ? tc8_expand4(ws[m] >> (4 * j)) : 0u;
+                        for (int j = 0; j < 8; ++j) c[j] = valid ? (kZ ? tcz_expand4_q(ws[m] >> (4 * j)) : tc8_expand4(ws[m] >> (4 * j))) : 0u;
                         tmem_st8(acol + m * 8, c);
                     }
                     tmem_st_wait();
@@ -412,6 +425,146 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
             uint32_t* tauc = p.col_thr + (size_t)u.pair * p.stride;
             for (int qt = u.qb0; qt < u.qb1; qt += kTcQTiles) {
                 const int nh = min(kTcQTiles, u.qb1 - qt);
+                if constexpr (kZ) {
+                // ================= ORB, "Z" encoding: the accumulator IS the packed key z = Z0 + 2^15 hamming + column =================
+                // Every element of a row is a distinct positive integer-valued float, smaller = nearer, ties = lower column, so the
+                // row's two nearest neighbours are the two smallest values this thread ever reads: three FMNMX per element, no
+                // bound, no slow path, no tie logic.  Columns keep the threshold scheme (their minimum runs over other warps' rows).
+                const int fq = p.frame_rows[u.q_frame], ft = p.frame_rows[u.t_frame];
+                const uint32_t qrow = (uint32_t)(qt * kTile + trow);
+                const bool qvalid = (int)qrow < fq;          // pad query rows read as z = Z0 + 2^22 + column: they must not win a column
+                // One CTA per pair (units_per_pair == 1): a threshold snapshot only ever holds minima of LOWER query rows (earlier
+                // query blocks; this block's own updates come after the snapshot was taken), so an equal distance can never win and
+                // the published threshold may exclude it (z - 1: same column, same distance => same z).  With the pair split over
+                // several CTAs other CTAs' (higher) rows are in the snapshot too and equal distances must still get through.
+                const float thr_sub = p.units_per_pair == 1 ? 1.f : 0.f;
+                float k1 = kTcZNone, k2 = kTcZNone;
+                for (int tt = 0; tt < u.ntt; ++tt, ++g, ++a) {
+                    const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
+                    mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);
+                    const float4* tp = reinterpret_cast<const float4*>(Thr + ts * kTcThrBytes) + part * (kTcPartCols / 4);
+                    const uint32_t as = a % kTcAccStages, aph = (a / kTcAccStages) & 1;
+                    mbar_wait_sleep<kTcSleepEpilogue>(&accFull[as], aph);
+                    if (warp == 0 && tt == u.ntt - 1) named_bar_arrive(2, 128 + 32);     // the query slot may be refilled (see the writers)
+                    tc_fence_after();
+                    uint32_t vb[32];
+                    tmem_ld32(tmem + lane_addr + as * 128 + part * kTcPartCols, vb);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&accEmpty[as]);
+                    if (!(p.debug_flags & 1)) {
+                        float v[32];
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(vb[c]);
+                        const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols);
+                        if (tt == u.ntt - 1) {       // only the last tile of a frame has pad rows (all-zero operands: z = 0)
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) v[c] = (int)(col0 + c) < ft ? v[c] : kTcZNone;
+                        }
+                        // ---- rows: running two smallest ----
+                        if constexpr (kZ2) {
+                            // four independent chains of 8 (instruction-level parallelism: one chain of 32 is 32 dependent FMNMX)
+                            float m1[4], m2[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                m1[i] = fminf(v[8 * i], v[8 * i + 1]);
+                                m2[i] = fmaxf(v[8 * i], v[8 * i + 1]);
+#pragma unroll
+                                for (int c = 2; c < 8; ++c) {
+                                    const float hi = fmaxf(m1[i], v[8 * i + c]);
+                                    m1[i] = fminf(m1[i], v[8 * i + c]);
+                                    m2[i] = fminf(m2[i], hi);
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {     // merge two sorted pairs: second smallest of four
+                                const float hi = fmaxf(k1, m1[i]);
+                                k1 = fminf(k1, m1[i]);
+                                k2 = fminf(fminf(k2, m2[i]), hi);
+                            }
+                        } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const float hi = fmaxf(k1, v[c]);
+                            k1 = fminf(k1, v[c]);
+                            k2 = fminf(k2, hi);
+                        }
+                        }
+                        // ---- columns: 4 chains of 8 threshold tests, one vote ----
+                        bool cf[4];
+#pragma unroll
+                        for (int cq = 0; cq < 4; ++cq) {
+                            const float4 x0 = tp[2 * cq], x1 = tp[2 * cq + 1];
+                            cf[cq] = qvalid & ((v[8 * cq] <= x0.x) | (v[8 * cq + 1] <= x0.y) | (v[8 * cq + 2] <= x0.z) | (v[8 * cq + 3] <= x0.w) |
+                                               (v[8 * cq + 4] <= x1.x) | (v[8 * cq + 5] <= x1.y) | (v[8 * cq + 6] <= x1.z) | (v[8 * cq + 7] <= x1.w));
+                        }
+                        if constexpr (kZ2) {
+                            // every lane publishes its own hits with fire-and-forget atomics: no vote, no REDUX, no event loop (two rows
+                            // beating the same column in one pass is rare, and the 64-bit minimum sorts them out anyway)
+#pragma unroll
+                            for (int cq = 0; cq < 4; ++cq) {
+                                if (cf[cq]) {
+                                    const float* thp = reinterpret_cast<const float*>(tp) + 8 * cq;
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float x = v[8 * cq + j];
+                                        if (x <= thp[j]) {
+                                            const uint32_t gcol = col0 + 8 * cq + j;
+                                            atomicMin(ck1 + gcol, make_key(__float_as_uint(x), qrow));
+                                            atomicMin(tauc + gcol, __float_as_uint(x - thr_sub));
+                                        }
+                                    }
+                                }
+                            }
+                        } else
+                        if (__any_sync(0xffffffffu, cf[0] | cf[1] | cf[2] | cf[3])) {
+#pragma unroll
+                            for (int cq = 0; cq < 4; ++cq) {
+                                if (__any_sync(0xffffffffu, cf[cq])) {
+                                    const float* thp = reinterpret_cast<const float*>(tp) + 8 * cq;
+                                    uint32_t pend = 0;
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j)
+                                        if (__any_sync(0xffffffffu, qvalid && v[8 * cq + j] <= thp[j])) pend |= 1u << j;
+#pragma unroll 1
+                                    while (pend) {
+                                        const int j = __ffs(pend) - 1;
+                                        pend &= pend - 1;
+                                        const bool s0 = j & 1, s1 = j & 2, s2 = j & 4;
+                                        const float a0 = s0 ? v[8 * cq + 1] : v[8 * cq], a1 = s0 ? v[8 * cq + 3] : v[8 * cq + 2];
+                                        const float a2 = s0 ? v[8 * cq + 5] : v[8 * cq + 4], a3 = s0 ? v[8 * cq + 7] : v[8 * cq + 6];
+                                        const float b0 = s1 ? a1 : a0, b1 = s1 ? a3 : a2;
+                                        const float x = s2 ? b1 : b0;
+                                        const bool hit = qvalid && x <= thp[j];
+                                        const uint32_t bits = hit ? __float_as_uint(x) : 0xffffffffu;
+                                        const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
+                                        const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
+                                        if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
+                                            const uint32_t gcol = col0 + 8 * cq + j;
+                                            atomicMin(ck1 + gcol, make_key(mn, qrow));
+                                            atomicMin(tauc + gcol, __float_as_uint(__uint_as_float(mn) - thr_sub));
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&thrEmpty[ts]);      // last read of this threshold snapshot
+                }
+                // merge the four column parts of the row: two smallest keys of (up to) eight; the column comes out of the key
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float z = e ? k2 : k1;
+                    if (z < 1.6e7f) {
+                        const uint32_t idx = (uint32_t)((int)z - kTcZ0i) & (uint32_t)(kTcZMaxRows - 1);
+                        const u64 k = make_key(__float_as_uint(z), idx);
+                        const u64 old = atomicMin(&mkey[trow], k);
+                        atomicMin(&mkey[kTile + trow], old > k ? old : k);
+                    }
+                }
+                } else {
                 // running top-2 of this thread's row in query tile 0 (t) and tile 1 (to); the two swap after every accumulator
                 RowTop2 t, to;
                 t.v1 = t.v2 = to.v1 = to.v2 = __uint_as_float(kTcBoundBits);
@@ -554,6 +707,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                         }
                     }
                 }
+                }   // (generic epilogue)
                 asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");
                 if (part < nh) {       // column part h publishes (and resets) query tile h
                     const uint32_t qrow = (uint32_t)((qt + part) * kTile + trow);
@@ -587,11 +741,13 @@ cudaError_t launch_sweep_l2_tc(const SweepParams& p, int sm_count, cudaStream_t 
     const int n_units = p.n_pairs * p.units_per_pair;
     if (n_units <= 0) return cudaSuccess;
     const int grid = n_units < sm_count ? n_units : sm_count;
-    const int qt = p.tc_qtiles == 2 ? 2 : 1;
-    const int kind = p.tc_kind == ESFM_KIND_B256 ? ESFM_KIND_B256 : ESFM_KIND_F32X64;
+    const int kind = (p.tc_kind == kTcKindB256Z || p.tc_kind == kTcKindB256Z2) ? p.tc_kind : (p.tc_kind == ESFM_KIND_B256 ? ESFM_KIND_B256 : ESFM_KIND_F32X64);
+    const int qt = (p.tc_qtiles == 2 && kind != kTcKindB256Z && kind != kTcKindB256Z2) ? 2 : 1;
     const size_t smem = sweep_tc_smem_bytes(qt, kind);
     void (*kern)(const SweepParams) =
-        kind == ESFM_KIND_B256 ? (qt == 2 ? sweep_l2_tc_kernel<2, ESFM_KIND_B256> : sweep_l2_tc_kernel<1, ESFM_KIND_B256>)
+        kind == kTcKindB256Z ? sweep_l2_tc_kernel<1, kTcKindB256Z>
+        : kind == kTcKindB256Z2 ? sweep_l2_tc_kernel<1, kTcKindB256Z2>
+        : kind == ESFM_KIND_B256 ? (qt == 2 ? sweep_l2_tc_kernel<2, ESFM_KIND_B256> : sweep_l2_tc_kernel<1, ESFM_KIND_B256>)
                                : (qt == 2 ? sweep_l2_tc_kernel<2, ESFM_KIND_F32X64> : sweep_l2_tc_kernel<1, ESFM_KIND_F32X64>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

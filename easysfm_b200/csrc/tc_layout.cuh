@@ -103,6 +103,49 @@ __host__ __device__ __forceinline__ uint32_t tc8_expand4(uint32_t n) {
 // byte offset of element (row rr in [0,8), k in [0,128)) inside one 1024-byte SWIZZLE_128B atom of bytes
 __host__ __device__ __forceinline__ int tc8_sw128_off(int rr, int k) { return rr * 128 + ((((k >> 4) ^ rr) & 7) << 4) + (k & 15); }
 
+// ---- ORB "Z" encoding: the MMA itself delivers a packed (distance, column) key ------------------------------------------
+// The fp32 accumulation of kind::f8f6f4 is exact for integers up to 2^23 (measured: csrc/microbench/f8_probe.cu,
+// profiles/f8_probe_r1.txt), so the operands can be scaled until the accumulator holds
+//     z = kTcZ0 + 2^15 * hamming + c,        c = the train row's index inside its frame (< 32768)
+// an exact positive integer, smaller = nearer, ties = lower column, and distinct for every column: a query row's two
+// nearest neighbours are then the two smallest of the floats it reads from tensor memory -- three FMNMX per element, no
+// bound, no slow path, no tie logic.
+//   main  q: bit 0 -> +256 (0x78), bit 1 -> -256 (0xF8);   t: bit 0 -> -64 (0xE8), bit 1 -> +64 (0x68)
+//         sum = 2^14 * (2 h - 256) = 2^15 h - 2^22
+//   aug   q' = (448 x 21, 1, 16, 256, 256, 0 x 7)      t' = (448 x 21, c & 15, (c >> 4) & 15, (c >> 8) & 15, 16 * (c >> 12), 0 x 7)
+//         sum = 21 * 448^2 + c = 2^22 + 20480 + c
+// Pad rows are all-zero operands (z = 0): the epilogue masks them by index (only the last tile of a frame has any).
+// (kTcZShift = 15, kTcZMaxRows, kTcZ0i = 20480: esfm_internal.cuh -- finalize.cu decodes the keys)
+constexpr float kTcZNone = 3.0e38f;                          // "no candidate" / masked
+// 4 descriptor bits (low nibble of n) -> 4 FP8 bytes: query role +-256, train role -+64
+__host__ __device__ __forceinline__ uint32_t tcz_expand4_q(uint32_t n) {
+    return ((((n & 0xfu) * 0x00204081u) & 0x01010101u) << 7) | 0x78787878u;
+}
+__host__ __device__ __forceinline__ uint32_t tcz_expand4_t(uint32_t n) {
+    return ((((n & 0xfu) * 0x00204081u) & 0x01010101u) << 7) ^ 0xe8e8e8e8u;
+}
+// E4M3 code of the integer v in [0, 15] (exact: at most 4 significant bits)
+__host__ __device__ __forceinline__ uint32_t tcz_fp8_digit(uint32_t v) {
+    if (v == 0) return 0u;
+    const uint32_t e = v >= 8 ? 3u : (v >= 4 ? 2u : (v >= 2 ? 1u : 0u));
+    return ((e + 7u) << 3) | (((v - (1u << e)) << 3) >> e);
+}
+// the 32 augmented bytes of a train row with frame index c, as 8 little-endian words
+__host__ __device__ __forceinline__ void tcz_train_aug(uint32_t c, uint32_t (&w)[8]) {
+    const uint32_t d3 = tcz_fp8_digit((c >> 12) & 7u);
+    w[0] = w[1] = w[2] = w[3] = w[4] = 0x7e7e7e7eu;                       // slots 0..19
+    w[5] = 0x7eu | (tcz_fp8_digit(c & 15u) << 8) | (tcz_fp8_digit((c >> 4) & 15u) << 16) | (tcz_fp8_digit((c >> 8) & 15u) << 24);   // 20..23
+    w[6] = d3 ? d3 + (4u << 3) : 0u;                                      // slot 24: 16 * digit = exponent + 4
+    w[7] = 0u;
+}
+// ... and of every query row: the multipliers
+__host__ __device__ __forceinline__ void tcz_query_aug(uint32_t (&w)[8]) {
+    w[0] = w[1] = w[2] = w[3] = w[4] = 0x7e7e7e7eu;
+    w[5] = 0x7eu | (0x38u << 8) | (0x58u << 16) | (0x78u << 24);          // 448, 1, 16, 256
+    w[6] = 0x78u;                                                         // 256
+    w[7] = 0u;
+}
+
 #ifdef __CUDACC__
 // ---- shared-memory matrix descriptors (tcgen05.mma operand A / B), K-major ---------------------------------------
 // bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
