@@ -182,8 +182,8 @@ def workload_config(kind, pairs_per_step, e2e_frames):
 
 def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budget_s, engine=None, e2e_arm=True):
     """Returns the result dict for one descriptor kind (device-resident value, e2e, roofline, cpu baseline).
-    `engine` selects the sweep kernel: SURF 'tc' (tcgen05 3xTF32) | 'ffma' (exact-FP32 FMA pipe); ORB 'tc' (tcgen05 FP8 +-1 dot
-    product) | 'popc' (XOR + POPC); None = library default."""
+    `engine` selects the sweep kernel: SURF 'tc' (tcgen05 3xTF32) | 'ffma' (exact-FP32 FMA pipe); ORB 'tc' (tcgen05 FP8 dot
+    product delivering packed keys) | 'popc' (XOR + POPC); None = library default."""
     import torch
     from easysfm_b200 import scheduler
     import easysfm_b200 as esfm
@@ -356,7 +356,7 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
         unit_ops, unit = 8.0, "TPOPC/s"                        # algorithmic: 8 x 32-bit POPC per comparison (north_star)
         peak = sms * POPC_LANES * sm_max * 1e6 / 1e12          # ... against the pipe the XOR+POPC design is bound by
         bound = "tensor"
-        kern = "sweep_l2_tc_kernel<1, B256>"
+        kern = "sweep_l2_tc_kernel<1, kTcKindB256Z>"
     else:
         unit_ops, unit = 8.0, "TPOPC/s"                        # 8 x 32-bit POPC per comparison (algorithmic, north_star)
         peak = sms * POPC_LANES * sm_max * 1e6 / 1e12
@@ -371,7 +371,8 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
                 "kernel_ms": sweep_ms, "comparisons_per_launch": comps_per_launch,
                 "hbm_gbs_algorithmic": None, "traffic": None}
     if bound == "tensor" and kind == "orb":
-        # ORB on the tensor cores: Hamming = (256 - dot) / 2 of FP8 +-1 vectors, exact.  `achieved`/`frac` stay in the north
+        # ORB on the tensor cores: scaled FP8 operands whose exact fp32 dot product is the packed key 20480 + 2^15 hamming + column
+        # ($ESFM_ORB_Z=0: plain +-1 vectors, Hamming = (256 - dot) / 2).  `achieved`/`frac` stay in the north
         # star's algorithmic unit (8 POPC per comparison against the POPC-pipe peak: > 1 means faster than any XOR+POPC kernel
         # can be); `executed_tflops` / `frac_executed` are the FP8 tensor FLOPs actually issued over the dense FP8 peak
         # (= 2 x the measured dense bf16 rate).  The kernel is bound by its selection epilogue, not by the tensor pipe.
@@ -379,8 +380,9 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
         roofline["executed_tflops"] = (comps_per_launch / (sweep_ms * 1e-3)) * TC8_FLOP_PER_CMP / 1e12
         roofline["frac_executed"] = roofline["executed_tflops"] / fp8_peak
         roofline["tensor_peak_tflops"] = fp8_peak
-        roofline["note"] = ("Hamming as an exact FP8 (+-1) dot product on tcgen05 (kind::f8f6f4): 576 tensor FLOP per comparison; "
-                            "frac is the algorithmic 8-POPC rate over the POPC-pipe peak")
+        roofline["note"] = ("Hamming as an exact FP8 dot product on tcgen05 (kind::f8f6f4) that yields packed (distance, column) keys: "
+                            "576 tensor FLOP per comparison; frac is the algorithmic 8-POPC rate over the POPC-pipe peak; the kernel is bound by "
+                            "its selection epilogue and by the 64 B/clk tensor-memory read-out (4.65e12 comparisons/s), not by the tensor pipe")
     if bound == "tensor" and kind == "surf":
         # `achieved`/`frac` use the ALGORITHMIC 128 FLOP per comparison.  The tensor cores execute 3.125x that
         # (3xTF32 split over 64 dims + 8 augmented columns); `frac_executed` is that executed rate over the same peak (= tensor-pipe utilisation),

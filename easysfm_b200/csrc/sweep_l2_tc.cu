@@ -7,20 +7,24 @@
 // candidates in direct form, so what this kernel must get right is the RANKING; its arithmetic is the 3xTF32 split
 // product of tc_layout.cuh (|error| ~ 2e-6 on 1/2 d^2, measured by csrc/microbench/tc_probe.cu).
 //
-// One persistent CTA per SM, 22 warps, four pipelines (TMA -> shared memory -> tensor memory -> registers).  A CTA works
-// on a QUERY BLOCK of two 128-row tiles at a time and streams the train frame past it once: every 68 KB train tile feeds
-// two 128 x 128 accumulators, so the L2 -> shared-memory traffic per comparison is half of a one-tile block (at one tile
-// per block the 148 SMs asked L2 for 6300 B/clk, exactly the measured L2 slice throughput cap).
-//   warp 16 (one lane)  TMA producer: one cp.async.bulk per 128-row train tile image (main 64 KB + augmented 4 KB) into a
-//                       3-stage full/empty mbarrier ring; the 128 running column thresholds of the tile ride in their own ring.
-//   warp 17             MMA issuer: per (train tile, query tile) 25 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8):
-//                       3 terms (lo.hi, hi.lo, hi.hi) x 8 k-steps with the query operand read from TENSOR MEMORY and the train
-//                       operand from SWIZZLE_128B shared-memory atoms, + 1 augmented k-step that adds both half norms exactly;
-//                       -1/2 d^2 accumulates in one of 2 tensor-memory stages (128 columns each);
-//                       tcgen05.commit publishes the accumulator stage and releases the shared-memory stage / query tile.
-//   warps 18-21         query writers: fp32 rows -> (hi, lo) TF32 operand of query tile h in tensor-memory columns
-//                       256 + 128 h .. (tcgen05.st) + its augmented block in shared memory; tile h of the NEXT block is
-//                       written while the MMAs of the other tile still run.
+// The same kernel template serves ORB / Hamming (cpp_code/src/feature_matching.cpp:71-92) as an exact FP8 dot product:
+// KIND = ESFM_KIND_B256 (+-1 operands, accumulator = -2 hamming, generic epilogue) and KIND = kTcKindB256Z (scaled operands
+// whose accumulator is the packed key 20480 + 2^15 hamming + column: branch-free row selection; the default).
+//
+// One persistent CTA per SM, 24 warps, four pipelines (TMA -> shared memory -> tensor memory -> registers).  A CTA works
+// on a QUERY BLOCK of QT (template parameter, 1 or 2) 128-row tiles at a time and streams the train frame past it once.
+//   warp 16 (one lane)  TMA producer: one cp.async.bulk per 128-row train tile image (SURF 68 KB, ORB 36 KB: main + augmented
+//                       columns) into a 3-stage full/empty mbarrier ring; the 128 running column thresholds of the tile ride
+//                       in their own 4-stage ring.
+//   warp 17             MMA issuer (warp-uniform control flow, one elected lane issues): per (train tile, query tile)
+//                       SURF: 25 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) = 3 terms (lo.hi, hi.lo, hi.hi) x 8
+//                       k-steps + 1 augmented k-step that adds both half norms exactly; ORB: 8 + 1 x kind::f8f6f4 (K=32).
+//                       The query operand is read from TENSOR MEMORY, the train operand from SWIZZLE_128B shared-memory atoms;
+//                       the result accumulates in one of the tensor-memory stages (128 columns each: 3 stages at QT = 1);
+//                       tcgen05.commit publishes the accumulator stage and releases the shared-memory stage.
+//   warps 20-23         query writers: rows of query tile h -> operand columns of tensor memory (tcgen05.st; SURF: fp32 ->
+//                       (hi, lo) TF32, ORB: bits -> FP8) + the tile's augmented block in shared memory; they block on a
+//                       named barrier until the epilogue has seen the last accumulator that read the slot.
 //   warps 0-15          epilogue: warp w owns TMEM lanes 32*(w%4).. (= query rows) and column quarter w/4.  tcgen05.ld
 //                       gives each THREAD one query row x 32 train columns, so the row's running top-2 is thread-private
 //                       (no shuffles); column minima go through a warp REDUX + one fire-and-forget atomicMin per hit.

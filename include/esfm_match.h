@@ -114,9 +114,9 @@ int esfm_device_sm_count(esfm_ctx_t* ctx, int* sms);
 int esfm_set_l2_engine(esfm_ctx_t* ctx, int engine);
 int esfm_get_l2_engine(esfm_ctx_t* ctx, int* engine);
 /* Which kernel serves ESFM_KIND_B256: XOR + POPC on the integer pipes (the north-star design), or the same Hamming
- * distance as an exact FP8 (+-1) dot product on the tcgen05 tensor cores (256 - 2 * hamming accumulates as a small integer
- * in fp32; 1.8x faster).  Both are bit-exact against OpenCV and against each other; default: $ESFM_HAMMING_ENGINE
- * ("popc" | "tc") at esfm_init, else ESFM_HAMMING_ENGINE_TC. */
+ * distance as an exact FP8 dot product on the tcgen05 tensor cores (bits become +-2^k, the fp32 accumulator holds the
+ * integer 20480 + 2^15 * hamming + column exactly; 2.3x faster).  Both are bit-exact against OpenCV and against each other;
+ * default: $ESFM_HAMMING_ENGINE ("popc" | "tc") at esfm_init, else ESFM_HAMMING_ENGINE_TC. */
 #define ESFM_HAMMING_ENGINE_POPC 0
 #define ESFM_HAMMING_ENGINE_TC 1
 int esfm_set_hamming_engine(esfm_ctx_t* ctx, int engine);
