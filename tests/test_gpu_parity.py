@@ -238,3 +238,27 @@ def test_hamming_engines_are_byte_identical(ctx):
     finally:
         ctx.set_hamming_engine(keep)
     assert out["popc"] == out["tc"]
+    # the +-1 operand encoding with the generic epilogue ($ESFM_ORB_Z=0, read at esfm_init): what frames with more than 32768
+    # rows fall back to (the default Z encoding packs the column index into 15 bits of the accumulator)
+    import os
+    import easysfm_b200 as esfm
+    old = os.environ.get("ESFM_ORB_Z")
+    os.environ["ESFM_ORB_Z"] = "0"
+    try:
+        with esfm.Context(0) as c2:
+            c2.set_hamming_engine("tc")
+            bank = c2.bank_from_frames(frames)
+            per = []
+            for ratio, cc in ((0.8, True), (0.8, False), (float("inf"), True)):
+                res = bank.match_all_pairs(ratio, cc)
+                per += [res.pair_at(k)[2].tobytes() for k in range(res.n_pairs)]
+            for (i, j) in ((4, 6), (6, 4), (0, 7), (3, 2), (0, 5), (2, 0)):
+                idx, dist = bank.knn2_pair(i, j)
+                per += [idx.tobytes(), dist.tobytes()]
+            bank.close()
+    finally:
+        if old is None:
+            os.environ.pop("ESFM_ORB_Z", None)
+        else:
+            os.environ["ESFM_ORB_Z"] = old
+    assert per == out["popc"]
