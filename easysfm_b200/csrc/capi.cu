@@ -51,7 +51,7 @@ struct esfm_ctx {
     int tc_qtiles = 1;                     // TC sweep geometry, SURF: query tiles per block (1 or 2; $ESFM_TC_QT)
     int tc_qtiles_orb = 1;                 // TC sweep geometry, ORB (1 or 2; $ESFM_TC_QT_ORB): 3 accumulator stages either way
     int orb_z = 1;                         // ORB tensor-core sweep with the "Z" operand encoding (packed keys from the MMA): default;
-                                           // $ESFM_ORB_Z=0 selects the +-1 encoding with the generic epilogue, 2 the experimental epilogue
+                                           // $ESFM_ORB_Z=0 selects the +-1 encoding with the generic epilogue
     int hamming_engine = ESFM_HAMMING_ENGINE_TC;     // which sweep kernel serves ESFM_KIND_B256 (esfm_set_hamming_engine / $ESFM_HAMMING_ENGINE)
     int l2_engine = ESFM_L2_ENGINE_TC;     // which sweep kernel serves ESFM_KIND_F32X64 (esfm_set_l2_engine / $ESFM_L2_ENGINE)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -203,7 +203,7 @@ extern "C" int esfm_init(int device, void* cuda_stream, esfm_ctx_t** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* qt = getenv("ESFM_TC_QT")) ctx->tc_qtiles = atoi(qt) == 2 ? 2 : 1;
     if (const char* qt = getenv("ESFM_TC_QT_ORB")) ctx->tc_qtiles_orb = atoi(qt) == 2 ? 2 : 1;
-    if (const char* z = getenv("ESFM_ORB_Z")) ctx->orb_z = atoi(z) == 2 ? 2 : (atoi(z) != 0);
+    if (const char* z = getenv("ESFM_ORB_Z")) ctx->orb_z = atoi(z) != 0;
     if (const char* eng = getenv("ESFM_HAMMING_ENGINE")) {
         if (!strcmp(eng, "tc") || !strcmp(eng, "tensor")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_TC;
         else if (!strcmp(eng, "popc")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_POPC;
@@ -641,8 +641,8 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     CUDA_TRY(cudaMemsetAsync(ctx->d_cursor, 0, 2 * sizeof(unsigned long long), ctx->stream));
     const bool tc = use_tc(ctx, b);
     // ORB "Z" encoding: the column index rides in the key, so every frame must have at most 2^15 rows; else the +-1 encoding
-    const int zmode = (tc && b->kind == ESFM_KIND_B256 && ctx->orb_z && b->max_rows <= kTcZMaxRows) ? ctx->orb_z : 0;
-    if (tc) if (int rc = ensure_tc_layout(ctx, b, zmode ? 1 : 0)) return rc;
+    const int zmode = (tc && b->kind == ESFM_KIND_B256 && ctx->orb_z && b->max_rows <= kTcZMaxRows) ? 1 : 0;
+    if (tc) if (int rc = ensure_tc_layout(ctx, b, zmode)) return rc;
     if (b->kind == ESFM_KIND_F32X64 || tc)  // column thresholds start at "no bound yet": 0x7f7f7f7f = 3.39e38f (FFMA engine),
                                       // 0x6f6f6f6f = 7.4e28f (TC engine: below its 1e30 pad-row norm)
         // (TC engine: 0x6f6f6f6f = 7.4e28f for SURF, 0x47474747 = 51015f for ORB -- above every real value, below the pad rows)
@@ -666,7 +666,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     sp.col_cap = pl.col_cap;
     if (const char* dbg = getenv("ESFM_TC_DEBUG")) sp.debug_flags = atoi(dbg);
     sp.tc_qtiles = b->kind == ESFM_KIND_B256 ? ctx->tc_qtiles_orb : ctx->tc_qtiles;
-    sp.tc_kind = zmode == 2 ? kTcKindB256Z2 : (zmode ? kTcKindB256Z : b->kind);
+    sp.tc_kind = zmode ? kTcKindB256Z : b->kind;
     if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
     cudaError_t e = tc ? launch_sweep_l2_tc(sp, ctx->sm_count, ctx->stream)
                        : (b->kind == ESFM_KIND_F32X64 ? launch_sweep_l2(sp, ctx->sm_count, ctx->stream)

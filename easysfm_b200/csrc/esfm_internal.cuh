@@ -33,7 +33,6 @@ constexpr int kHamTile = 256;                        // train rows per smem stag
 constexpr int kHamStages = 4;
 constexpr int kHamRQ = 4;                            // query rows held in registers per thread
 constexpr int kTcKindB256Z = 2;                      // internal sweep kind: B256 with the "Z" operand encoding (tc_layout.cuh)
-constexpr int kTcKindB256Z2 = 3;                     // ... with the experimental epilogue variant ($ESFM_ORB_Z=2)
 constexpr int kTcZShift = 15;                        // Z key = kTcZ0i + (hamming << kTcZShift) + train row index inside its frame
 constexpr int kTcZMaxRows = 1 << kTcZShift;          // frames with more rows use the generic tensor-core epilogue
 constexpr int kTcZ0i = 21 * 448 * 448 - (1 << 22);   // 20480: what the 21 offset slots leave after cancelling -2^22

@@ -150,10 +150,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     constexpr int kTcTileBytes = G::kTileBytes;       // (shadows the SURF constant of tc_layout.cuh)
     constexpr int kTcMainBytes = G::kMainBytes;
     constexpr int kTcGroupBytes = G::kGroupBytes;
-    constexpr uint32_t kTcBoundBits = KIND == ESFM_KIND_F32X64 ? kTcBoundBitsF32 : ((KIND == kTcKindB256Z || KIND == kTcKindB256Z2) ? kTcBoundBitsZ : kTcBoundBitsB256);
+    constexpr uint32_t kTcBoundBits = KIND == ESFM_KIND_F32X64 ? kTcBoundBitsF32 : (KIND == kTcKindB256Z ? kTcBoundBitsZ : kTcBoundBitsB256);
     constexpr bool kOrb = KIND != ESFM_KIND_F32X64;       // FP8 operands (both ORB encodings share the MMA sequence and the tile geometry)
-    constexpr bool kZ = KIND == kTcKindB256Z || KIND == kTcKindB256Z2;
-    constexpr bool kZ2 = KIND == kTcKindB256Z2;      // experimental: independent row chains, per-lane column atomics
+    constexpr bool kZ = KIND == kTcKindB256Z;
     static_assert(!kZ || kTcQTiles == 1, "the Z epilogue keeps one row state per thread");
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment
@@ -467,33 +466,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                             for (int c = 0; c < 32; ++c) v[c] = (int)(col0 + c) < ft ? v[c] : kTcZNone;
                         }
                         // ---- rows: running two smallest ----
-                        if constexpr (kZ2) {
-                            // four independent chains of 8 (instruction-level parallelism: one chain of 32 is 32 dependent FMNMX)
-                            float m1[4], m2[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                m1[i] = fminf(v[8 * i], v[8 * i + 1]);
-                                m2[i] = fmaxf(v[8 * i], v[8 * i + 1]);
-#pragma unroll
-                                for (int c = 2; c < 8; ++c) {
-                                    const float hi = fmaxf(m1[i], v[8 * i + c]);
-                                    m1[i] = fminf(m1[i], v[8 * i + c]);
-                                    m2[i] = fminf(m2[i], hi);
-                                }
-                            }
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {     // merge two sorted pairs: second smallest of four
-                                const float hi = fmaxf(k1, m1[i]);
-                                k1 = fminf(k1, m1[i]);
-                                k2 = fminf(fminf(k2, m2[i]), hi);
-                            }
-                        } else {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
                             const float hi = fmaxf(k1, v[c]);
                             k1 = fminf(k1, v[c]);
                             k2 = fminf(k2, hi);
-                        }
                         }
                         // ---- columns: 4 chains of 8 threshold tests, one vote ----
                         bool cf[4];
@@ -503,25 +480,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                             cf[cq] = qvalid & ((v[8 * cq] <= x0.x) | (v[8 * cq + 1] <= x0.y) | (v[8 * cq + 2] <= x0.z) | (v[8 * cq + 3] <= x0.w) |
                                                (v[8 * cq + 4] <= x1.x) | (v[8 * cq + 5] <= x1.y) | (v[8 * cq + 6] <= x1.z) | (v[8 * cq + 7] <= x1.w));
                         }
-                        if constexpr (kZ2) {
-                            // every lane publishes its own hits with fire-and-forget atomics: no vote, no REDUX, no event loop (two rows
-                            // beating the same column in one pass is rare, and the 64-bit minimum sorts them out anyway)
-#pragma unroll
-                            for (int cq = 0; cq < 4; ++cq) {
-                                if (cf[cq]) {
-                                    const float* thp = reinterpret_cast<const float*>(tp) + 8 * cq;
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) {
-                                        const float x = v[8 * cq + j];
-                                        if (x <= thp[j]) {
-                                            const uint32_t gcol = col0 + 8 * cq + j;
-                                            atomicMin(ck1 + gcol, make_key(__float_as_uint(x), qrow));
-                                            atomicMin(tauc + gcol, __float_as_uint(x - thr_sub));
-                                        }
-                                    }
-                                }
-                            }
-                        } else
                         if (__any_sync(0xffffffffu, cf[0] | cf[1] | cf[2] | cf[3])) {
 #pragma unroll
                             for (int cq = 0; cq < 4; ++cq) {
@@ -745,12 +703,11 @@ cudaError_t launch_sweep_l2_tc(const SweepParams& p, int sm_count, cudaStream_t 
     const int n_units = p.n_pairs * p.units_per_pair;
     if (n_units <= 0) return cudaSuccess;
     const int grid = n_units < sm_count ? n_units : sm_count;
-    const int kind = (p.tc_kind == kTcKindB256Z || p.tc_kind == kTcKindB256Z2) ? p.tc_kind : (p.tc_kind == ESFM_KIND_B256 ? ESFM_KIND_B256 : ESFM_KIND_F32X64);
-    const int qt = (p.tc_qtiles == 2 && kind != kTcKindB256Z && kind != kTcKindB256Z2) ? 2 : 1;
+    const int kind = p.tc_kind == kTcKindB256Z ? kTcKindB256Z : (p.tc_kind == ESFM_KIND_B256 ? ESFM_KIND_B256 : ESFM_KIND_F32X64);
+    const int qt = (p.tc_qtiles == 2 && kind != kTcKindB256Z) ? 2 : 1;
     const size_t smem = sweep_tc_smem_bytes(qt, kind);
     void (*kern)(const SweepParams) =
         kind == kTcKindB256Z ? sweep_l2_tc_kernel<1, kTcKindB256Z>
-        : kind == kTcKindB256Z2 ? sweep_l2_tc_kernel<1, kTcKindB256Z2>
         : kind == ESFM_KIND_B256 ? (qt == 2 ? sweep_l2_tc_kernel<2, ESFM_KIND_B256> : sweep_l2_tc_kernel<1, ESFM_KIND_B256>)
                                : (qt == 2 ? sweep_l2_tc_kernel<2, ESFM_KIND_F32X64> : sweep_l2_tc_kernel<1, ESFM_KIND_F32X64>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

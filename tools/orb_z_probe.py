@@ -74,7 +74,7 @@ ref_bank = timing_bank(ref_ctx)
 ref_all = all_pairs_bytes(ref_bank)
 rate(ref_ctx, ref_bank, "popc      ")
 ref_bank.close()
-for z in [int(x) for x in os.environ.get("ORB_Z_PROBE_MODES", "0,1,2").split(",")]:
+for z in [int(x) for x in os.environ.get("ORB_Z_PROBE_MODES", "0,1").split(",")]:
     os.environ["ESFM_ORB_Z"] = str(z)
     ctx = esfm.Context(0)
     ctx.set_hamming_engine("tc")
