@@ -50,6 +50,7 @@ struct esfm_ctx {
     bool profiling = true;
     int tc_qtiles = 1;                     // TC sweep geometry, SURF: query tiles per block (1 or 2; $ESFM_TC_QT)
     int tc_qtiles_orb = 1;                 // TC sweep geometry, ORB (1 or 2; $ESFM_TC_QT_ORB): 3 accumulator stages either way
+    int surf_bf = 0;                       // SURF tensor-core sweep with the branch-free row selection (EXPERIMENTAL, $ESFM_TC_SURF_BF=1)
     int orb_z = 1;                         // ORB tensor-core sweep with the "Z" operand encoding (packed keys from the MMA): default;
                                            // $ESFM_ORB_Z=0 selects the +-1 encoding with the generic epilogue
     int hamming_engine = ESFM_HAMMING_ENGINE_TC;     // which sweep kernel serves ESFM_KIND_B256 (esfm_set_hamming_engine / $ESFM_HAMMING_ENGINE)
@@ -204,6 +205,7 @@ extern "C" int esfm_init(int device, void* cuda_stream, esfm_ctx_t** out) {
     if (const char* qt = getenv("ESFM_TC_QT")) ctx->tc_qtiles = atoi(qt) == 2 ? 2 : 1;
     if (const char* qt = getenv("ESFM_TC_QT_ORB")) ctx->tc_qtiles_orb = atoi(qt) == 2 ? 2 : 1;
     if (const char* z = getenv("ESFM_ORB_Z")) ctx->orb_z = atoi(z) != 0;
+    if (const char* bf = getenv("ESFM_TC_SURF_BF")) ctx->surf_bf = atoi(bf) != 0;
     if (const char* eng = getenv("ESFM_HAMMING_ENGINE")) {
         if (!strcmp(eng, "tc") || !strcmp(eng, "tensor")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_TC;
         else if (!strcmp(eng, "popc")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_POPC;
@@ -666,7 +668,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, size_t n, double
     sp.col_cap = pl.col_cap;
     if (const char* dbg = getenv("ESFM_TC_DEBUG")) sp.debug_flags = atoi(dbg);
     sp.tc_qtiles = b->kind == ESFM_KIND_B256 ? ctx->tc_qtiles_orb : ctx->tc_qtiles;
-    sp.tc_kind = zmode ? kTcKindB256Z : b->kind;
+    sp.tc_kind = zmode ? kTcKindB256Z : ((tc && b->kind == ESFM_KIND_F32X64 && ctx->surf_bf && ctx->tc_qtiles == 1) ? kTcKindF32BF : b->kind);
     if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
     cudaError_t e = tc ? launch_sweep_l2_tc(sp, ctx->sm_count, ctx->stream)
                        : (b->kind == ESFM_KIND_F32X64 ? launch_sweep_l2(sp, ctx->sm_count, ctx->stream)

@@ -11,3 +11,4 @@ timeout 240 ncu --set full --clock-control none --import-source on -k regex:^swe
 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k 'regex:^(sweep_|finalize|pack_)' -c 120 --csv \
     --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --cpu-budget-s 0 --no-alt-engine > gpurun_out/bench_under_ncu.log 2>&1
 tail -2 gpurun_out/launches.csv | cut -c1-200
+timeout 200 python tools/surf_bf_probe.py > gpurun_out/surf_bf_probe.txt 2>&1; cat gpurun_out/surf_bf_probe.txt
