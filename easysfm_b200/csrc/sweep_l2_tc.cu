@@ -438,287 +438,287 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
             for (int qt = u.qb0; qt < u.qb1; qt += kTcQTiles) {
                 const int nh = min(kTcQTiles, u.qb1 - qt);
                 if constexpr (kZ) {
-                // ================= ORB, "Z" encoding: the accumulator IS the packed key z = Z0 + 2^15 hamming + column =================
-                // Every element of a row is a distinct positive integer-valued float, smaller = nearer, ties = lower column, so the
-                // row's two nearest neighbours are the two smallest values this thread ever reads: three FMNMX per element, no
-                // bound, no slow path, no tie logic.  Columns keep the threshold scheme (their minimum runs over other warps' rows).
-                const int fq = p.frame_rows[u.q_frame], ft = p.frame_rows[u.t_frame];
-                const uint32_t qrow = (uint32_t)(qt * kTile + trow);
-                const bool qvalid = (int)qrow < fq;          // pad query rows read as z = Z0 + 2^22 + column: they must not win a column
-                // One CTA per pair (units_per_pair == 1): a threshold snapshot only ever holds minima of LOWER query rows (earlier
-                // query blocks; this block's own updates come after the snapshot was taken), so an equal distance can never win and
-                // the published threshold may exclude it (z - 1: same column, same distance => same z).  With the pair split over
-                // several CTAs other CTAs' (higher) rows are in the snapshot too and equal distances must still get through.
-                const float thr_sub = p.units_per_pair == 1 ? 1.f : 0.f;
-                float k1 = kTcZNone, k2 = kTcZNone;
-                for (int tt = 0; tt < u.ntt; ++tt, ++g, ++a) {
-                    const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
-                    mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);
-                    const float4* tp = reinterpret_cast<const float4*>(Thr + ts * kTcThrBytes) + part * (kTcPartCols / 4);
-                    const uint32_t as = a % kTcAccStages, aph = (a / kTcAccStages) & 1;
-                    mbar_wait_sleep<kTcSleepEpilogue>(&accFull[as], aph);
-                    if (warp == 0 && tt == u.ntt - 1) named_bar_arrive(2, 128 + 32);     // the query slot may be refilled (see the writers)
-                    tc_fence_after();
-                    uint32_t vb[32];
-                    tmem_ld32(tmem + lane_addr + as * 128 + part * kTcPartCols, vb);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&accEmpty[as]);
-                    if (!(p.debug_flags & 1)) {
-                        float v[32];
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(vb[c]);
-                        const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols);
-                        if (tt == u.ntt - 1) {       // only the last tile of a frame has pad rows (all-zero operands: z = 0)
-#pragma unroll
-                            for (int c = 0; c < 32; ++c) v[c] = (int)(col0 + c) < ft ? v[c] : kTcZNone;
-                        }
-                        // ---- rows: running two smallest ----
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const float hi = fmaxf(k1, v[c]);
-                            k1 = fminf(k1, v[c]);
-                            k2 = fminf(k2, hi);
-                        }
-                        // ---- columns: 4 chains of 8 threshold tests, one vote ----
-                        bool cf[4];
-#pragma unroll
-                        for (int cq = 0; cq < 4; ++cq) {
-                            const float4 x0 = tp[2 * cq], x1 = tp[2 * cq + 1];
-                            cf[cq] = qvalid & ((v[8 * cq] <= x0.x) | (v[8 * cq + 1] <= x0.y) | (v[8 * cq + 2] <= x0.z) | (v[8 * cq + 3] <= x0.w) |
-                                               (v[8 * cq + 4] <= x1.x) | (v[8 * cq + 5] <= x1.y) | (v[8 * cq + 6] <= x1.z) | (v[8 * cq + 7] <= x1.w));
-                        }
-                        if (__any_sync(0xffffffffu, cf[0] | cf[1] | cf[2] | cf[3])) {
-#pragma unroll
-                            for (int cq = 0; cq < 4; ++cq) {
-                                if (__any_sync(0xffffffffu, cf[cq])) {
-                                    const float* thp = reinterpret_cast<const float*>(tp) + 8 * cq;
-                                    uint32_t pend = 0;
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j)
-                                        if (__any_sync(0xffffffffu, qvalid && v[8 * cq + j] <= thp[j])) pend |= 1u << j;
-#pragma unroll 1
-                                    while (pend) {
-                                        const int j = __ffs(pend) - 1;
-                                        pend &= pend - 1;
-                                        const bool s0 = j & 1, s1 = j & 2, s2 = j & 4;
-                                        const float a0 = s0 ? v[8 * cq + 1] : v[8 * cq], a1 = s0 ? v[8 * cq + 3] : v[8 * cq + 2];
-                                        const float a2 = s0 ? v[8 * cq + 5] : v[8 * cq + 4], a3 = s0 ? v[8 * cq + 7] : v[8 * cq + 6];
-                                        const float b0 = s1 ? a1 : a0, b1 = s1 ? a3 : a2;
-                                        const float x = s2 ? b1 : b0;
-                                        const bool hit = qvalid && x <= thp[j];
-                                        const uint32_t bits = hit ? __float_as_uint(x) : 0xffffffffu;
-                                        const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
-                                        const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
-                                        if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
-                                            const uint32_t gcol = col0 + 8 * cq + j;
-                                            atomicMin(ck1 + gcol, make_key(mn, qrow));
-                                            atomicMin(tauc + gcol, __float_as_uint(__uint_as_float(mn) - thr_sub));
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&thrEmpty[ts]);      // last read of this threshold snapshot
-                }
-                // merge the four column parts of the row: two smallest keys of (up to) eight; the column comes out of the key
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float z = e ? k2 : k1;
-                    if (z < 1.6e7f) {
-                        const uint32_t idx = (uint32_t)((int)z - kTcZ0i) & (uint32_t)(kTcZMaxRows - 1);
-                        const u64 k = make_key(__float_as_uint(z), idx);
-                        const u64 old = atomicMin(&mkey[trow], k);
-                        atomicMin(&mkey[kTile + trow], old > k ? old : k);
-                    }
-                }
-                } else {
-                // running top-2 of this thread's row in query tile 0 (t) and tile 1 (to); the two swap after every accumulator
-                RowTop2 t, to;
-                t.v1 = t.v2 = to.v1 = to.v2 = __uint_as_float(kTcBoundBits);
-                t.i1 = t.i2 = to.i1 = to.i2 = 0xffffffffu;
-                float bf1 = -3.0e38f, bf2 = -3.0e38f;      // (kBF: running two LARGEST of -1/2 d^2, low mantissa bits cleared; indices in t.i1, t.i2)
-                for (int tt = 0; tt < u.ntt; ++tt, ++g) {
-                    const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
-                    mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);
-                    const float4* tp = reinterpret_cast<const float4*>(Thr + ts * kTcThrBytes) + part * (kTcPartCols / 4);
-#pragma unroll 1
-                    for (int h = 0; h < nh; ++h, ++a) {
+                    // ================= ORB, "Z" encoding: the accumulator IS the packed key z = Z0 + 2^15 hamming + column =================
+                    // Every element of a row is a distinct positive integer-valued float, smaller = nearer, ties = lower column, so the
+                    // row's two nearest neighbours are the two smallest values this thread ever reads: three FMNMX per element, no
+                    // bound, no slow path, no tie logic.  Columns keep the threshold scheme (their minimum runs over other warps' rows).
+                    const int fq = p.frame_rows[u.q_frame], ft = p.frame_rows[u.t_frame];
+                    const uint32_t qrow = (uint32_t)(qt * kTile + trow);
+                    const bool qvalid = (int)qrow < fq;          // pad query rows read as z = Z0 + 2^22 + column: they must not win a column
+                    // One CTA per pair (units_per_pair == 1): a threshold snapshot only ever holds minima of LOWER query rows (earlier
+                    // query blocks; this block's own updates come after the snapshot was taken), so an equal distance can never win and
+                    // the published threshold may exclude it (z - 1: same column, same distance => same z).  With the pair split over
+                    // several CTAs other CTAs' (higher) rows are in the snapshot too and equal distances must still get through.
+                    const float thr_sub = p.units_per_pair == 1 ? 1.f : 0.f;
+                    float k1 = kTcZNone, k2 = kTcZNone;
+                    for (int tt = 0; tt < u.ntt; ++tt, ++g, ++a) {
+                        const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
+                        mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);
+                        const float4* tp = reinterpret_cast<const float4*>(Thr + ts * kTcThrBytes) + part * (kTcPartCols / 4);
                         const uint32_t as = a % kTcAccStages, aph = (a / kTcAccStages) & 1;
-                        const uint32_t qrow = (uint32_t)((qt + h) * kTile + trow);     // frame row of this thread
-                        uint32_t* sb = &sbound[h * kTile + trow];
                         mbar_wait_sleep<kTcSleepEpilogue>(&accFull[as], aph);
-                        if (warp == 0 && tt == u.ntt - 1) named_bar_arrive(2 + h, 128 + 32);   // slot h may be refilled (see the writers)
+                        if (warp == 0 && tt == u.ntt - 1) named_bar_arrive(2, 128 + 32);     // the query slot may be refilled (see the writers)
                         tc_fence_after();
-                        // All 32 columns of this thread go to registers at once and the accumulator stage is released right
-                        // away: the tensor pipe never waits for the selection logic below.
                         uint32_t vb[32];
                         tmem_ld32(tmem + lane_addr + as * 128 + part * kTcPartCols, vb);
-                        // The row's running second best over ALL column parts (each part keeps a private top-2; the shared
-                        // bound only filters, with '>=' so equal values still reach the private strict-'<' insertion).
-                        float nb = 0.f;
-                        if constexpr (!kBF) nb = -__uint_as_float(*reinterpret_cast<volatile uint32_t*>(sb));
                         tmem_ld_wait();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&accEmpty[as]);
-                        if (p.debug_flags & 1) continue;
-                        float v[32];
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(vb[c]);   // v = -1/2 d^2
-                        // ---- fast path: maxima of 8 groups of 4 columns -> one row test; 4 chains of 8 column tests; ONE vote ----
-                        float gm[8];
-                        bool rflag = false;
-                        if constexpr (!kBF) {
-#pragma unroll
-                        for (int gq = 0; gq < 8; ++gq)
-                            gm[gq] = fmaxf(fmaxf(fmaxf(v[4 * gq], v[4 * gq + 1]), v[4 * gq + 2]), v[4 * gq + 3]);
-                        const float rmax = fmaxf(fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), fmaxf(fmaxf(gm[3], gm[4]), gm[5])), fmaxf(gm[6], gm[7]));
-                        rflag = rmax >= nb;
-                        }
-                        // (A pre-test on one threshold per group of 4 columns -- 8 compares and 2 loads instead of 32 and 8 -- was
-                        // tried and lost 15 %: the loosest of four thresholds lets far too many rows through to the slow path.)
-                        bool cf[4];
-#pragma unroll
-                        for (int cq = 0; cq < 4; ++cq) {
-                            const float4 x0 = tp[2 * cq], x1 = tp[2 * cq + 1];
-                            cf[cq] = (v[8 * cq] >= -x0.x) | (v[8 * cq + 1] >= -x0.y) | (v[8 * cq + 2] >= -x0.z) | (v[8 * cq + 3] >= -x0.w) |
-                                     (v[8 * cq + 4] >= -x1.x) | (v[8 * cq + 5] >= -x1.y) | (v[8 * cq + 6] >= -x1.z) | (v[8 * cq + 7] >= -x1.w);
-                        }
-                        const bool cflag = cf[0] | cf[1] | cf[2] | cf[3];
-                        if (__any_sync(0xffffffffu, rflag || cflag)) {
-                            // ---- slow path: ~2 ln F hits per row and ~ln F per column over a whole sweep ----
+                        if (!(p.debug_flags & 1)) {
+                            float v[32];
+    #pragma unroll
+                            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(vb[c]);
                             const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols);
-                            // columns first (the row insertion below retires elements of v[])
-                            if (__any_sync(0xffffffffu, cflag)) {
-#pragma unroll
+                            if (tt == u.ntt - 1) {       // only the last tile of a frame has pad rows (all-zero operands: z = 0)
+    #pragma unroll
+                                for (int c = 0; c < 32; ++c) v[c] = (int)(col0 + c) < ft ? v[c] : kTcZNone;
+                            }
+                            // ---- rows: running two smallest ----
+    #pragma unroll
+                            for (int c = 0; c < 32; ++c) {
+                                const float hi = fmaxf(k1, v[c]);
+                                k1 = fminf(k1, v[c]);
+                                k2 = fminf(k2, hi);
+                            }
+                            // ---- columns: 4 chains of 8 threshold tests, one vote ----
+                            bool cf[4];
+    #pragma unroll
+                            for (int cq = 0; cq < 4; ++cq) {
+                                const float4 x0 = tp[2 * cq], x1 = tp[2 * cq + 1];
+                                cf[cq] = qvalid & ((v[8 * cq] <= x0.x) | (v[8 * cq + 1] <= x0.y) | (v[8 * cq + 2] <= x0.z) | (v[8 * cq + 3] <= x0.w) |
+                                                   (v[8 * cq + 4] <= x1.x) | (v[8 * cq + 5] <= x1.y) | (v[8 * cq + 6] <= x1.z) | (v[8 * cq + 7] <= x1.w));
+                            }
+                            if (__any_sync(0xffffffffu, cf[0] | cf[1] | cf[2] | cf[3])) {
+    #pragma unroll
                                 for (int cq = 0; cq < 4; ++cq) {
                                     if (__any_sync(0xffffffffu, cf[cq])) {
-                                        // which of the chain's 8 columns have a hit in some lane (warp-uniform mask), then ONE shared
-                                        // event body in a loop: 32 unrolled copies of it were 19 KB of rarely executed code
                                         const float* thp = reinterpret_cast<const float*>(tp) + 8 * cq;
                                         uint32_t pend = 0;
-#pragma unroll
+    #pragma unroll
                                         for (int j = 0; j < 8; ++j)
-                                            if (__any_sync(0xffffffffu, v[8 * cq + j] >= -thp[j])) pend |= 1u << j;
-#pragma unroll 1
+                                            if (__any_sync(0xffffffffu, qvalid && v[8 * cq + j] <= thp[j])) pend |= 1u << j;
+    #pragma unroll 1
                                         while (pend) {
                                             const int j = __ffs(pend) - 1;
                                             pend &= pend - 1;
-                                            // v[8 cq + j] for a warp-uniform j: three levels of selects
                                             const bool s0 = j & 1, s1 = j & 2, s2 = j & 4;
                                             const float a0 = s0 ? v[8 * cq + 1] : v[8 * cq], a1 = s0 ? v[8 * cq + 3] : v[8 * cq + 2];
                                             const float a2 = s0 ? v[8 * cq + 5] : v[8 * cq + 4], a3 = s0 ? v[8 * cq + 7] : v[8 * cq + 6];
                                             const float b0 = s1 ? a1 : a0, b1 = s1 ? a3 : a2;
                                             const float x = s2 ? b1 : b0;
-                                            const bool hit = x >= -thp[j];
-                                            const uint32_t bits = hit ? __float_as_uint(fmaxf(-x, 0.f)) : 0xffffffffu;
+                                            const bool hit = qvalid && x <= thp[j];
+                                            const uint32_t bits = hit ? __float_as_uint(x) : 0xffffffffu;
                                             const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
                                             const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
                                             if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
                                                 const uint32_t gcol = col0 + 8 * cq + j;
                                                 atomicMin(ck1 + gcol, make_key(mn, qrow));
-                                                atomicMin(tauc + gcol, mn);
+                                                atomicMin(tauc + gcol, __float_as_uint(__uint_as_float(mn) - thr_sub));
                                             }
                                         }
                                     }
                                 }
                             }
-                            if constexpr (!kBF)
-                            if (rflag) {
-                                // Per group of 4 columns a LOOP (a real branch, never if-converted) that takes the group's maximum while it
-                                // still beats the bound: insert it, retire it, recompute the group maximum.  Typically one trip in
-                                // one group.  Equal values leave the group lowest column first, so ascending-index ties hold.
-                                bool ins = false;
-#pragma unroll
-                                for (int gq = 0; gq < 8; ++gq) {
-                                    while (gm[gq] >= nb) {
-                                        const float m = gm[gq], d = -m;
-                                        if (!(d < t.v2)) break;     // let through by another part's bound or an equal value: nothing here can enter
-                                        const int j = v[4 * gq] == m ? 0 : (v[4 * gq + 1] == m ? 1 : (v[4 * gq + 2] == m ? 2 : 3));
-                                        const uint32_t idx = col0 + 4 * gq + j;
-                                        if (d < t.v1) {
-                                            t.v2 = t.v1; t.i2 = t.i1;
-                                            t.v1 = d;    t.i1 = idx;
-                                        } else {
-                                            t.v2 = d;    t.i2 = idx;
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&thrEmpty[ts]);      // last read of this threshold snapshot
+                    }
+                    // merge the four column parts of the row: two smallest keys of (up to) eight; the column comes out of the key
+    #pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float z = e ? k2 : k1;
+                        if (z < 1.6e7f) {
+                            const uint32_t idx = (uint32_t)((int)z - kTcZ0i) & (uint32_t)(kTcZMaxRows - 1);
+                            const u64 k = make_key(__float_as_uint(z), idx);
+                            const u64 old = atomicMin(&mkey[trow], k);
+                            atomicMin(&mkey[kTile + trow], old > k ? old : k);
+                        }
+                    }
+                } else {
+                    // running top-2 of this thread's row in query tile 0 (t) and tile 1 (to); the two swap after every accumulator
+                    RowTop2 t, to;
+                    t.v1 = t.v2 = to.v1 = to.v2 = __uint_as_float(kTcBoundBits);
+                    t.i1 = t.i2 = to.i1 = to.i2 = 0xffffffffu;
+                    float bf1 = -3.0e38f, bf2 = -3.0e38f;      // (kBF: running two LARGEST of -1/2 d^2, low mantissa bits cleared; indices in t.i1, t.i2)
+                    for (int tt = 0; tt < u.ntt; ++tt, ++g) {
+                        const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
+                        mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);
+                        const float4* tp = reinterpret_cast<const float4*>(Thr + ts * kTcThrBytes) + part * (kTcPartCols / 4);
+    #pragma unroll 1
+                        for (int h = 0; h < nh; ++h, ++a) {
+                            const uint32_t as = a % kTcAccStages, aph = (a / kTcAccStages) & 1;
+                            const uint32_t qrow = (uint32_t)((qt + h) * kTile + trow);     // frame row of this thread
+                            uint32_t* sb = &sbound[h * kTile + trow];
+                            mbar_wait_sleep<kTcSleepEpilogue>(&accFull[as], aph);
+                            if (warp == 0 && tt == u.ntt - 1) named_bar_arrive(2 + h, 128 + 32);   // slot h may be refilled (see the writers)
+                            tc_fence_after();
+                            // All 32 columns of this thread go to registers at once and the accumulator stage is released right
+                            // away: the tensor pipe never waits for the selection logic below.
+                            uint32_t vb[32];
+                            tmem_ld32(tmem + lane_addr + as * 128 + part * kTcPartCols, vb);
+                            // The row's running second best over ALL column parts (each part keeps a private top-2; the shared
+                            // bound only filters, with '>=' so equal values still reach the private strict-'<' insertion).
+                            float nb = 0.f;
+                            if constexpr (!kBF) nb = -__uint_as_float(*reinterpret_cast<volatile uint32_t*>(sb));
+                            tmem_ld_wait();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&accEmpty[as]);
+                            if (p.debug_flags & 1) continue;
+                            float v[32];
+    #pragma unroll
+                            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(vb[c]);   // v = -1/2 d^2
+                            // ---- fast path: maxima of 8 groups of 4 columns -> one row test; 4 chains of 8 column tests; ONE vote ----
+                            float gm[8];
+                            bool rflag = false;
+                            if constexpr (!kBF) {
+    #pragma unroll
+                            for (int gq = 0; gq < 8; ++gq)
+                                gm[gq] = fmaxf(fmaxf(fmaxf(v[4 * gq], v[4 * gq + 1]), v[4 * gq + 2]), v[4 * gq + 3]);
+                            const float rmax = fmaxf(fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), fmaxf(fmaxf(gm[3], gm[4]), gm[5])), fmaxf(gm[6], gm[7]));
+                            rflag = rmax >= nb;
+                            }
+                            // (A pre-test on one threshold per group of 4 columns -- 8 compares and 2 loads instead of 32 and 8 -- was
+                            // tried and lost 15 %: the loosest of four thresholds lets far too many rows through to the slow path.)
+                            bool cf[4];
+    #pragma unroll
+                            for (int cq = 0; cq < 4; ++cq) {
+                                const float4 x0 = tp[2 * cq], x1 = tp[2 * cq + 1];
+                                cf[cq] = (v[8 * cq] >= -x0.x) | (v[8 * cq + 1] >= -x0.y) | (v[8 * cq + 2] >= -x0.z) | (v[8 * cq + 3] >= -x0.w) |
+                                         (v[8 * cq + 4] >= -x1.x) | (v[8 * cq + 5] >= -x1.y) | (v[8 * cq + 6] >= -x1.z) | (v[8 * cq + 7] >= -x1.w);
+                            }
+                            const bool cflag = cf[0] | cf[1] | cf[2] | cf[3];
+                            if (__any_sync(0xffffffffu, rflag || cflag)) {
+                                // ---- slow path: ~2 ln F hits per row and ~ln F per column over a whole sweep ----
+                                const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols);
+                                // columns first (the row insertion below retires elements of v[])
+                                if (__any_sync(0xffffffffu, cflag)) {
+    #pragma unroll
+                                    for (int cq = 0; cq < 4; ++cq) {
+                                        if (__any_sync(0xffffffffu, cf[cq])) {
+                                            // which of the chain's 8 columns have a hit in some lane (warp-uniform mask), then ONE shared
+                                            // event body in a loop: 32 unrolled copies of it were 19 KB of rarely executed code
+                                            const float* thp = reinterpret_cast<const float*>(tp) + 8 * cq;
+                                            uint32_t pend = 0;
+    #pragma unroll
+                                            for (int j = 0; j < 8; ++j)
+                                                if (__any_sync(0xffffffffu, v[8 * cq + j] >= -thp[j])) pend |= 1u << j;
+    #pragma unroll 1
+                                            while (pend) {
+                                                const int j = __ffs(pend) - 1;
+                                                pend &= pend - 1;
+                                                // v[8 cq + j] for a warp-uniform j: three levels of selects
+                                                const bool s0 = j & 1, s1 = j & 2, s2 = j & 4;
+                                                const float a0 = s0 ? v[8 * cq + 1] : v[8 * cq], a1 = s0 ? v[8 * cq + 3] : v[8 * cq + 2];
+                                                const float a2 = s0 ? v[8 * cq + 5] : v[8 * cq + 4], a3 = s0 ? v[8 * cq + 7] : v[8 * cq + 6];
+                                                const float b0 = s1 ? a1 : a0, b1 = s1 ? a3 : a2;
+                                                const float x = s2 ? b1 : b0;
+                                                const bool hit = x >= -thp[j];
+                                                const uint32_t bits = hit ? __float_as_uint(fmaxf(-x, 0.f)) : 0xffffffffu;
+                                                const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
+                                                const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
+                                                if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
+                                                    const uint32_t gcol = col0 + 8 * cq + j;
+                                                    atomicMin(ck1 + gcol, make_key(mn, qrow));
+                                                    atomicMin(tauc + gcol, mn);
+                                                }
+                                            }
                                         }
-                                        ins = true;
-                                        nb = fmaxf(nb, -t.v2);
-#pragma unroll
-                                        for (int e = 0; e < 4; ++e) v[4 * gq + e] = (e == j) ? -3.0e38f : v[4 * gq + e];
-                                        gm[gq] = fmaxf(fmaxf(fmaxf(v[4 * gq], v[4 * gq + 1]), v[4 * gq + 2]), v[4 * gq + 3]);
                                     }
                                 }
-                                if (ins) atomicMin(sb, __float_as_uint(fmaxf(t.v2, 0.f)));
-                            }
-                        }
-                        if constexpr (kBF) {
-                            // ---- rows, branch-free: two largest of the 32 column-tagged values, then one merge into the running pair ----
-                            const uint32_t bcol0 = (uint32_t)(tt * kTile + part * kTcPartCols);
-                            float m1, m2;
-                            {
-                                const float w0 = __uint_as_float((vb[0] & 0xffffffe0u) | 0u), w1 = __uint_as_float((vb[1] & 0xffffffe0u) | 1u);
-                                m1 = fmaxf(w0, w1);
-                                m2 = fminf(w0, w1);
-                            }
-#pragma unroll
-                            for (int c = 2; c < 32; ++c) {
-                                const float w = __uint_as_float((vb[c] & 0xffffffe0u) | (uint32_t)c);
-                                const float lo = fminf(m1, w);
-                                m1 = fmaxf(m1, w);
-                                m2 = fmaxf(m2, lo);
-                            }
-                            if (m1 > bf2) {       // (running values have their tag bits cleared: on equal truncated values the earlier tile stays)
-                                const bool a1 = m1 > bf1;
-                                const float s_new = a1 ? m2 : m1, s_old = a1 ? bf1 : bf2;
-                                const uint32_t s_oldi = a1 ? t.i1 : t.i2;
-                                const bool c2 = s_new > s_old;
-                                const uint32_t mb = __float_as_uint(m1), sbits = __float_as_uint(s_new);
-                                if (a1) {
-                                    bf1 = __uint_as_float(mb & 0xffffffe0u);
-                                    t.i1 = bcol0 + (mb & 31u);
+                                if constexpr (!kBF)
+                                if (rflag) {
+                                    // Per group of 4 columns a LOOP (a real branch, never if-converted) that takes the group's maximum while it
+                                    // still beats the bound: insert it, retire it, recompute the group maximum.  Typically one trip in
+                                    // one group.  Equal values leave the group lowest column first, so ascending-index ties hold.
+                                    bool ins = false;
+    #pragma unroll
+                                    for (int gq = 0; gq < 8; ++gq) {
+                                        while (gm[gq] >= nb) {
+                                            const float m = gm[gq], d = -m;
+                                            if (!(d < t.v2)) break;     // let through by another part's bound or an equal value: nothing here can enter
+                                            const int j = v[4 * gq] == m ? 0 : (v[4 * gq + 1] == m ? 1 : (v[4 * gq + 2] == m ? 2 : 3));
+                                            const uint32_t idx = col0 + 4 * gq + j;
+                                            if (d < t.v1) {
+                                                t.v2 = t.v1; t.i2 = t.i1;
+                                                t.v1 = d;    t.i1 = idx;
+                                            } else {
+                                                t.v2 = d;    t.i2 = idx;
+                                            }
+                                            ins = true;
+                                            nb = fmaxf(nb, -t.v2);
+    #pragma unroll
+                                            for (int e = 0; e < 4; ++e) v[4 * gq + e] = (e == j) ? -3.0e38f : v[4 * gq + e];
+                                            gm[gq] = fmaxf(fmaxf(fmaxf(v[4 * gq], v[4 * gq + 1]), v[4 * gq + 2]), v[4 * gq + 3]);
+                                        }
+                                    }
+                                    if (ins) atomicMin(sb, __float_as_uint(fmaxf(t.v2, 0.f)));
                                 }
-                                bf2 = c2 ? __uint_as_float(sbits & 0xffffffe0u) : s_old;
-                                t.i2 = c2 ? bcol0 + (sbits & 31u) : s_oldi;
+                            }
+                            if constexpr (kBF) {
+                                // ---- rows, branch-free: two largest of the 32 column-tagged values, then one merge into the running pair ----
+                                const uint32_t bcol0 = (uint32_t)(tt * kTile + part * kTcPartCols);
+                                float m1, m2;
+                                {
+                                    const float w0 = __uint_as_float((vb[0] & 0xffffffe0u) | 0u), w1 = __uint_as_float((vb[1] & 0xffffffe0u) | 1u);
+                                    m1 = fmaxf(w0, w1);
+                                    m2 = fminf(w0, w1);
+                                }
+    #pragma unroll
+                                for (int c = 2; c < 32; ++c) {
+                                    const float w = __uint_as_float((vb[c] & 0xffffffe0u) | (uint32_t)c);
+                                    const float lo = fminf(m1, w);
+                                    m1 = fmaxf(m1, w);
+                                    m2 = fmaxf(m2, lo);
+                                }
+                                if (m1 > bf2) {       // (running values have their tag bits cleared: on equal truncated values the earlier tile stays)
+                                    const bool a1 = m1 > bf1;
+                                    const float s_new = a1 ? m2 : m1, s_old = a1 ? bf1 : bf2;
+                                    const uint32_t s_oldi = a1 ? t.i1 : t.i2;
+                                    const bool c2 = s_new > s_old;
+                                    const uint32_t mb = __float_as_uint(m1), sbits = __float_as_uint(s_new);
+                                    if (a1) {
+                                        bf1 = __uint_as_float(mb & 0xffffffe0u);
+                                        t.i1 = bcol0 + (mb & 31u);
+                                    }
+                                    bf2 = c2 ? __uint_as_float(sbits & 0xffffffe0u) : s_old;
+                                    t.i2 = c2 ? bcol0 + (sbits & 31u) : s_oldi;
+                                }
+                            }
+                            if (kTcQTiles == 2 && nh == 2) {      // next accumulator belongs to the other query tile
+                                const RowTop2 x = t;
+                                t = to;
+                                to = x;
                             }
                         }
-                        if (kTcQTiles == 2 && nh == 2) {      // next accumulator belongs to the other query tile
-                            const RowTop2 x = t;
-                            t = to;
-                            to = x;
-                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&thrEmpty[ts]);      // last read of this threshold snapshot
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&thrEmpty[ts]);      // last read of this threshold snapshot
-                }
-                // ---- end of the sweep for this query block: merge the column parts of every row, publish ----
-                // 64-bit shared-memory atomics on packed keys: the smallest key ends in mkey[.][0], the smallest of all the
-                // "losers" (displaced old minimum, or the newcomer if it did not win) in mkey[.][1] = the second smallest overall.
-                // (an even number of swaps per train tile: t is tile 0's state again, `to` tile 1's)
-                if constexpr (kBF) {     // back to the generic form (1/2 d^2, smaller = nearer); pad rows (-1e30) may have filled a short row
-                    t.v1 = -bf1; t.v2 = -bf2;
-                    if (bf1 < -1.0e29f) t.i1 = 0xffffffffu;
-                    if (bf2 < -1.0e29f) t.i2 = 0xffffffffu;
-                }
-#pragma unroll
-                for (int h = 0; h < kTcQTiles; ++h) {
-                    if (h < nh) {
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const RowTop2& s = h ? to : t;
-                            const uint32_t idx = e ? s.i2 : s.i1;
-                            if (idx != 0xffffffffu) {
-                                const u64 k = make_key(__float_as_uint(fmaxf(e ? s.v2 : s.v1, 0.f)), idx);
-                                const u64 old = atomicMin(&mkey[(h * 2) * kTile + trow], k);
-                                atomicMin(&mkey[(h * 2 + 1) * kTile + trow], old > k ? old : k);
+                    // ---- end of the sweep for this query block: merge the column parts of every row, publish ----
+                    // 64-bit shared-memory atomics on packed keys: the smallest key ends in mkey[.][0], the smallest of all the
+                    // "losers" (displaced old minimum, or the newcomer if it did not win) in mkey[.][1] = the second smallest overall.
+                    // (an even number of swaps per train tile: t is tile 0's state again, `to` tile 1's)
+                    if constexpr (kBF) {     // back to the generic form (1/2 d^2, smaller = nearer); pad rows (-1e30) may have filled a short row
+                        t.v1 = -bf1; t.v2 = -bf2;
+                        if (bf1 < -1.0e29f) t.i1 = 0xffffffffu;
+                        if (bf2 < -1.0e29f) t.i2 = 0xffffffffu;
+                    }
+    #pragma unroll
+                    for (int h = 0; h < kTcQTiles; ++h) {
+                        if (h < nh) {
+    #pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const RowTop2& s = h ? to : t;
+                                const uint32_t idx = e ? s.i2 : s.i1;
+                                if (idx != 0xffffffffu) {
+                                    const u64 k = make_key(__float_as_uint(fmaxf(e ? s.v2 : s.v1, 0.f)), idx);
+                                    const u64 old = atomicMin(&mkey[(h * 2) * kTile + trow], k);
+                                    atomicMin(&mkey[(h * 2 + 1) * kTile + trow], old > k ? old : k);
+                                }
                             }
                         }
                     }
-                }
                 }   // (generic epilogue)
                 asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");
                 if (part < nh) {       // column part h publishes (and resets) query tile h
