@@ -409,15 +409,20 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
     roofline["hbm_peak_gbs"] = peaks.get("hbm_gbs")
     # measured DRAM traffic of this kernel on this command (one ncu pass, committed under profiles/): far BELOW the per-pair
     # algorithmic bytes because pairs launched together share their train frame in L2 (capi.cu sorts a chunk by train frame)
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tr = json.load(f).get({"surf": "surf_tc", "orb": "orb_tc"}[kind] if engine == "tc" else kind)
+    import glob
+    tkey = {"surf": "surf_tc", "orb": "orb_tc"}[kind] if engine == "tc" else kind
+    for tpath in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_traffic_r*.json")), reverse=True):    # newest round that has this kernel
+        try:
+            with open(tpath) as f:
+                tr = json.load(f).get(tkey)
+        except (OSError, ValueError):
+            tr = None
         if tr:
             per_pair = (tr["dram_read_bytes_per_launch"] + tr["dram_write_bytes_per_launch"]) / tr["pairs_per_launch"]
             roofline["traffic"] = per_pair * (comps_per_launch / (n_feat * n_feat))
-            roofline["traffic_source"] = "profiles/ncu_traffic_r1.json (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+            roofline["traffic_source"] = f"profiles/{os.path.basename(tpath)} (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
             roofline["algorithmic_bytes_per_launch"] = (comps_per_launch / (n_feat * n_feat)) * bytes_per_pair
+            break
 
     # ---- CPU baseline (rank 0, N = 1 only): the reference's cv2 calls on a bounded sample ----------------
     cpu = None
