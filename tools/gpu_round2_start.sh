@@ -1,6 +1,7 @@
 #!/bin/bash
 # First GPU call of round 2: everything round 1 could not re-measure after the ORB "Z" encoding became the default.
 # Every command under its own timeout; everything lands in gpurun_out/ as it finishes.
+# Afterwards, here: python tools/profiles_from_gpurun.py r2   (gpurun_out/ -> profiles/)
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
 ( time timeout 400 python -m pytest tests -m gpu -x -q --durations=8 ) > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log
