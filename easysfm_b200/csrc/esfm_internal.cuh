@@ -66,7 +66,7 @@ struct SweepParams {
                                 // (distance, column) keys from the MMA); tc_main holds that kind's images
     int tc_qtiles;              // TC sweep geometry: query tiles per block, 1 or 2 ($ESFM_TC_QT, $ESFM_TC_QT_ORB)
     int debug_flags;            // TC sweep pipeline probes ($ESFM_TC_DEBUG; results are WRONG when set): 1 = epilogue only drains,
-                                // 2 = no MMAs issued, 4 = no train-tile loads
+                                // 2 = no MMAs issued, 4 = no train-tile loads, 8 = no column events, 16 = no row selection
 };
 
 struct FinalizeParams {

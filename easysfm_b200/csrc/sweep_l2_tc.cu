@@ -475,11 +475,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                                 for (int c = 0; c < 32; ++c) v[c] = (int)(col0 + c) < ft ? v[c] : kTcZNone;
                             }
                             // ---- rows: running two smallest ----
+                            if (!(p.debug_flags & 16)) {
     #pragma unroll
                             for (int c = 0; c < 32; ++c) {
                                 const float hi = fmaxf(k1, v[c]);
                                 k1 = fminf(k1, v[c]);
                                 k2 = fminf(k2, hi);
+                            }
                             }
                             // ---- columns: 4 chains of 8 threshold tests, one vote ----
                             bool cf[4];
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                                 cf[cq] = qvalid & ((v[8 * cq] <= x0.x) | (v[8 * cq + 1] <= x0.y) | (v[8 * cq + 2] <= x0.z) | (v[8 * cq + 3] <= x0.w) |
                                                    (v[8 * cq + 4] <= x1.x) | (v[8 * cq + 5] <= x1.y) | (v[8 * cq + 6] <= x1.z) | (v[8 * cq + 7] <= x1.w));
                             }
-                            if (__any_sync(0xffffffffu, cf[0] | cf[1] | cf[2] | cf[3])) {
+                            if (!(p.debug_flags & 8) && __any_sync(0xffffffffu, cf[0] | cf[1] | cf[2] | cf[3])) {
     #pragma unroll
                                 for (int cq = 0; cq < 4; ++cq) {
                                     if (__any_sync(0xffffffffu, cf[cq])) {
@@ -577,7 +579,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                             for (int gq = 0; gq < 8; ++gq)
                                 gm[gq] = fmaxf(fmaxf(fmaxf(v[4 * gq], v[4 * gq + 1]), v[4 * gq + 2]), v[4 * gq + 3]);
                             const float rmax = fmaxf(fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), fmaxf(fmaxf(gm[3], gm[4]), gm[5])), fmaxf(gm[6], gm[7]));
-                            rflag = rmax >= nb;
+                            rflag = rmax >= nb && !(p.debug_flags & 16);
                             }
                             // (A pre-test on one threshold per group of 4 columns -- 8 compares and 2 loads instead of 32 and 8 -- was
                             // tried and lost 15 %: the loosest of four thresholds lets far too many rows through to the slow path.)
@@ -588,7 +590,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                                 cf[cq] = (v[8 * cq] >= -x0.x) | (v[8 * cq + 1] >= -x0.y) | (v[8 * cq + 2] >= -x0.z) | (v[8 * cq + 3] >= -x0.w) |
                                          (v[8 * cq + 4] >= -x1.x) | (v[8 * cq + 5] >= -x1.y) | (v[8 * cq + 6] >= -x1.z) | (v[8 * cq + 7] >= -x1.w);
                             }
-                            const bool cflag = cf[0] | cf[1] | cf[2] | cf[3];
+                            const bool cflag = (cf[0] | cf[1] | cf[2] | cf[3]) && !(p.debug_flags & 8);
                             if (__any_sync(0xffffffffu, rflag || cflag)) {
                                 // ---- slow path: ~2 ln F hits per row and ~ln F per column over a whole sweep ----
                                 const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols);
