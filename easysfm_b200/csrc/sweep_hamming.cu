@@ -211,7 +211,9 @@ size_t sweep_hamming_smem_bytes(int col_cap) {
 }
 
 int sweep_hamming_max_rows() {
-    const size_t cap = (232448 - sweep_hamming_smem_bytes(0)) / 4;
+    // the launch sizes the column minima by the tile-padded row count (plan_chunks: stride rounded up to kTile), so the limit
+    // is rounded DOWN to a whole tile: a frame the bank accepts always launches
+    const size_t cap = (232448 - sweep_hamming_smem_bytes(0)) / 4 / kTile * kTile;
     const size_t lim = (1u << kHamIdxBits) - 1;
     return (int)(cap < lim ? cap : lim);
 }

@@ -22,6 +22,32 @@ def dist64(Q, T):
     return out
 
 
+class LazyDist64:
+    """float64 ground-truth distances of a big pair, evaluated row by row / column by column on demand (an 8000 x 8000
+    float64 matrix is 512 MB and seconds of work; justify_l2 only ever looks at the few rows and columns that differ)."""
+
+    def __init__(self, Q, T):
+        self.Q = Q.astype(np.float64)
+        self.T = T.astype(np.float64)
+        self.shape = (Q.shape[0], T.shape[0])
+        self._rows, self._cols = {}, {}
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple):          # D[:, t]
+            sl, t = key
+            assert sl == slice(None)
+            t = int(t)
+            if t not in self._cols:
+                d = self.Q - self.T[t]
+                self._cols[t] = np.sqrt(np.einsum("qk,qk->q", d, d))
+            return self._cols[t]
+        q = int(key)                        # D[q]
+        if q not in self._rows:
+            d = self.T - self.Q[q]
+            self._rows[q] = np.sqrt(np.einsum("tk,tk->t", d, d))
+        return self._rows[q]
+
+
 def assert_matches_equal(got, ref, exact_distance=True):
     assert len(got) == len(ref), f"match count {len(got)} != {len(ref)}"
     np.testing.assert_array_equal(got["queryIdx"], ref["queryIdx"])
@@ -45,7 +71,6 @@ def justify_l2(Q, T, ratio, cross_check, got, ref, D=None, tol=REL_TOL):
     g = {int(m["queryIdx"]): m for m in got}
     r = {int(m["queryIdx"]): m for m in ref}
     diffs = 0
-    order = np.argsort(D, axis=1, kind="stable")[:, :3] if D.shape[1] >= 3 else None
     for q in sorted(set(g) | set(r)):
         mg, mr = g.get(q), r.get(q)
         if mg is not None and mr is not None and mg["trainIdx"] == mr["trainIdx"]:
