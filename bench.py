@@ -6,9 +6,14 @@ Workload (BASELINE.json configs[3], the config the metric is quoted on): synthet
 is 499,500 image pairs = 3.2e13 comparisons (~1.5 min on one B200), so one *step* is a fixed slice of it:
   value : `pairs_per_step` consecutive pairs of this rank's block-cyclic shard of the triangle, descriptor bank
           already resident in HBM (device-resident throughput; only per-pair counts come back to the host);
-  e2e   : the public call a user makes -- esfm_bank_set_frame_pinned x M + esfm_bank_commit + esfm_match_all_pairs on M
-          host frames (M(M-1)/2 ~ pairs_per_step), host->device upload of the frames from pinned memory and
-          device->host copy of the compacted matches inside the timed region.
+  e2e   : the public call a user makes on HOST buffers -- scheduler.match_all_pairs(frames): esfm_bank_set_frame x M from
+          PAGEABLE memory (what a cv::Mat is) + esfm_bank_commit + all M(M-1)/2 pairs + the compacted matches back on rank 0's
+          host, all inside the timed region.  The triangle is FIXED (M frames, ~4 x pairs_per_step pairs), so at N GPUs this
+          is the sharded job itself (strong scaling): NCCL broadcast of the bank, work-balanced pair deal, chunked NCCL return of
+          the matches to rank 0.  `e2e.sha1` digests (counts, matches) of the last step: it must be equal at N = 1/2/4/8.
+          `e2e_pinned` (N = 1) is the same step fed from page-locked frames (esfm_bank_set_frame_pinned).
+  parity_sample : after the timed loop one timed step's matches are fetched and a seeded sample of its pairs is checked
+          against the oracle (outside the timed region).
 Both are reported as descriptor comparisons/s (rows_q * rows_t per pair, counted once even with cross-check).
 `--impl reference` times the reference's own CPU path (cv2.BFMatcher knnMatch(k=2) + reverse knnMatch(k=1) as in
 python_code/feature_match.py:26-39) on a bounded sample of the same pairs with all host threads.
@@ -124,6 +129,46 @@ def cpu_reference_sample(host_bank, pairs, budget_s, cross_check):
                 return comps / t_total, n_done, t_total, cv2.getNumThreads()
 
 
+def parity_sample(kind, results, step_pairs, raw, n_feat, row_bytes, np_dtype, cols, n_sample):
+    """A seeded sample of one TIMED step's pairs against the oracle (test infrastructure used as the checker, outside the
+    timed region): ORB bit-exact; SURF identical candidates => bit-identical distances, any differing query must be a
+    float64-verified near-tie within the north star's 1e-5 relative tolerance (tests/util.justify_l2)."""
+    import oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import LazyDist64, justify_l2
+    results.fetch()
+    rng = np.random.default_rng(12345)
+    sel = np.sort(rng.choice(len(step_pairs), min(n_sample, len(step_pairs)), replace=False))
+    frame_cache = {}
+
+    def frame(f):
+        if f not in frame_cache:
+            lo = int(f) * n_feat * row_bytes
+            frame_cache[f] = raw[lo: lo + n_feat * row_bytes].cpu().numpy().view(np_dtype).reshape(n_feat, cols)
+        return frame_cache[f]
+
+    mismatches, near_ties, n_matches = 0, 0, 0
+    for k in sel:
+        q, t, got = results.pair_at(int(k))
+        assert (q, t) == tuple(int(x) for x in step_pairs[k])
+        Q, T = frame(q), frame(t)
+        ref = oracle.match(Q, T, RATIO, CROSS_CHECK)
+        n_matches += len(ref)
+        same = len(got) == len(ref) and (got["queryIdx"] == ref["queryIdx"]).all() and (got["trainIdx"] == ref["trainIdx"]).all()
+        if same and (got["distance"] == ref["distance"]).all():
+            continue
+        if kind == "orb":
+            mismatches += 1
+            continue
+        try:
+            near_ties += justify_l2(Q, T, RATIO, CROSS_CHECK, got, ref, D=LazyDist64(Q, T))
+        except AssertionError:
+            mismatches += 1
+    return {"pairs": int(len(sel)), "mismatches": int(mismatches), "matches_checked": int(n_matches),
+            "queries_differing_at_float64_near_ties": int(near_ties),
+            "checker": "oracle.match (oracle/bf_oracle.c) on the last timed device-resident step; SURF tolerance 1e-5 relative"}
+
+
 def run_reference(args, kind):
     """--impl reference: cv2.BFMatcher on the box's host cores; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -176,7 +221,8 @@ def workload_config(kind, pairs_per_step, e2e_frames):
            "ratio": RATIO, "cross_check": CROSS_CHECK,
            "l2_flush": "inputs larger than L2: every step touches new frames of a bank (2.0 GB SURF / 0.64 GB ORB) >> 126 MB L2"}
     if e2e_frames:
-        cfg["e2e_step"] = f"esfm_match_all_pairs on {e2e_frames} host frames ({e2e_frames * (e2e_frames - 1) // 2} pairs)"
+        cfg["e2e_step"] = (f"all pairs of a fixed triangle of {e2e_frames} pageable host frames ({e2e_frames * (e2e_frames - 1) // 2} pairs), "
+                           "matches returned to rank 0's host: the same job at every N (strong scaling)")
     return cfg
 
 
@@ -196,7 +242,8 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
         n_images = args.images
     sms = ctx.sm_count
     pairs_per_step = args.pairs_per_step or sms * (16 if kind == "surf" else 64)
-    e2e_frames = int((1 + (1 + 8 * pairs_per_step) ** 0.5) / 2)  # M(M-1)/2 ~ pairs_per_step
+    e2e_frames = args.e2e_frames or int((1 + (1 + 8 * 4 * pairs_per_step) ** 0.5) / 2)  # M(M-1)/2 ~ 4 x pairs_per_step
+    e2e_frames = max(2, min(e2e_frames, n_images))
 
     # ---- setup (untimed): bank generated on rank 0's GPU, replicated with one NCCL broadcast -------------
     t_setup = time.perf_counter()
@@ -224,14 +271,15 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
     torch.cuda.synchronize()
     bank.commit_device()
 
-    # host copy (pinned) of the frames the e2e steps and the CPU baseline read
+    # host copy (PAGEABLE numpy memory, like the reference's cv::Mat data) of the frames the e2e steps, the parity sample and
+    # the CPU baseline read; rank 0 only
     n_host = min(n_images, e2e_frames * (steps + warmup) + 2)
     row_bytes = 256 if kind == "surf" else 32
-    host_raw = torch.empty((n_host * n_feat * row_bytes,), dtype=torch.uint8, pin_memory=True)
-    host_raw.copy_(raw[: host_raw.numel()])
-    torch.cuda.synchronize()
     np_dtype, cols = (np.float32, 64) if kind == "surf" else (np.uint8, 32)
-    host_bank = host_raw.numpy().view(np_dtype).reshape(n_host, n_feat, cols)
+    host_bank = None
+    if rank == 0 and (e2e_arm or cpu_budget_s > 0):
+        host_raw = raw[: n_host * n_feat * row_bytes].cpu()
+        host_bank = host_raw.numpy().view(np_dtype).reshape(n_host, n_feat, cols)
 
     pairs = scheduler.all_pairs(n_images)
     mine = scheduler.shard_pairs(len(pairs), rank, world, block=64)
@@ -261,10 +309,12 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     n_matches = 0
+    r_last = None
     for s in range(warmup, warmup + steps):
-        r = bank.match_pairs(step_pairs(s), RATIO, CROSS_CHECK, device_resident=True)
-        n_matches += r.n_matches
-        r.close()
+        if r_last is not None:
+            r_last.close()
+        r_last = bank.match_pairs(step_pairs(s), RATIO, CROSS_CHECK, device_resident=True)
+        n_matches += r_last.n_matches
     ev1.record()
     sync_all()
     clocks = sampler.stop()
@@ -285,58 +335,88 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
     sweep_ms = (st1["sweep_ms_total"] - st0["sweep_ms_total"]) / max(1, st1["sweep_launches"] - st0["sweep_launches"])
     comps_per_launch = comps_local / max(1, st1["sweep_launches"] - st0["sweep_launches"])
 
-    # ---- end-to-end arm: host frames in, host matches out, through the public API ----------------------
+    # ---- parity of what was just timed (outside the timed region): the LAST timed step's matches vs the oracle -----------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_sample(kind, r_last, step_pairs(warmup + steps - 1), raw, n_feat, row_bytes, np_dtype, cols, args.parity_pairs)
+    r_last.close()
+
+    # ---- end-to-end arm: PAGEABLE host frames in, host matches out (on rank 0), through the public API -----------------
     dbg = os.environ.get("BENCH_E2E_DEBUG") == "1"
+    e2e_pairs = e2e_frames * (e2e_frames - 1) // 2
+
+    def e2e_window(s):
+        return (s * e2e_frames) % max(1, n_host - e2e_frames + 1)
 
     def e2e_step(s):
-        t = [time.perf_counter()]
-        f0 = (s * e2e_frames) % max(1, n_host - e2e_frames + 1)
-        b = ctx.bank(kind_id, e2e_frames)
-        for k in range(e2e_frames):
-            b.set_frame_pinned(k, host_bank[f0 + k])     # the step's inputs live in pinned host memory: no staging copy
-        t.append(time.perf_counter())
-        b.commit()
-        t.append(time.perf_counter())
-        res = b.match_all_pairs(RATIO, CROSS_CHECK)
-        t.append(time.perf_counter())
-        nm = res.n_matches
-        res.close()
-        b.close()
-        t.append(time.perf_counter())
+        tm = {}
+        frames = None
+        if rank == 0:
+            f0 = e2e_window(s)
+            frames = [host_bank[f0 + k] for k in range(e2e_frames)]
+        res = scheduler.match_all_pairs(frames, RATIO, CROSS_CHECK, ctx=ctx, reuse_staging=True, timing=tm)
         if dbg and rank == 0:
             st = ctx.stats()
-            print("e2e step %d: set_frame %.1f commit %.1f match %.1f (sweep %.1f finalize %.1f) close %.1f ms" % (
-                s, *[1e3 * (t[i + 1] - t[i]) for i in range(3)], st["last_sweep_ms"], st["last_finalize_ms"], 1e3 * (t[4] - t[3])), file=sys.stderr)
-        return nm
+            print("e2e step %d: upload+broadcast %.1f ms, match+return %.1f ms (rank 0 last sweep %.1f finalize %.1f), %d matches" % (
+                s, 1e3 * tm["upload_broadcast_s"], 1e3 * tm["match_gather_s"], st["last_sweep_ms"], st["last_finalize_ms"],
+                res.n_matches), file=sys.stderr)
+        return res
 
-    e2e_steps = steps if e2e_arm else 0
-    for s in range(warmup if e2e_arm else 0):
-        e2e_step(s)
-    sync_all()
-    st2 = ctx.stats()
-    ev0.record()
-    for s in range(warmup, warmup + e2e_steps):
-        e2e_step(s)
-    ev1.record()
-    sync_all()
-    st3 = ctx.stats()
-    e2e_ms = max(ev0.elapsed_time(ev1), 1e-9)
-    e2e_comps_local = st3["comparisons"] - st2["comparisons"]
-    if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-        c = torch.tensor([float(e2e_comps_local)], dtype=torch.float64, device=dev)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        e2e_comps = float(c.item())
-    else:
-        e2e_comps = float(e2e_comps_local)
-    e2e = {"value": e2e_comps / (e2e_ms * 1e-3), "unit": "comparisons/s",
-           "h2d_bytes_per_step": int((st3["h2d_bytes"] - st2["h2d_bytes"]) / steps),
-           "d2h_bytes_per_step": int((st3["d2h_bytes"] - st2["d2h_bytes"]) / steps),
-           "ms_per_step": e2e_ms / steps}
-    if not e2e_arm:
-        e2e = None
+    e2e = None
+    if e2e_arm:
+        for s in range(warmup):
+            e2e_step(s)
+        sync_all()
+        st2 = ctx.stats()
+        ev0.record()
+        res = None
+        n_e2e_matches = 0
+        for s in range(warmup, warmup + steps):
+            res = e2e_step(s)
+            if rank == 0:
+                n_e2e_matches += res.n_matches
+        ev1.record()
+        sync_all()
+        st3 = ctx.stats()
+        e2e_ms = max(ev0.elapsed_time(ev1), 1e-9)
+        if world > 1:
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        e2e_comps = float(steps) * e2e_pairs * n_feat * n_feat
+        e2e = {"value": e2e_comps / (e2e_ms * 1e-3), "unit": "comparisons/s", "scaling": "strong",
+               "h2d_bytes_per_step": int((st3["h2d_bytes"] - st2["h2d_bytes"]) / steps),                  # rank 0: the frames (+ pair lists)
+               "d2h_bytes_per_step": int(n_e2e_matches * 16 / steps + e2e_pairs * 12),                    # matches + counts/offsets reaching rank 0's host
+               "ms_per_step": e2e_ms / steps, "frames": e2e_frames, "pairs_per_step": e2e_pairs,
+               "host_memory": "pageable (esfm_bank_set_frame: staged through pinned memory, upload overlapped frame by frame)",
+               "return_path": "device->host on the one GPU" if world == 1 else
+                              f"{world} ranks: NCCL broadcast of the bank, work-balanced deal, chunked NCCL send of the matches to rank 0, device->host there"}
+        if rank == 0:
+            e2e["sha1"] = res.sha1()      # (counts, matches) of the last step's triangle: equal at every N iff the results are
+            e2e["matches_last_step"] = res.n_matches
+        del res
+        if world == 1:
+            # same step fed from page-locked frames (no staging copy): what a caller with a pinned descriptor arena gets
+            pin = torch.empty((e2e_frames * n_feat * row_bytes,), dtype=torch.uint8, pin_memory=True)
+            pin_np = pin.numpy().view(np_dtype).reshape(e2e_frames, n_feat, cols)
+            def pinned_step(s):
+                f0 = e2e_window(s)
+                pin_np[:] = host_bank[f0:f0 + e2e_frames]      # (untimed part of a real pipeline: the extractor writes there)
+                t0 = time.perf_counter()
+                b = ctx.bank(kind_id, e2e_frames)
+                for k in range(e2e_frames):
+                    b.set_frame_pinned(k, pin_np[k])
+                b.commit()
+                r = b.match_all_pairs(RATIO, CROSS_CHECK)
+                n = r.n_matches
+                r.close(); b.close()
+                return time.perf_counter() - t0
+            for s in range(2):
+                pinned_step(s)
+            tp = sum(pinned_step(warmup + s) for s in range(3))
+            e2e["e2e_pinned"] = {"value": 3.0 * e2e_pairs * n_feat * n_feat / tp, "unit": "comparisons/s", "ms_per_step": 1e3 * tp / 3,
+                                 "note": "esfm_bank_set_frame_pinned (host wall clock, 3 steps)"}
+            del pin, pin_np
 
     # ---- roofline of the dominant kernel (the sweep) -----------------------------------------------------
     peaks, peak_src = _peaks()
@@ -439,12 +519,13 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if kind == "surf" else "u8", "data": "synthetic",
         "config": workload_config(kind, pairs_per_step, e2e_frames),
         "pairs_per_s": value / (n_feat * n_feat), "matches_per_step": n_matches / steps,
-        "engine": engine, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "engine": engine, "e2e": e2e, "parity_sample": parity, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "cpu_baseline": cpu,
         "setup_s": setup_s, "bank_broadcast_ms": bcast_ms,
         "full_job_estimate_s": (n_images * (n_images - 1) / 2) * (n_feat * n_feat) / value,
     }
     bank.close()
-    del host_bank, host_raw, raw
+    del host_bank, raw
     torch.cuda.empty_cache()
     return out
 
@@ -466,6 +547,9 @@ def main():
     ap.add_argument("--hamming-engine", default=None, choices=["tc", "popc"],
                     help="ORB sweep kernel: tcgen05 FP8 +-1 dot product ('tc') or XOR + POPC ('popc'); default = library default")
     ap.add_argument("--no-alt-engine", action="store_true", help="skip the short run of the other engine of each kind")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of a sample of the timed step (runs under ncu)")
+    ap.add_argument("--parity-pairs", type=int, default=20)
+    ap.add_argument("--e2e-frames", type=int, default=0, help="frames of the fixed e2e triangle (default: ~4 x pairs_per_step pairs)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -504,7 +588,7 @@ def main():
         # the other engine of this kind on the same workload, device-resident arm only (short: it is context, not the headline)
         a = bench_kind(args, kind, ctx, dev, rank, world, dist, 3, 3, 0.0, engine=other_engine[kind][engines[kind]], e2e_arm=False)
         (ctx.set_l2_engine if kind == "surf" else ctx.set_hamming_engine)(engines[kind])
-        return {k: a[k] for k in ("engine", "value", "unit", "ms_per_step", "roofline", "clocks")}
+        return {k: a[k] for k in ("engine", "value", "unit", "ms_per_step", "roofline", "clocks", "parity_sample")}
 
     primary = bench_kind(args, args.kind, ctx, dev, rank, world, dist, args.steps, args.warmup, args.cpu_budget_s,
                          engine=engines[args.kind])
@@ -514,8 +598,8 @@ def main():
         other = "orb" if args.kind == "surf" else "surf"
         sec = bench_kind(args, other, ctx, dev, rank, world, dist, max(3, args.steps // 2), args.warmup, args.cpu_budget_s / 2,
                          engine=engines[other])
-        primary["secondary"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "dtype", "config", "pairs_per_s", "e2e", "engine",
-                                                    "roofline", "cpu_baseline", "gpu_launches", "clocks", "full_job_estimate_s")}
+        primary["secondary"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "dtype", "config", "pairs_per_s", "e2e", "parity_sample",
+                                                    "engine", "roofline", "cpu_baseline", "gpu_launches", "clocks", "full_job_estimate_s")}
         if not args.no_alt_engine and world == 1:
             primary["secondary"]["alt_engine"] = alt_run(other)
     ctx.close()

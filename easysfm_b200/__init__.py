@@ -13,11 +13,15 @@ every compute call raises.
 """
 from .capi import (  # noqa: F401
     DMATCH_DTYPE,
+    KEEP_DIGESTS,
+    KEEP_MATCHES,
     KIND_B256,
     KIND_F32X64,
     Bank,
     Context,
     EsfmError,
+    MultiBank,
+    MultiContext,
     Results,
     library_path,
     load_library,
@@ -28,4 +32,4 @@ from .capi import (  # noqa: F401
 from .feature_matching import FeatureMatching, Frame, pairwise_match_descriptors  # noqa: F401
 from .scheduler import all_pairs, match_all_pairs, shard_pairs  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

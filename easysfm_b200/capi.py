@@ -25,6 +25,8 @@ L2_ENGINE_FFMA = 0
 L2_ENGINE_TC = 1
 HAMMING_ENGINE_POPC = 0
 HAMMING_ENGINE_TC = 1
+KEEP_MATCHES = 0
+KEEP_DIGESTS = 1
 
 
 class EsfmError(RuntimeError):
@@ -44,6 +46,21 @@ class Stats(ctypes.Structure):
         ("last_finalize_ms", c_double),
         ("sweep_ms_total", c_double),
         ("sweep_launches", c_uint64),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class MultiTiming(ctypes.Structure):
+    _fields_ = [
+        ("broadcast_ms", c_double),
+        ("commit_ms", c_double),
+        ("match_ms", c_double),
+        ("device_ms_max", c_double),
+        ("device_ms_min", c_double),
+        ("work_imbalance", c_double),
+        ("used_nccl", c_int),
     ]
 
     def as_dict(self):
@@ -80,6 +97,7 @@ SIGNATURES = {
     "esfm_match_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_int, POINTER(c_void_p)]),
     "esfm_match_pairs_device": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_int, POINTER(c_void_p)]),
     "esfm_results_fetch": (c_int, [c_void_p]),
+    "esfm_bank_chunk_pairs": (c_int, [c_void_p, POINTER(c_int64)]),
     "esfm_match_pair": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_void_p, c_int, POINTER(c_int)]),
     "esfm_match_descriptors": (c_int, [c_void_p, c_int, c_void_p, c_int, c_size_t, c_void_p, c_int, c_size_t, c_int,
                                        c_double, c_int, c_void_p, c_int, POINTER(c_int)]),
@@ -92,6 +110,28 @@ SIGNATURES = {
     "esfm_results_save": (c_int, [c_void_p, c_char_p]),
     "esfm_results_load": (c_int, [c_char_p, POINTER(c_void_p)]),
     "esfm_results_params": (c_int, [c_void_p, POINTER(c_int), POINTER(ctypes.c_double), POINTER(c_int)]),
+    "esfm_results_frame_rows": (c_int, [c_void_p, POINTER(c_int32), c_int, POINTER(c_int)]),
+    "esfm_results_validate": (c_int, [c_void_p, c_int, POINTER(c_int32)]),
+    "esfm_match_pairs_keep": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_int, c_int, POINTER(c_void_p)]),
+    "esfm_results_copy_all": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int64)]),
+    "esfm_results_digests": (c_int, [c_void_p, POINTER(c_uint64)]),
+    "esfm_results_segment_count": (c_int, [c_void_p, POINTER(c_int)]),
+    "esfm_results_segment_at": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_int64)]),
+    "esfm_results_pair_layout": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int64)]),
+    "esfm_results_device_matches": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64)]),
+    "esfm_results_device_layout": (c_int, [c_void_p, POINTER(c_int64)]),
+    "esfm_multi_init": (c_int, [c_int, POINTER(c_int), POINTER(c_void_p)]),
+    "esfm_multi_destroy": (c_int, [c_void_p]),
+    "esfm_multi_device_count": (c_int, [c_void_p, POINTER(c_int)]),
+    "esfm_multi_ctx": (c_int, [c_void_p, c_int, POINTER(c_void_p)]),
+    "esfm_multi_timing": (c_int, [c_void_p, POINTER(MultiTiming)]),
+    "esfm_multi_bank_create": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "esfm_multi_bank_set_frame": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_size_t]),
+    "esfm_multi_bank_primary": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "esfm_multi_bank_commit": (c_int, [c_void_p]),
+    "esfm_multi_bank_destroy": (c_int, [c_void_p]),
+    "esfm_multi_match_all_pairs": (c_int, [c_void_p, c_double, c_int, c_int, POINTER(c_void_p)]),
+    "esfm_multi_match_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_int, c_int, POINTER(c_void_p)]),
 }
 
 _LIB = None
@@ -146,10 +186,14 @@ def _as_desc(arr, kind=None):
 class Context:
     """One CUDA device + stream (esfm_ctx_t)."""
 
-    def __init__(self, device: int = 0, stream: int | None = None):
+    def __init__(self, device: int = 0, stream: int | None = None, _borrowed=None):
         self._lib = load_library()
-        h = c_void_p()
-        _check(self._lib.esfm_init(int(device), c_void_p(stream) if stream else None, ctypes.byref(h)))
+        self._owned = _borrowed is None
+        if _borrowed is None:
+            h = c_void_p()
+            _check(self._lib.esfm_init(int(device), c_void_p(stream) if stream else None, ctypes.byref(h)))
+        else:
+            h = _borrowed            # a per-device context of a MultiContext: destroyed by esfm_multi_destroy
         self._h = h
         self.device = int(device)
         # banks and result batches borrow the context's stream, scratch and pinned pool: they must go first
@@ -159,7 +203,8 @@ class Context:
         if getattr(self, "_h", None):
             for child in list(getattr(self, "_children", ())):
                 child.close()
-            self._lib.esfm_destroy(self._h)
+            if self._owned:
+                self._lib.esfm_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -243,19 +288,24 @@ class Context:
 class Bank:
     """Device-resident descriptor bank (esfm_bank_t)."""
 
-    def __init__(self, ctx: Context, kind: int, n_frames: int):
+    def __init__(self, ctx: Context, kind: int, n_frames: int, _borrowed=None):
         self._lib = ctx._lib
         self.ctx = ctx
         self.kind = int(kind)
-        h = c_void_p()
-        _check(self._lib.esfm_bank_create(ctx._h, int(kind), int(n_frames), ctypes.byref(h)))
+        self._owned = _borrowed is None
+        if _borrowed is None:
+            h = c_void_p()
+            _check(self._lib.esfm_bank_create(ctx._h, int(kind), int(n_frames), ctypes.byref(h)))
+        else:
+            h = _borrowed            # the primary replica of a MultiBank: destroyed by esfm_multi_bank_destroy
         self._h = h
         self.n_frames = int(n_frames)
         ctx._children.add(self)
 
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.esfm_bank_destroy(self._h)
+            if self._owned:
+                self._lib.esfm_bank_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -305,6 +355,12 @@ class Bank:
         _check(self._lib.esfm_bank_frame_rows(self._h, int(frame_id), ctypes.byref(r)))
         return r.value
 
+    def chunk_pairs(self) -> int:
+        """Largest batch the library processes as one chunk (a device-resident batch must not exceed it)."""
+        n = c_int64()
+        _check(self._lib.esfm_bank_chunk_pairs(self._h, ctypes.byref(n)))
+        return n.value
+
     def device_bytes(self) -> int:
         n = c_size_t()
         _check(self._lib.esfm_bank_device_bytes(self._h, ctypes.byref(n)))
@@ -316,11 +372,15 @@ class Bank:
         _check(self._lib.esfm_match_all_pairs(self._h, float(ratio), int(bool(cross_check)), ctypes.byref(h)))
         return Results(self._lib, h, self.ctx)
 
-    def match_pairs(self, pairs, ratio: float, cross_check: bool = False, device_resident: bool = False) -> "Results":
+    def match_pairs(self, pairs, ratio: float, cross_check: bool = False, device_resident: bool = False,
+                    keep: int = KEEP_MATCHES) -> "Results":
         p = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
         h = c_void_p()
-        fn = self._lib.esfm_match_pairs_device if device_resident else self._lib.esfm_match_pairs
-        _check(fn(self._h, p.ctypes.data, p.shape[0], float(ratio), int(bool(cross_check)), ctypes.byref(h)))
+        if device_resident:
+            _check(self._lib.esfm_match_pairs_device(self._h, p.ctypes.data, p.shape[0], float(ratio), int(bool(cross_check)), ctypes.byref(h)))
+        else:
+            _check(self._lib.esfm_match_pairs_keep(self._h, p.ctypes.data, p.shape[0], float(ratio), int(bool(cross_check)), int(keep),
+                                                   ctypes.byref(h)))
         return Results(self._lib, h, self.ctx)
 
     def match_pair(self, query_frame: int, train_frame: int, ratio: float, cross_check: bool = False) -> np.ndarray:
@@ -352,16 +412,20 @@ def load_results(path: str) -> "Results":
     return Results(lib, h)
 
 
-def write_match_file(path: str, pairs, matches_per_pair, kind: int, ratio: float, cross_check: bool):
-    """The match-file format written with numpy (tools and tests; the library's writer is esfm_results_save)."""
+def write_match_file(path: str, pairs, matches_per_pair, kind: int, ratio: float, cross_check: bool, frame_rows=None):
+    """The match-file format written with numpy (tools and tests; the library's writer is esfm_results_save).
+    frame_rows given -> version 2 (row counts of the bank's frames stored), else version 1."""
     pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
     counts = np.array([len(m) for m in matches_per_pair], np.int32)
     hdr = np.zeros(1, MATCH_FILE_HEADER)
-    hdr["magic"], hdr["version"], hdr["dmatch_bytes"] = b"ESFMMTCH", 1, DMATCH_DTYPE.itemsize
+    hdr["magic"], hdr["version"], hdr["dmatch_bytes"] = b"ESFMMTCH", 1 if frame_rows is None else 2, DMATCH_DTYPE.itemsize
     hdr["n_pairs"], hdr["n_matches"] = len(pairs), int(counts.sum())
     hdr["kind"], hdr["cross_check"], hdr["ratio"] = kind, int(bool(cross_check)), ratio
     with open(path, "wb") as f:
         f.write(hdr.tobytes())
+        if frame_rows is not None:
+            f.write(np.array([len(frame_rows), 0], np.int32).tobytes())
+            f.write(np.asarray(frame_rows, np.int32).tobytes())
         f.write(pairs.tobytes())
         f.write(counts.tobytes())
         for m in matches_per_pair:
@@ -372,6 +436,9 @@ def read_match_file(path: str):
     """-> (header record, pairs [n,2] int32, counts [n] int32, matches [n_matches] DMATCH_DTYPE)."""
     with open(path, "rb") as f:
         hdr = np.frombuffer(f.read(MATCH_FILE_HEADER.itemsize), MATCH_FILE_HEADER)[0]
+        if int(hdr["version"]) == 2:
+            nf = int(np.frombuffer(f.read(8), np.int32)[0])
+            f.read(4 * nf)
         n = int(hdr["n_pairs"])
         pairs = np.frombuffer(f.read(8 * n), np.int32).reshape(n, 2)
         counts = np.frombuffer(f.read(4 * n), np.int32)
@@ -416,6 +483,20 @@ class Results:
         """Write the (fetched) batch to a match file (include/esfm_match.h: persistence)."""
         _check(self._lib.esfm_results_save(self._h, os.fsencode(path)))
 
+    def frame_rows(self):
+        """Row counts of the frames the batch was matched on (empty array: unknown, a version-1 file)."""
+        n = c_int()
+        _check(self._lib.esfm_results_frame_rows(self._h, None, 0, ctypes.byref(n)))
+        rows = np.zeros(n.value, np.int32)
+        if n.value:
+            _check(self._lib.esfm_results_frame_rows(self._h, rows.ctypes.data_as(POINTER(c_int32)), n.value, ctypes.byref(n)))
+        return rows
+
+    def validate(self, frame_rows):
+        """Raises EsfmError unless the batch fits frames with these row counts (stored counts, pair ids, every match index)."""
+        rows = np.ascontiguousarray(frame_rows, dtype=np.int32)
+        _check(self._lib.esfm_results_validate(self._h, len(rows), rows.ctypes.data_as(POINTER(c_int32))))
+
     def params(self):
         """(kind, ratio, cross_check) the batch was matched with."""
         k, r, c = c_int(), ctypes.c_double(), c_int()
@@ -427,6 +508,49 @@ class Results:
             return np.zeros(0, DMATCH_DTYPE)
         buf = (ctypes.c_char * (n * DMATCH_DTYPE.itemsize)).from_address(ptr)
         return np.frombuffer(buf, dtype=DMATCH_DTYPE, count=n).copy()
+
+    def all_matches(self):
+        """Every pair's matches back to back in batch order, in one call: (matches, offsets[n_pairs + 1])."""
+        out = np.zeros(max(self.n_matches, 1), DMATCH_DTYPE)
+        off = np.zeros(self.n_pairs + 1, np.int64)
+        _check(self._lib.esfm_results_copy_all(self._h, out.ctypes.data, self.n_matches, off.ctypes.data_as(POINTER(c_int64))))
+        return out[: self.n_matches], off
+
+    def segments(self):
+        """Zero-copy views: ([segment arrays], segment index per pair, offset per pair).  The arrays alias library memory and
+        are valid until close()."""
+        n = c_int()
+        _check(self._lib.esfm_results_segment_count(self._h, ctypes.byref(n)))
+        segs = []
+        for s in range(n.value):
+            p, m = c_void_p(), c_int64()
+            _check(self._lib.esfm_results_segment_at(self._h, s, ctypes.byref(p), ctypes.byref(m)))
+            if m.value == 0 or not p.value:
+                segs.append(np.zeros(0, DMATCH_DTYPE))
+            else:
+                buf = (ctypes.c_char * (m.value * DMATCH_DTYPE.itemsize)).from_address(p.value)
+                segs.append(np.frombuffer(buf, dtype=DMATCH_DTYPE, count=m.value))
+        seg = np.zeros(self.n_pairs, np.int32)
+        off = np.zeros(self.n_pairs, np.int64)
+        if self.n_pairs:
+            _check(self._lib.esfm_results_pair_layout(self._h, seg.ctypes.data_as(POINTER(c_int32)), off.ctypes.data_as(POINTER(c_int64))))
+        return segs, seg, off
+
+    def digests(self) -> np.ndarray:
+        """64-bit digest per pair (count, indices and distance bits of its matches, in order)."""
+        out = np.zeros(self.n_pairs, np.uint64)
+        if self.n_pairs:
+            _check(self._lib.esfm_results_digests(self._h, out.ctypes.data_as(POINTER(c_uint64))))
+        return out
+
+    def device_matches(self):
+        """(device pointer, n_matches, per-pair offsets) of a device-resident batch's match arena."""
+        p, n = c_void_p(), c_int64()
+        _check(self._lib.esfm_results_device_matches(self._h, ctypes.byref(p), ctypes.byref(n)))
+        off = np.zeros(self.n_pairs, np.int64)
+        if self.n_pairs:
+            _check(self._lib.esfm_results_device_layout(self._h, off.ctypes.data_as(POINTER(c_int64))))
+        return p.value, n.value, off
 
     def pair_at(self, k: int):
         q, t, n, p = c_int(), c_int(), c_int(), c_void_p()
@@ -441,3 +565,120 @@ class Results:
     def __iter__(self):
         for k in range(self.n_pairs):
             yield self.pair_at(k)
+
+
+class MultiContext:
+    """Several GPUs of one box driven by this one process (esfm_multi_t): one worker thread + stream per device inside the
+    library, bank replicated with one ncclBroadcast, matches merged into one Results in the caller's pair order."""
+
+    def __init__(self, devices):
+        self._lib = load_library()
+        devs = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
+        arr = (c_int * len(devs))(*devs)
+        h = c_void_p()
+        _check(self._lib.esfm_multi_init(len(devs), arr, ctypes.byref(h)))
+        self._h = h
+        self.devices = devs
+        self._children = weakref.WeakSet()
+        self.contexts = []
+        for k, d in enumerate(devs):
+            c = c_void_p()
+            _check(self._lib.esfm_multi_ctx(self._h, k, ctypes.byref(c)))
+            self.contexts.append(Context(d, _borrowed=c))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for child in list(getattr(self, "_children", ())):
+                child.close()
+            for c in self.contexts:
+                c.close()
+            self._lib.esfm_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_engines(self, l2=None, hamming=None):
+        for c in self.contexts:
+            if l2:
+                c.set_l2_engine(l2)
+            if hamming:
+                c.set_hamming_engine(hamming)
+
+    def timing(self) -> dict:
+        t = MultiTiming()
+        _check(self._lib.esfm_multi_timing(self._h, ctypes.byref(t)))
+        return t.as_dict()
+
+    def stats(self):
+        return [c.stats() for c in self.contexts]
+
+    def bank(self, kind: int, n_frames: int) -> "MultiBank":
+        return MultiBank(self, kind, n_frames)
+
+    def bank_from_frames(self, frames) -> "MultiBank":
+        frames = list(frames)
+        _, kind = _as_desc(frames[0])
+        b = MultiBank(self, kind, len(frames))
+        for i, f in enumerate(frames):
+            b.set_frame(i, f)
+        b.commit()
+        return b
+
+
+class MultiBank:
+    """A descriptor bank replicated on every device of a MultiContext (esfm_multi_bank_t)."""
+
+    def __init__(self, multi: MultiContext, kind: int, n_frames: int):
+        self._lib = multi._lib
+        self.multi = multi
+        self.kind = int(kind)
+        self.n_frames = int(n_frames)
+        h = c_void_p()
+        _check(self._lib.esfm_multi_bank_create(multi._h, int(kind), int(n_frames), ctypes.byref(h)))
+        self._h = h
+        multi._children.add(self)
+        p = c_void_p()
+        _check(self._lib.esfm_multi_bank_primary(self._h, ctypes.byref(p)))
+        self.primary = Bank(multi.contexts[0], kind, n_frames, _borrowed=p)   # device-0 replica: set_frame_pinned / device fill
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.primary.close()
+            self._lib.esfm_multi_bank_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_frame(self, frame_id: int, desc):
+        a, _ = _as_desc(desc, self.kind)
+        _check(self._lib.esfm_multi_bank_set_frame(self._h, int(frame_id), a.ctypes.data, a.shape[0], a.shape[1],
+                                                   a.strides[0] if a.shape[0] else a.shape[1] * a.itemsize))
+
+    def commit(self):
+        _check(self._lib.esfm_multi_bank_commit(self._h))
+
+    def match_all_pairs(self, ratio: float, cross_check: bool = False, keep: int = KEEP_MATCHES) -> "Results":
+        h = c_void_p()
+        _check(self._lib.esfm_multi_match_all_pairs(self._h, float(ratio), int(bool(cross_check)), int(keep), ctypes.byref(h)))
+        return Results(self._lib, h, self.multi)
+
+    def match_pairs(self, pairs, ratio: float, cross_check: bool = False, keep: int = KEEP_MATCHES) -> "Results":
+        p = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        h = c_void_p()
+        _check(self._lib.esfm_multi_match_pairs(self._h, p.ctypes.data, p.shape[0], float(ratio), int(bool(cross_check)), int(keep),
+                                                ctypes.byref(h)))
+        return Results(self._lib, h, self.multi)

@@ -33,8 +33,7 @@ constexpr int kHamTile = 256;                        // train rows per smem stag
 constexpr int kHamStages = 4;
 constexpr int kHamRQ = 4;                            // query rows held in registers per thread
 constexpr int kTcKindB256Z = 2;                      // internal sweep kind: B256 with the "Z" operand encoding (tc_layout.cuh)
-constexpr int kTcKindF32BF = 4;                      // internal sweep kind: F32X64 with the branch-free row selection (experimental, $ESFM_TC_SURF_BF=1)
-__host__ __device__ constexpr bool tc_kind_is_f32(int k) { return k == ESFM_KIND_F32X64 || k == kTcKindF32BF; }
+__host__ __device__ constexpr bool tc_kind_is_f32(int k) { return k == ESFM_KIND_F32X64; }
 constexpr int kTcZShift = 15;                        // Z key = kTcZ0i + (hamming << kTcZShift) + train row index inside its frame
 constexpr int kTcZMaxRows = 1 << kTcZShift;          // frames with more rows use the generic tensor-core epilogue
 constexpr int kTcZ0i = 21 * 448 * 448 - (1 << 22);   // 20480: what the 21 offset slots leave after cancelling -2^22

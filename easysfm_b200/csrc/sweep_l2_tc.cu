@@ -153,15 +153,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     constexpr uint32_t kTcBoundBits = tc_kind_is_f32(KIND) ? kTcBoundBitsF32 : (KIND == kTcKindB256Z ? kTcBoundBitsZ : kTcBoundBitsB256);
     constexpr bool kOrb = !tc_kind_is_f32(KIND);          // FP8 operands (both ORB encodings share the MMA sequence and the tile geometry)
     constexpr bool kZ = KIND == kTcKindB256Z;
-    // EXPERIMENTAL ($ESFM_TC_SURF_BF=1, not yet run on a GPU): SURF rows selected branch-free -- the thread-local column goes into the
-    // low 5 mantissa bits of every accumulator, the pass's two largest come out of one FMNMX chain and merge into the running
-    // pair once per pass (earlier tiles win ties on the truncated value).  Ranking error 2^-18 relative instead of ~4e-7 absolute;
-    // finalize.cu re-evaluates the two candidates exactly either way.  The query half norm carries a bias of 2^-10 so that every
-    // accumulator is negative (rounding noise on exact duplicates is ~4e-7 for unit-norm descriptors): for negative floats a
-    // larger mantissa is a smaller value, which is what makes the LOWEST column win among equal truncated values.
-    constexpr bool kBF = KIND == kTcKindF32BF;
-    constexpr float kTcBfBias = 0.0009765625f;
-    static_assert(!(kZ || kBF) || kTcQTiles == 1, "the Z / branch-free epilogues keep one row state per thread");
+    static_assert(!kZ || kTcQTiles == 1, "the Z epilogue keeps one row state per thread");
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -374,7 +366,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                     hs = __fmaf_rn(x.z, x.z, hs); hs = __fmaf_rn(x.w, x.w, hs);
                 }
                 float hq = valid ? 0.5f * hs : kTcPadNorm;   // pad rows can never win a column
-                if constexpr (kBF) { if (valid) hq += kTcBfBias; }
                 float hqh, hqm, hql;
                 tc_split3(hq, hqh, hqm, hql);
                 const uint32_t use = h == 0 ? quse[0] : quse[1];
@@ -542,7 +533,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                     RowTop2 t, to;
                     t.v1 = t.v2 = to.v1 = to.v2 = __uint_as_float(kTcBoundBits);
                     t.i1 = t.i2 = to.i1 = to.i2 = 0xffffffffu;
-                    float bf1 = -3.0e38f, bf2 = -3.0e38f;      // (kBF: running two LARGEST of -1/2 d^2, low mantissa bits cleared; indices in t.i1, t.i2)
                     for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                         const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
                         mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);
@@ -561,8 +551,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                             tmem_ld32(tmem + lane_addr + as * 128 + part * kTcPartCols, vb);
                             // The row's running second best over ALL column parts (each part keeps a private top-2; the shared
                             // bound only filters, with '>=' so equal values still reach the private strict-'<' insertion).
-                            float nb = 0.f;
-                            if constexpr (!kBF) nb = -__uint_as_float(*reinterpret_cast<volatile uint32_t*>(sb));
+                            float nb = -__uint_as_float(*reinterpret_cast<volatile uint32_t*>(sb));
                             tmem_ld_wait();
                             tc_fence_before();
                             __syncwarp();
@@ -573,14 +562,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                             for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(vb[c]);   // v = -1/2 d^2
                             // ---- fast path: maxima of 8 groups of 4 columns -> one row test; 4 chains of 8 column tests; ONE vote ----
                             float gm[8];
-                            bool rflag = false;
-                            if constexpr (!kBF) {
     #pragma unroll
                             for (int gq = 0; gq < 8; ++gq)
                                 gm[gq] = fmaxf(fmaxf(fmaxf(v[4 * gq], v[4 * gq + 1]), v[4 * gq + 2]), v[4 * gq + 3]);
                             const float rmax = fmaxf(fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), fmaxf(fmaxf(gm[3], gm[4]), gm[5])), fmaxf(gm[6], gm[7]));
-                            rflag = rmax >= nb && !(p.debug_flags & 16);
-                            }
+                            const bool rflag = rmax >= nb && !(p.debug_flags & 16);
                             // (A pre-test on one threshold per group of 4 columns -- 8 compares and 2 loads instead of 32 and 8 -- was
                             // tried and lost 15 %: the loosest of four thresholds lets far too many rows through to the slow path.)
                             bool cf[4];
@@ -629,7 +615,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                                         }
                                     }
                                 }
-                                if constexpr (!kBF)
                                 if (rflag) {
                                     // Per group of 4 columns a LOOP (a real branch, never if-converted) that takes the group's maximum while it
                                     // still beats the bound: insert it, retire it, recompute the group maximum.  Typically one trip in
@@ -658,36 +643,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                                     if (ins) atomicMin(sb, __float_as_uint(fmaxf(t.v2, 0.f)));
                                 }
                             }
-                            if constexpr (kBF) {
-                                // ---- rows, branch-free: two largest of the 32 column-tagged values, then one merge into the running pair ----
-                                const uint32_t bcol0 = (uint32_t)(tt * kTile + part * kTcPartCols);
-                                float m1, m2;
-                                {
-                                    const float w0 = __uint_as_float((vb[0] & 0xffffffe0u) | 0u), w1 = __uint_as_float((vb[1] & 0xffffffe0u) | 1u);
-                                    m1 = fmaxf(w0, w1);
-                                    m2 = fminf(w0, w1);
-                                }
-    #pragma unroll
-                                for (int c = 2; c < 32; ++c) {
-                                    const float w = __uint_as_float((vb[c] & 0xffffffe0u) | (uint32_t)c);
-                                    const float lo = fminf(m1, w);
-                                    m1 = fmaxf(m1, w);
-                                    m2 = fmaxf(m2, lo);
-                                }
-                                if (m1 > bf2) {       // (running values have their tag bits cleared: on equal truncated values the earlier tile stays)
-                                    const bool a1 = m1 > bf1;
-                                    const float s_new = a1 ? m2 : m1, s_old = a1 ? bf1 : bf2;
-                                    const uint32_t s_oldi = a1 ? t.i1 : t.i2;
-                                    const bool c2 = s_new > s_old;
-                                    const uint32_t mb = __float_as_uint(m1), sbits = __float_as_uint(s_new);
-                                    if (a1) {
-                                        bf1 = __uint_as_float(mb & 0xffffffe0u);
-                                        t.i1 = bcol0 + (mb & 31u);
-                                    }
-                                    bf2 = c2 ? __uint_as_float(sbits & 0xffffffe0u) : s_old;
-                                    t.i2 = c2 ? bcol0 + (sbits & 31u) : s_oldi;
-                                }
-                            }
                             if (kTcQTiles == 2 && nh == 2) {      // next accumulator belongs to the other query tile
                                 const RowTop2 x = t;
                                 t = to;
@@ -701,11 +656,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                     // 64-bit shared-memory atomics on packed keys: the smallest key ends in mkey[.][0], the smallest of all the
                     // "losers" (displaced old minimum, or the newcomer if it did not win) in mkey[.][1] = the second smallest overall.
                     // (an even number of swaps per train tile: t is tile 0's state again, `to` tile 1's)
-                    if constexpr (kBF) {     // back to the generic form (1/2 d^2, smaller = nearer); pad rows (-1e30) may have filled a short row
-                        t.v1 = -bf1; t.v2 = -bf2;
-                        if (bf1 < -1.0e29f) t.i1 = 0xffffffffu;
-                        if (bf2 < -1.0e29f) t.i2 = 0xffffffffu;
-                    }
     #pragma unroll
                     for (int h = 0; h < kTcQTiles; ++h) {
                         if (h < nh) {
@@ -755,12 +705,11 @@ cudaError_t launch_sweep_l2_tc(const SweepParams& p, int sm_count, cudaStream_t 
     const int n_units = p.n_pairs * p.units_per_pair;
     if (n_units <= 0) return cudaSuccess;
     const int grid = n_units < sm_count ? n_units : sm_count;
-    const int kind = (p.tc_kind == kTcKindB256Z || p.tc_kind == kTcKindF32BF) ? p.tc_kind : (p.tc_kind == ESFM_KIND_B256 ? ESFM_KIND_B256 : ESFM_KIND_F32X64);
-    const int qt = (p.tc_qtiles == 2 && kind != kTcKindB256Z && kind != kTcKindF32BF) ? 2 : 1;
+    const int kind = p.tc_kind == kTcKindB256Z ? p.tc_kind : (p.tc_kind == ESFM_KIND_B256 ? ESFM_KIND_B256 : ESFM_KIND_F32X64);
+    const int qt = (p.tc_qtiles == 2 && kind != kTcKindB256Z) ? 2 : 1;
     const size_t smem = sweep_tc_smem_bytes(qt, kind);
     void (*kern)(const SweepParams) =
         kind == kTcKindB256Z ? sweep_l2_tc_kernel<1, kTcKindB256Z>
-        : kind == kTcKindF32BF ? sweep_l2_tc_kernel<1, kTcKindF32BF>
         : kind == ESFM_KIND_B256 ? (qt == 2 ? sweep_l2_tc_kernel<2, ESFM_KIND_B256> : sweep_l2_tc_kernel<1, ESFM_KIND_B256>)
                                : (qt == 2 ? sweep_l2_tc_kernel<2, ESFM_KIND_F32X64> : sweep_l2_tc_kernel<1, ESFM_KIND_F32X64>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

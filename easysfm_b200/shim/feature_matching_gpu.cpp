@@ -9,7 +9,8 @@
 //     on the GPU for every call (esfm_match_descriptors).
 //   * all-pairs path: call p3dv::esfm_prepare_all_pairs(frames, 'S'|'O', ratio, cross_check) once before the
 //     pair loop (a one-line hook at sfm.cpp:131); every later matchFeatures* call on those frames with the same
-//     ratio is a lookup into the precomputed result (esfm_results_pair).
+//     ratio is a lookup into the precomputed result (esfm_results_pair).  ESFM_GPUS=N (N > 1) runs that pass on N GPUs
+//     of the box from this one process (esfm_multi_*: ncclBroadcast of the bank, pairs dealt by work, matches merged).
 //   * resume: p3dv::esfm_save_matches(path) after the prepare step writes the whole batch to a match file;
 //     p3dv::esfm_load_matches(frames, 'S'|'O', ratio, path) in a later run makes the same lookups work without
 //     matching again (and without touching the GPU).
@@ -37,14 +38,19 @@ namespace {
 
 struct GpuState {
     esfm_ctx_t* ctx = nullptr;
-    esfm_bank_t* bank = nullptr;          // all-pairs bank (esfm_prepare_all_pairs)
+    esfm_bank_t* bank = nullptr;          // all-pairs bank (esfm_prepare_all_pairs), one GPU
+    esfm_multi_t* multi = nullptr;        // ... or several GPUs (ESFM_GPUS > 1)
+    esfm_multi_bank_t* mbank = nullptr;
     esfm_results_t* results = nullptr;
     esfm_kind kind = ESFM_KIND_F32X64;
     double ratio = 0.0;
-    bool cross_check = false;
+    bool cross_check = false;             // the mode of the prepared / loaded batch; also what the per-call path uses from then on
+    bool have_mode = false;
     std::map<unsigned int, int> frame_index;  // frame_t::frame_id -> bank slot
     ~GpuState() {
         if (results) esfm_results_destroy(results);
+        if (mbank) esfm_multi_bank_destroy(mbank);
+        if (multi) esfm_multi_destroy(multi);
         if (bank) esfm_bank_destroy(bank);
         if (ctx) esfm_destroy(ctx);
     }
@@ -60,6 +66,16 @@ bool env_cross_check() {
     return e && e[0] == '1';
 }
 
+// One cross-check mode per process: $ESFM_CROSS_CHECK until a batch is prepared or loaded, that batch's mode afterwards --
+// so a lookup and a per-call fallback of the same run can never disagree.
+bool effective_cross_check();
+
+int env_gpus() {
+    const char* e = std::getenv("ESFM_GPUS");
+    const int n = e ? std::atoi(e) : 1;
+    return n < 1 ? 1 : n;
+}
+
 bool ensure_ctx() {
     GpuState& s = state();
     if (s.ctx) return true;
@@ -69,6 +85,11 @@ bool ensure_ctx() {
         return false;
     }
     return true;
+}
+
+bool effective_cross_check() {
+    GpuState& s = state();
+    return s.have_mode ? s.cross_check : env_cross_check();
 }
 
 bool check_mat(const cv::Mat& m, esfm_kind kind) {
@@ -89,7 +110,7 @@ bool match_common(esfm_kind kind, const char* tag, frame_t& f1, frame_t& f2, std
     }
     const size_t before = matches.size();
     bool done = false;
-    if (s.results && s.kind == kind && s.ratio == ratio) {  // all-pairs lookup
+    if (s.results && s.kind == kind && s.ratio == ratio && s.cross_check == effective_cross_check()) {  // all-pairs lookup
         auto a = s.frame_index.find(f1.frame_id), b = s.frame_index.find(f2.frame_id);
         if (a != s.frame_index.end() && b != s.frame_index.end()) {
             const esfm_dmatch_t* p = nullptr;
@@ -106,7 +127,7 @@ bool match_common(esfm_kind kind, const char* tag, frame_t& f1, frame_t& f2, std
         std::vector<esfm_dmatch_t> buf((size_t)std::max(q.rows, 1));
         int n = 0;
         const int rc = esfm_match_descriptors(s.ctx, kind, q.data, q.rows, (size_t)q.step, t.data, t.rows, (size_t)t.step,
-                                              kind == ESFM_KIND_F32X64 ? 64 : 32, ratio, env_cross_check() ? 1 : 0,
+                                              kind == ESFM_KIND_F32X64 ? 64 : 32, ratio, effective_cross_check() ? 1 : 0,
                                               buf.data(), (int)buf.size(), &n);
         if (rc != ESFM_OK) {
             std::cerr << "match" << tag << " failed: " << esfm_last_error() << std::endl;
@@ -129,22 +150,35 @@ bool match_common(esfm_kind kind, const char* tag, frame_t& f1, frame_t& f2, std
 // train = frames[j], j < i).  feature = 'S' (SURF, L2) or 'O' (ORB, Hamming) as in sfm.cpp:52.
 bool esfm_prepare_all_pairs(std::vector<frame_t>& frames, char feature, double ratio_thre, bool cross_check) {
     GpuState& s = state();
-    if (!ensure_ctx()) return false;
+    const int gpus = env_gpus();
     if (s.results) { esfm_results_destroy(s.results); s.results = nullptr; }
+    if (s.mbank) { esfm_multi_bank_destroy(s.mbank); s.mbank = nullptr; }
     if (s.bank) { esfm_bank_destroy(s.bank); s.bank = nullptr; }
     s.frame_index.clear();
     s.kind = feature == 'O' ? ESFM_KIND_B256 : ESFM_KIND_F32X64;
     s.ratio = ratio_thre;
     s.cross_check = cross_check;
-    int rc = esfm_bank_create(s.ctx, s.kind, (int)frames.size(), &s.bank);
+    s.have_mode = true;
+    int rc = ESFM_OK;
+    if (gpus > 1) {
+        if (!s.multi) rc = esfm_multi_init(gpus, nullptr, &s.multi);
+        if (rc == ESFM_OK) rc = esfm_multi_bank_create(s.multi, s.kind, (int)frames.size(), &s.mbank);
+    } else {
+        if (!ensure_ctx()) return false;
+        rc = esfm_bank_create(s.ctx, s.kind, (int)frames.size(), &s.bank);
+    }
     for (size_t i = 0; rc == ESFM_OK && i < frames.size(); ++i) {
         const cv::Mat& d = frames[i].descriptors;
         if (!check_mat(d, s.kind)) { std::cerr << "esfm_prepare_all_pairs: frame " << i << " has the wrong descriptor type" << std::endl; return false; }
-        rc = esfm_bank_set_frame(s.bank, (int)i, d.data, d.rows, d.rows ? d.cols : (s.kind == ESFM_KIND_F32X64 ? 64 : 32), (size_t)d.step);
+        const int cols = d.rows ? d.cols : (s.kind == ESFM_KIND_F32X64 ? 64 : 32);
+        rc = gpus > 1 ? esfm_multi_bank_set_frame(s.mbank, (int)i, d.data, d.rows, cols, (size_t)d.step)
+                      : esfm_bank_set_frame(s.bank, (int)i, d.data, d.rows, cols, (size_t)d.step);
         s.frame_index[frames[i].frame_id] = (int)i;
     }
-    if (rc == ESFM_OK) rc = esfm_bank_commit(s.bank);
-    if (rc == ESFM_OK) rc = esfm_match_all_pairs(s.bank, ratio_thre, cross_check ? 1 : 0, &s.results);
+    if (rc == ESFM_OK) rc = gpus > 1 ? esfm_multi_bank_commit(s.mbank) : esfm_bank_commit(s.bank);
+    if (rc == ESFM_OK)
+        rc = gpus > 1 ? esfm_multi_match_all_pairs(s.mbank, ratio_thre, cross_check ? 1 : 0, ESFM_KEEP_MATCHES, &s.results)
+                      : esfm_match_all_pairs(s.bank, ratio_thre, cross_check ? 1 : 0, &s.results);
     if (rc != ESFM_OK) {
         std::cerr << "esfm_prepare_all_pairs failed: " << esfm_last_error() << std::endl;
         return false;
@@ -175,11 +209,21 @@ bool esfm_load_matches(std::vector<frame_t>& frames, char feature, double ratio_
         esfm_results_destroy(r);
         return false;
     }
+    // the file must belong to THIS frame list: stored row counts (version-2 files), pair ids and every match index are checked,
+    // so a file saved for another image set cannot hand out-of-range indices to the RANSAC / triangulation code
+    std::vector<int32_t> rows(frames.size());
+    for (size_t i = 0; i < frames.size(); ++i) rows[i] = frames[i].descriptors.rows;
+    if (esfm_results_validate(r, (int)rows.size(), rows.data()) != ESFM_OK) {
+        std::cerr << "esfm_load_matches: " << path << " does not fit these frames: " << esfm_last_error() << std::endl;
+        esfm_results_destroy(r);
+        return false;
+    }
     if (s.results) esfm_results_destroy(s.results);
     s.results = r;
     s.kind = want;
     s.ratio = ratio_thre;
     s.cross_check = cc != 0;
+    s.have_mode = true;
     s.frame_index.clear();
     for (size_t i = 0; i < frames.size(); ++i) s.frame_index[frames[i].frame_id] = (int)i;
     return true;

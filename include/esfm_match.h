@@ -25,7 +25,9 @@
  * throws across the boundary; esfm_last_error() returns a message for the calling thread's last failure.
  * There is NO CPU fallback: without a CUDA device every compute entry point fails with ESFM_ERR_CUDA.
  *
- * Threading: one host thread drives one context; calls on one context are not re-entrant.
+ * Threading: one host thread drives one context; calls on one context are not re-entrant.  esfm_multi_* (several GPUs of one
+ * box from ONE host process, the shape of the reference's single-process caller cpp_code/test/sfm.cpp:32) starts one worker
+ * thread per device internally; the caller still makes one call.
  */
 #ifndef ESFM_MATCH_H_
 #define ESFM_MATCH_H_
@@ -37,7 +39,7 @@
 extern "C" {
 #endif
 
-#define ESFM_ABI_VERSION 1
+#define ESFM_ABI_VERSION 2
 
 typedef enum esfm_status {
     ESFM_OK = 0,
@@ -166,6 +168,9 @@ int esfm_match_pairs(esfm_bank_t* bank, const esfm_pair_t* pairs, int64_t n_pair
 int esfm_match_pairs_device(esfm_bank_t* bank, const esfm_pair_t* pairs, int64_t n_pairs, double ratio,
                             int cross_check, esfm_results_t** results);
 int esfm_results_fetch(esfm_results_t* results);
+/* Largest batch of pairs of this bank that the library processes as ONE chunk (bounded scratch: <= 4 GB of keys, <= 2 GB of
+ * match arena, <= 65536 pairs); only a one-chunk device-resident batch can be fetched / read on the device afterwards. */
+int esfm_bank_chunk_pairs(esfm_bank_t* bank, int64_t* max_pairs);
 /* One pair, caller-owned output (the unmodified per-call shape of matchFeaturesORB/SURF).
  * `cap` = capacity of `out` in matches (rows of the query frame is always enough). */
 int esfm_match_pair(esfm_bank_t* bank, int query_frame, int train_frame, double ratio, int cross_check,
@@ -179,6 +184,15 @@ int esfm_match_descriptors(esfm_ctx_t* ctx, esfm_kind kind, const void* query, i
  * idx = -1 / dist = +inf where the train frame has fewer rows. */
 int esfm_knn2_pair(esfm_bank_t* bank, int query_frame, int train_frame, int32_t* idx, float* dist);
 
+/* What a batch keeps on the host.  The whole-job configs produce more matches than a host should hold at once
+ * (5000 images x 4k ORB features: ~2e10 match records), so a batch can keep only a 64-bit digest per pair (count, indices and
+ * distance bits of its matches folded in order) -- enough to compare runs across GPU counts -- next to the per-pair counts. */
+#define ESFM_KEEP_MATCHES 0
+#define ESFM_KEEP_DIGESTS 1
+/* esfm_match_pairs with an explicit keep mode (ESFM_KEEP_DIGESTS: matches are downloaded chunk by chunk, digested, dropped). */
+int esfm_match_pairs_keep(esfm_bank_t* bank, const esfm_pair_t* pairs, int64_t n_pairs, double ratio, int cross_check, int keep,
+                          esfm_results_t** results);
+
 /* ---- results (replaces frame_pair_t::matches, utility.h:62) -------------------------------- */
 
 int esfm_results_counts(esfm_results_t* results, int64_t* n_pairs, int64_t* n_matches);
@@ -190,6 +204,23 @@ int esfm_results_pair(esfm_results_t* results, int query_frame, int train_frame,
                       int* n_matches);
 /* Per-pair match counts for the whole batch (n_pairs int32 values). */
 int esfm_results_pair_counts(esfm_results_t* results, int32_t* counts);
+/* Bulk accessor: every pair's matches back to back in batch order, in ONE call (n_matches records, esfm_results_counts);
+ * `offsets` (optional, n_pairs + 1 entries) receives where each pair starts.  ESFM_ERR_CAPACITY if `cap` is too small. */
+int esfm_results_copy_all(esfm_results_t* results, esfm_dmatch_t* out, int64_t cap, int64_t* offsets);
+/* Zero-copy view of a fetched batch: its matches live in a few host segments (one per chunk and device); every pair's matches
+ * are contiguous inside one of them.  esfm_results_pair_layout fills, per pair, the segment index and the offset (in matches)
+ * inside it; esfm_results_segment_at returns a segment.  Valid until esfm_results_destroy. */
+int esfm_results_segment_count(esfm_results_t* results, int* n_segments);
+int esfm_results_segment_at(esfm_results_t* results, int segment, const esfm_dmatch_t** matches, int64_t* n_matches);
+int esfm_results_pair_layout(esfm_results_t* results, int32_t* segment, int64_t* offset);
+/* Per-pair 64-bit digests (n_pairs values): stored ones for ESFM_KEEP_DIGESTS batches, else computed from the matches. */
+int esfm_results_digests(esfm_results_t* results, uint64_t* digests);
+/* Device-resident batch (esfm_match_pairs_device, one chunk): the dense match arena on the device, pairs back to back in LAUNCH
+ * order (`device_offsets` of esfm_results_device_layout); valid until the next matching call on the context.  For callers that
+ * move matches between GPUs themselves (the one-process-per-GPU scheduler: NCCL send of this buffer). */
+int esfm_results_device_matches(esfm_results_t* results, void** dev_ptr, int64_t* n_matches);
+/* Offset (in matches) of every pair of a device-resident batch inside that arena (n_pairs values). */
+int esfm_results_device_layout(esfm_results_t* results, int64_t* offsets);
 int esfm_results_destroy(esfm_results_t* results);
 
 /* ---- persistence (restart the SfM pipeline after matching) --------------------
@@ -205,6 +236,51 @@ int esfm_results_save(esfm_results_t* results, const char* path);
 /* The parameters the batch was matched with (also stored in the file, so a resumed run can check them). */
 int esfm_results_params(esfm_results_t* results, int* kind, double* ratio, int* cross_check);
 int esfm_results_load(const char* path, esfm_results_t** results);
+/* Row counts of the frames the batch was matched on (n_frames = 0: unknown, a version-1 file); rows may be NULL. */
+int esfm_results_frame_rows(esfm_results_t* results, int32_t* rows, int cap, int* n_frames);
+/* ESFM_OK iff the batch fits a frame list with these row counts: stored row counts equal, every pair inside [0, n_frames),
+ * every match index inside its frames' rows.  Call it after esfm_results_load before trusting the indices. */
+int esfm_results_validate(esfm_results_t* results, int n_frames, const int32_t* rows);
+
+/* ---- several GPUs of one box, one host process (caller: the single-threaded pair loop sfm.cpp:140-161) -----
+ * esfm_multi_init binds n devices (ids = NULL: devices 0..n-1).  A multi bank is fed like a bank (set_frame x N, or through
+ * its primary replica on device 0); esfm_multi_bank_commit uploads it to device 0, replicates the raw descriptors on the other
+ * devices with ONE ncclBroadcast over NVLink (NCCL is loaded at run time: libnccl.so.2, or $ESFM_NCCL_LIBRARY) and builds
+ * the derived layouts on every device.  esfm_multi_match_* deals blocks of consecutive pairs to the devices by work
+ * (rows_q * rows_t), runs one worker thread + stream per device, returns each device's matches over its own PCIe link
+ * chunk by chunk (the copy of chunk k overlaps the sweep of chunk k + 1) and merges them into ONE results object in the
+ * caller's pair order: byte-identical to the single-device result.  No inter-GPU traffic during matching.
+ * The same device may be listed several times (tests on a one-GPU box): its replicas are then filled by device copies. */
+typedef struct esfm_multi esfm_multi_t;
+typedef struct esfm_multi_bank esfm_multi_bank_t;
+typedef struct esfm_multi_timing_t {
+    double broadcast_ms;      /* last esfm_multi_bank_commit: replication of the raw bank on devices 1..n-1 (host wall clock) */
+    double commit_ms;         /* last esfm_multi_bank_commit: the whole call */
+    double match_ms;          /* last esfm_multi_match_*: the whole call (host wall clock, results merged) */
+    double device_ms_max;     /* ... slowest device's share */
+    double device_ms_min;     /* ... fastest device's share */
+    double work_imbalance;    /* max over devices of assigned comparisons / mean, minus 1 */
+    int used_nccl;            /* 1 = ncclBroadcast, 0 = device copies (one device, or a device listed twice) */
+} esfm_multi_timing_t;
+
+int esfm_multi_init(int n_devices, const int* device_ids, esfm_multi_t** multi);
+int esfm_multi_destroy(esfm_multi_t* multi);
+int esfm_multi_device_count(esfm_multi_t* multi, int* n_devices);
+/* Borrowed per-device context (engine selection, stats); k in [0, n_devices). */
+int esfm_multi_ctx(esfm_multi_t* multi, int k, esfm_ctx_t** ctx);
+int esfm_multi_timing(esfm_multi_t* multi, esfm_multi_timing_t* out);
+
+int esfm_multi_bank_create(esfm_multi_t* multi, esfm_kind kind, int n_frames, esfm_multi_bank_t** bank);
+int esfm_multi_bank_set_frame(esfm_multi_bank_t* bank, int frame_id, const void* data, int rows, int cols, size_t step_bytes);
+/* Borrowed device-0 replica, for every other way of filling a bank (esfm_bank_set_frame_pinned, or esfm_bank_set_frame_rows +
+ * esfm_bank_alloc_device + esfm_bank_device_rows when the descriptors are produced on the device).  Do not commit it. */
+int esfm_multi_bank_primary(esfm_multi_bank_t* bank, esfm_bank_t** primary);
+int esfm_multi_bank_commit(esfm_multi_bank_t* bank);
+int esfm_multi_bank_destroy(esfm_multi_bank_t* bank);
+/* All N(N-1)/2 pairs in the reference's loop order (sfm.cpp:140-161), or an explicit list; keep = ESFM_KEEP_MATCHES | _DIGESTS. */
+int esfm_multi_match_all_pairs(esfm_multi_bank_t* bank, double ratio, int cross_check, int keep, esfm_results_t** results);
+int esfm_multi_match_pairs(esfm_multi_bank_t* bank, const esfm_pair_t* pairs, int64_t n_pairs, double ratio, int cross_check,
+                           int keep, esfm_results_t** results);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,7 @@ def test_python_binding_table_matches_header():
 def test_abi_version_and_struct_layout():
     import easysfm_b200 as esfm
     lib = esfm.load_library()
-    assert lib.esfm_abi_version() == 1
+    assert lib.esfm_abi_version() == 2
     assert esfm.DMATCH_DTYPE.itemsize == 16          # layout of cv::DMatch
     assert [esfm.DMATCH_DTYPE.fields[k][1] for k in ("queryIdx", "trainIdx", "imgIdx", "distance")] == [0, 4, 8, 12]
 

@@ -50,6 +50,39 @@ def test_load_numpy_written_file_and_lookups(tmp_path):
     r.close()
 
 
+def test_version2_file_carries_frame_rows_and_validates(tmp_path):
+    """Version 2 stores the bank's per-frame row counts; esfm_results_validate refuses a batch that does not fit the caller's
+    frames (other row counts, fewer frames, or -- for version-1 files without row counts -- any out-of-range match index)."""
+    n_frames = 6
+    pairs, per_pair = _fake_batch(2, n_frames)
+    rows = [500, 500, 501, 640, 500, 777]
+    v2 = str(tmp_path / "v2.matches")
+    esfm.write_match_file(v2, pairs, per_pair, esfm.KIND_F32X64, 0.5, False, frame_rows=rows)
+    r = esfm.load_results(v2)
+    assert r.frame_rows().tolist() == rows
+    r.validate(rows)
+    with pytest.raises(esfm.EsfmError):
+        r.validate(rows[:-1] + [778])               # a frame changed size since the batch was matched
+    with pytest.raises(esfm.EsfmError):
+        r.validate(rows[:-1])                       # fewer frames
+    again = str(tmp_path / "v2_again.matches")
+    r.save(again)
+    assert open(v2, "rb").read() == open(again, "rb").read()
+    hdr, p2, c2, m2 = esfm.read_match_file(again)
+    assert int(hdr["version"]) == 2 and (p2 == pairs).all() and m2.tobytes() == np.concatenate(per_pair).tobytes()
+    r.close()
+    v1 = str(tmp_path / "v1.matches")
+    esfm.write_match_file(v1, pairs, per_pair, esfm.KIND_F32X64, 0.5, False)
+    r1 = esfm.load_results(v1)
+    assert len(r1.frame_rows()) == 0
+    r1.validate(rows)                               # every index < 500: fits
+    with pytest.raises(esfm.EsfmError):
+        r1.validate([500, 500, 501, 640, 500, 10])  # frame 5 has 10 rows now: some queryIdx of pairs (5, j) is out of range
+    with pytest.raises(esfm.EsfmError):
+        r1.validate(rows[:4])                       # pairs reference frames 4 and 5
+    r1.close()
+
+
 def test_empty_batch_and_bad_files(tmp_path):
     path = str(tmp_path / "empty.matches")
     esfm.write_match_file(path, np.zeros((0, 2), np.int32), [], esfm.KIND_F32X64, 0.5, False)
@@ -98,6 +131,14 @@ def test_shim_resumes_from_match_file_without_a_device(tmp_path):
     assert pos == len(raw)
     # a file matched with another ratio is refused (the shim's SURF default ratio is 0.5, the file says 0.8 / ORB)
     assert subprocess.call([exe, "S", str(len(rows))] + [str(r) for r in rows] + [blob, "3", out],
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) == 7
+    # ... and so is a file that belongs to other frames: stored row counts differ / an index would be out of range
+    esfm.write_match_file(out + ".matches", pairs, per_pair, esfm.KIND_B256, 0.8, False, frame_rows=[50, 0, 31, 44])
+    assert subprocess.call([exe, "O", str(len(rows))] + [str(r) for r in rows] + [blob, "3", out],
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) == 7
+    esfm.write_match_file(out + ".matches", pairs, per_pair, esfm.KIND_B256, 0.8, False)
+    small = [5, 0, 3, 4]
+    assert subprocess.call([exe, "O", str(len(small))] + [str(r) for r in small] + [blob, "3", out],
                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) == 7
 
 
