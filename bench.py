@@ -364,12 +364,12 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
 
     e2e = None
     if e2e_arm:
+        res = None
         for s in range(warmup):
-            e2e_step(s)
+            res = e2e_step(s)     # (held until the next step returns, exactly like the timed steps: the pinned pools reach steady state)
         sync_all()
         st2 = ctx.stats()
         ev0.record()
-        res = None
         n_e2e_matches = 0
         for s in range(warmup, warmup + steps):
             res = e2e_step(s)

@@ -67,7 +67,8 @@ struct DeviceRestore {
     ~DeviceRestore() { if (dev >= 0) cudaSetDevice(dev); }
 };
 
-constexpr int kDealBlock = 64;     // consecutive pairs dealt together (they share the query frame: L2 locality inside a device)
+constexpr int kDealBlock = 64;     // consecutive pairs dealt together (they share the query frame: L2 locality inside a device);
+                                   // small batches use smaller blocks so that every device still gets ~8 of them
 
 }  // namespace
 
@@ -260,8 +261,9 @@ extern "C" int esfm_multi_match_pairs(esfm_multi_bank_t* mb, const esfm_pair_t* 
     // unbalance a deal by count).  Deterministic; every device keeps its pairs in the caller's order.
     std::vector<std::vector<int64_t>> mine((size_t)nd);
     std::vector<double> load((size_t)nd, 0.0);
-    for (int64_t b0 = 0; b0 < n_pairs; b0 += kDealBlock) {
-        const int64_t b1 = std::min<int64_t>(n_pairs, b0 + kDealBlock);
+    const int64_t block = std::max<int64_t>(1, std::min<int64_t>(kDealBlock, n_pairs / ((int64_t)nd * 8)));
+    for (int64_t b0 = 0; b0 < n_pairs; b0 += block) {
+        const int64_t b1 = std::min<int64_t>(n_pairs, b0 + block);
         double w = 0.0;
         for (int64_t k = b0; k < b1; ++k) w += (double)p->rows[(size_t)pairs[k].query] * (double)p->rows[(size_t)pairs[k].train] + 1.0;
         const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());

@@ -55,13 +55,16 @@ def pair_work(pairs: np.ndarray, rows: Sequence[int]) -> np.ndarray:
     return r[pairs[:, 0]] * r[pairs[:, 1]]
 
 
-def deal_pairs(work: np.ndarray, world: int, block: int = DEAL_BLOCK) -> np.ndarray:
+def deal_pairs(work: np.ndarray, world: int, block: Optional[int] = None) -> np.ndarray:
     """owner[pair]: blocks of `block` consecutive pairs, each to the rank with the least work so far (work + 1 per pair, as in
-    csrc/multi.cu).  Deterministic: every rank computes the same deal."""
+    csrc/multi.cu; default block: 64, smaller for small batches so that every rank still gets ~8 blocks).  Deterministic:
+    every rank computes the same deal."""
     n = len(work)
     owner = np.zeros(n, np.int32)
     if world <= 1 or n == 0:
         return owner
+    if block is None:
+        block = max(1, min(DEAL_BLOCK, n // (world * 8)))
     nb = (n + block - 1) // block
     bw = np.add.reduceat(work.astype(np.float64) + 1.0, np.arange(0, n, block))
     load = np.zeros(world)
@@ -276,7 +279,7 @@ _STAGING = _PinnedStaging()
 
 
 def match_all_pairs(frames: Optional[Sequence[np.ndarray]], ratio: float, cross_check: bool, ctx=None, group=None,
-                    block: int = DEAL_BLOCK, reuse_staging: bool = False, timing: Optional[dict] = None):
+                    block: Optional[int] = None, reuse_staging: bool = False, timing: Optional[dict] = None):
     """All pairs of `frames` (given on rank 0) across every rank of `group`.  Returns on rank 0 a ShardedResults in the
     reference's loop order; None on other ranks.  Without a process group: runs on ctx's GPU alone.
     reuse_staging=True keeps rank 0's copies of the other ranks' matches in pinned buffers that the NEXT call overwrites

@@ -59,7 +59,7 @@ def test_chunk_pipeline_is_invisible(ctx, kind):
         assert parts.pair_at(k)[2].tobytes() == whole.pair_at(k)[2].tobytes()
     assert (parts.pair_counts() == whole.pair_counts()).all() and (dig.pair_counts() == whole.pair_counts()).all()
     assert (whole.digests() == parts.digests()).all() and (whole.digests() == dig.digests()).all()
-    assert len(set(whole.digests().tolist())) > 40                       # (pairs with an empty frame share the empty digest)
+    assert len(set(whole.digests().tolist())) > 30                       # (the 30 pairs with a 0/1/2-row frame share few digests)
     with pytest.raises(esfm.EsfmError):
         dig.pair_at(3)                                                   # matches were not kept
     i, j, m = whole.pair_at(40)

@@ -26,7 +26,7 @@ smoke)
   timeout 180 python __graft_entry__.py smoke > gpurun_out/smoke.txt 2>&1 || { echo "SMOKE FAILED"; tail -15 gpurun_out/smoke.txt; exit 1; }
   tail -2 gpurun_out/smoke.txt | cut -c1-200 ;;
 tests)
-  ( time timeout ${TESTS_TIMEOUT:-600} python -m pytest tests -m gpu -x -q --durations=10 ${TESTS_K:+-k "$TESTS_K"} ) > gpurun_out/pytest_gpu.log 2>&1
+  ( time timeout ${TESTS_TIMEOUT:-600} python -m pytest tests -m gpu ${TESTS_FLAGS--x} -q --durations=10 ${TESTS_K:+-k "$TESTS_K"} ) > gpurun_out/pytest_gpu.log 2>&1
   tail -25 gpurun_out/pytest_gpu.log ;;
 bench)
   ( time BENCH_E2E_DEBUG=1 timeout 420 python bench.py $BENCH_ARGS ) > gpurun_out/bench.json 2> gpurun_out/bench.err
