@@ -197,6 +197,42 @@ static cudaError_t pool_malloc(esfm_ctx* ctx, void** p, size_t bytes) {
     return cudaMallocFromPoolAsync(p, std::max<size_t>(bytes, 16), ctx->mempool, ctx->stream);
 }
 
+int esfm::reserve_stream_slots(esfm_ctx* ctx) {
+    if (ctx->h_slot[0]) return ESFM_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    for (int k = 0; k < esfm_ctx::kSlots; ++k) {
+        cudaError_t e = cudaMallocHost((void**)&ctx->h_slot[k], esfm_ctx::kSlotMatches * sizeof(esfm_dmatch_t));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_slot[k], cudaEventDisableTiming);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(ESFM_ERR_NOMEM, "pinned stream slot allocation failed: %s", cudaGetErrorString(e)); }
+    }
+    return ESFM_OK;
+}
+
+// `n` matches from the device arena `src` to pageable host memory `dst`, through the pinned slots: the device->host copy of the
+// next pieces runs (copy stream) while the helper threads move the current piece out of its slot.
+static int stream_down(esfm_ctx* ctx, const esfm_dmatch_t* src, esfm_dmatch_t* dst, size_t n) {
+    if (int rc = reserve_stream_slots(ctx)) return rc;
+    const size_t P = esfm_ctx::kSlotMatches;
+    const size_t pieces = (n + P - 1) / P;
+    size_t issued = 0, done = 0;
+    while (done < pieces) {
+        while (issued < pieces && issued - done < (size_t)esfm_ctx::kSlots) {
+            const size_t cnt = std::min(P, n - issued * P);
+            const int sl = (int)(issued % esfm_ctx::kSlots);
+            CUDA_TRY(cudaMemcpyAsync(ctx->h_slot[sl], src + issued * P, cnt * sizeof(esfm_dmatch_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CUDA_TRY(cudaEventRecord(ctx->ev_slot[sl], ctx->copy_stream));
+            ++issued;
+        }
+        const size_t cnt = std::min(P, n - done * P);
+        const int sl = (int)(done % esfm_ctx::kSlots);
+        CUDA_TRY(cudaEventSynchronize(ctx->ev_slot[sl]));
+        ctx->copier->copy(dst + done * P, ctx->h_slot[sl], cnt * sizeof(esfm_dmatch_t));
+        ++done;
+    }
+    ctx->stats.d2h_bytes += n * sizeof(esfm_dmatch_t);
+    return ESFM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
@@ -296,11 +332,15 @@ extern "C" int esfm_destroy(esfm_ctx_t* ctx) {
         cudaFree(cb.d_pairs); cudaFree(cb.d_pair_off); cudaFree(cb.d_pair_cnt); cudaFree(cb.d_cursor); cudaFree(cb.arena);
         if (cb.h_pairs) cudaFreeHost(cb.h_pairs);
         if (cb.h_meta) cudaFreeHost(cb.h_meta);
-        if (cb.h_ring) cudaFreeHost(cb.h_ring);
         for (cudaEvent_t ev : {cb.ev_t0, cb.ev_t1, cb.ev_t2, cb.ev_meta, cb.ev_copied})
             if (ev) cudaEventDestroy(ev);
     }
     for (auto& b : ctx->pool) cudaFreeHost(b.ptr);
+    for (int k = 0; k < esfm_ctx::kSlots; ++k) {
+        if (ctx->h_slot[k]) cudaFreeHost(ctx->h_slot[k]);
+        if (ctx->ev_slot[k]) cudaEventDestroy(ctx->ev_slot[k]);
+    }
+    free(ctx->h_scratch);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);     // (the stream-ordered frees of the pair banks)
     if (ctx->mempool) cudaMemPoolDestroy(ctx->mempool);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -889,8 +929,9 @@ constexpr uint64_t kOffMask = ((uint64_t)1 << 40) - 1;
 // The chunk pipeline.  Chunk k is swept and finalised on the compute stream into arena[k & 1]; its per-pair counts and
 // offsets, then its matches, travel to the host on the copy stream while chunk k + 1 is being swept; the host thread stays one
 // chunk ahead of the device:
-//     iteration k:  enqueue compute(k) | A(k-1): wait for counts(k-1), enqueue its match download | enqueue counts(k) download
-//                   | B(k-2): matches(k-2) are on the host: move them to their final place (or digest them)
+//     iteration k:  enqueue compute(k) | finish(k-1): wait for counts(k-1), bring its matches to the host | enqueue counts(k)
+// A one-chunk batch lands in ONE pinned buffer borrowed from the context's pool (kept by the results; steady-state calls reuse
+// it); the chunks of a longer batch are streamed through small pinned slots into pageable, huge-page-advised segments.
 int esfm::match_pairs_impl(esfm_bank* b, const esfm_pair_t* pairs, int64_t n_pairs, double ratio, int cross_check, const MatchOpts& opts,
                            esfm_results** out) {
     if (!b || !out) return fail(ESFM_ERR_INVALID, "esfm_match_pairs: NULL argument");
@@ -928,10 +969,10 @@ int esfm::match_pairs_impl(esfm_bank* b, const esfm_pair_t* pairs, int64_t n_pai
 
     const ChunkPlan pl = plan_chunks(b, n_pairs);
     const size_t n_chunks = ((size_t)n_pairs + pl.chunk_pairs - 1) / pl.chunk_pairs;
-    const bool ring = opts.fetch && (n_chunks > 1 || digests_only);   // matches pass through a pinned ring on their way to pageable memory
+    const bool streamed = opts.fetch && (n_chunks > 1 || digests_only);   // matches go to pageable memory through the pinned slots
     if (int rc = ensure_scratch(ctx, b, pl, n_chunks > 1 ? 2 : 1)) return rc;
 
-    struct Chunk { size_t c0 = 0, n = 0; std::vector<uint32_t> order; unsigned long long n_matches = 0; int seg = -1; };
+    struct Chunk { size_t c0 = 0, n = 0; std::vector<uint32_t> order; };
     Chunk chunks[2];
 
     auto enqueue_compute = [&](size_t k) -> int {
@@ -972,7 +1013,7 @@ int esfm::match_pairs_impl(esfm_bank* b, const esfm_pair_t* pairs, int64_t n_pai
         ctx->stats.d2h_bytes += ch.n * (sizeof(int32_t) + sizeof(unsigned long long)) + 2 * sizeof(unsigned long long);
         return ESFM_OK;
     };
-    auto stage_a = [&](size_t k) -> int {           // chunk k has been finalised: book its pairs, start the match download
+    auto finish = [&](size_t k) -> int {            // chunk k has been finalised: book its pairs, bring its matches to the host
         Chunk& ch = chunks[k & 1];
         ChunkBuf& cb = ctx->buf[k & 1];
         CUDA_TRY(cudaEventSynchronize(cb.ev_meta));
@@ -980,81 +1021,78 @@ int esfm::match_pairs_impl(esfm_bank* b, const esfm_pair_t* pairs, int64_t n_pai
         const unsigned long long* h_cur = (const unsigned long long*)cb.h_meta;
         const unsigned long long* h_off = h_cur + 2;
         const int32_t* h_cnt = (const int32_t*)(h_off + ch.n);
-        ch.n_matches = h_cur[0];
-        if ((int)h_cur[1] != 0 || ch.n_matches > cb.arena_cap) return fail(ESFM_ERR_CAPACITY, "match arena overflow (internal sizing error)");
-        ch.seg = (int)res->segments.size();
+        const unsigned long long n_matches = h_cur[0];
+        if ((int)h_cur[1] != 0 || n_matches > cb.arena_cap) return fail(ESFM_ERR_CAPACITY, "match arena overflow (internal sizing error)");
+        const int seg = (int)res->segments.size();
         for (size_t i = 0; i < ch.n; ++i) {
             res->counts[ch.c0 + ch.order[i]] = h_cnt[i];
-            res->offsets[ch.c0 + ch.order[i]] = ((uint64_t)ch.seg << 40) | (uint64_t)h_off[i];
+            res->offsets[ch.c0 + ch.order[i]] = ((uint64_t)seg << 40) | (uint64_t)h_off[i];
             const PairDesc& pd = cb.h_pairs[i];
             ctx->stats.comparisons += (uint64_t)b->rows[pd.q_frame] * (uint64_t)b->rows[pd.t_frame];
         }
         ctx->stats.pairs += ch.n;
-        res->total_matches += (int64_t)ch.n_matches;
+        res->total_matches += (int64_t)n_matches;
         if (!opts.fetch) {
             res->dev_buf = (int)(k & 1);
-            res->device_matches = ch.n_matches;
+            res->device_matches = n_matches;
             res->arena_generation = n_chunks > 1 ? 0 : cb.generation;   // several chunks: the arenas are reused, nothing to fetch later
             return ESFM_OK;
         }
-        const size_t bytes = (size_t)ch.n_matches * sizeof(esfm_dmatch_t);
-        esfm_dmatch_t* dst = nullptr;
-        if (ring) {
-            if (int rc = grow_pinned(&cb.h_ring, &cb.h_ring_cap, (size_t)ch.n_matches)) return rc;
-            dst = cb.h_ring;
-            if (!digests_only) {
-                esfm_results::Segment sg{nullptr, (size_t)ch.n_matches, nullptr};
-                if (ch.n_matches > 0) {
-                    sg.ptr = heap_segment_alloc((size_t)ch.n_matches);
-                    if (!sg.ptr) return fail(ESFM_ERR_NOMEM, "host buffer of %zu bytes for the matches failed", bytes);
-                }
-                res->segments.push_back(sg);
-            }
-        } else {
-            esfm_results::Segment sg{nullptr, (size_t)ch.n_matches, ctx};
-            if (ch.n_matches > 0) {
+        const size_t bytes = (size_t)n_matches * sizeof(esfm_dmatch_t);
+        if (!streamed) {
+            esfm_results::Segment sg{nullptr, (size_t)n_matches, ctx};
+            if (n_matches > 0) {
                 sg.ptr = (esfm_dmatch_t*)pool_acquire(ctx, bytes, nullptr);
                 if (!sg.ptr) return fail(ESFM_ERR_NOMEM, "pinned buffer of %zu bytes for the matches failed", bytes);
             }
             res->segments.push_back(sg);
+            if (n_matches > 0) {
+                CUDA_TRY(cudaMemcpyAsync(sg.ptr, cb.arena, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                ctx->stats.d2h_bytes += bytes;
+                CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+            }
+            return ESFM_OK;
+        }
+        esfm_dmatch_t* dst = nullptr;
+        if (digests_only) {
+            if (ctx->h_scratch_cap < (size_t)n_matches) {
+                free(ctx->h_scratch);
+                ctx->h_scratch_cap = 0;
+                const size_t want = (size_t)n_matches + (size_t)n_matches / 4;
+                ctx->h_scratch = heap_segment_alloc(want);
+                if (!ctx->h_scratch) return fail(ESFM_ERR_NOMEM, "host scratch of %zu bytes failed", want * sizeof(esfm_dmatch_t));
+                ctx->h_scratch_cap = want;
+            }
+            dst = ctx->h_scratch;
+        } else {
+            esfm_results::Segment sg{nullptr, (size_t)n_matches, nullptr};
+            if (n_matches > 0) {
+                sg.ptr = heap_segment_alloc((size_t)n_matches);
+                if (!sg.ptr) return fail(ESFM_ERR_NOMEM, "host buffer of %zu bytes for the matches failed", bytes);
+            }
+            res->segments.push_back(sg);
             dst = sg.ptr;
         }
-        if (ch.n_matches > 0) {
-            CUDA_TRY(cudaMemcpyAsync(dst, cb.arena, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
-            ctx->stats.d2h_bytes += bytes;
-        }
+        if (n_matches > 0)
+            if (int rc = stream_down(ctx, cb.arena, dst, (size_t)n_matches)) return rc;
+        // every piece has left the arena: the chunk after next may overwrite it
         CUDA_TRY(cudaEventRecord(cb.ev_copied, ctx->copy_stream));
         cb.copy_pending = true;
-        return ESFM_OK;
-    };
-    auto stage_b = [&](size_t k) -> int {           // chunk k's matches are in pinned host memory
-        if (!opts.fetch) return ESFM_OK;
-        Chunk& ch = chunks[k & 1];
-        ChunkBuf& cb = ctx->buf[k & 1];
-        CUDA_TRY(cudaEventSynchronize(cb.ev_copied));
-        if (!ring) return ESFM_OK;
-        if (digests_only) {
+        if (digests_only)
             for (size_t i = 0; i < ch.n; ++i) {
                 const size_t g = ch.c0 + ch.order[i];
-                res->digests[g] = digest_matches(cb.h_ring + (res->offsets[g] & kOffMask), res->counts[g]);
+                res->digests[g] = digest_matches(dst + (res->offsets[g] & kOffMask), res->counts[g]);
             }
-        } else if (ch.n_matches > 0) {
-            ctx->copier->copy(res->segments[(size_t)ch.seg].ptr, cb.h_ring, (size_t)ch.n_matches * sizeof(esfm_dmatch_t));
-        }
         return ESFM_OK;
     };
 
     int rc = ESFM_OK;
     for (size_t k = 0; k < n_chunks && !rc; ++k) {
-        // B(k-2) first when its ring slot / order vector is about to be reused by chunk k
-        if (k >= 2) rc = stage_b(k - 2);
-        if (!rc) rc = enqueue_compute(k);
-        if (!rc && k >= 1) rc = stage_a(k - 1);
+        rc = enqueue_compute(k);
+        if (!rc && k >= 1) rc = finish(k - 1);      // (the device is busy with chunk k meanwhile)
         if (!rc) rc = enqueue_meta(k);
     }
-    if (!rc && n_chunks >= 2) rc = stage_b(n_chunks - 2);
-    if (!rc) rc = stage_a(n_chunks - 1);
-    if (!rc) rc = stage_b(n_chunks - 1);
+    if (!rc) rc = finish(n_chunks - 1);
     if (rc) {
         cudaStreamSynchronize(ctx->stream);         // nothing may still write into buffers the guard is about to release
         cudaStreamSynchronize(ctx->copy_stream);

@@ -59,7 +59,6 @@ struct ChunkBuf {
     // pinned host memory
     PairDesc* h_pairs = nullptr;   size_t h_pairs_cap = 0;     // launch-ordered pair list (upload)
     unsigned char* h_meta = nullptr; size_t h_meta_bytes = 0;  // cursor + offsets + counts (download)
-    esfm_dmatch_t* h_ring = nullptr; size_t h_ring_cap = 0;    // matches of a multi-chunk batch on their way to pageable memory
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_t2 = nullptr;   // sweep start / sweep end / finalize end
     cudaEvent_t ev_meta = nullptr, ev_copied = nullptr;
     bool copy_pending = false;                   // a device->host copy of the arena may still be in flight (ev_copied)
@@ -91,6 +90,14 @@ struct esfm_ctx {
     struct Pinned { void* ptr; size_t bytes; bool in_use; };
     std::vector<Pinned> pool;
     esfm::CopyPool* copier = nullptr;
+    // Matches of a multi-chunk batch reach pageable host memory through a FEW SMALL pinned slots, piece by piece (device->host
+    // copy of piece i + 1 overlapped with the host copy of piece i): allocating pinned memory costs ~1 s per GB, so whole-chunk
+    // pinned buffers would cost more than the sweeps of a job that runs a handful of chunks per device.
+    static constexpr int kSlots = 4;
+    static constexpr size_t kSlotMatches = (size_t)2 << 20;     // 2 Mi matches = 32 MB per slot
+    esfm_dmatch_t* h_slot[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_slot[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    esfm_dmatch_t* h_scratch = nullptr; size_t h_scratch_cap = 0;   // pageable scratch of digests-only batches (one chunk's matches)
     struct esfm_bank* pair_bank[2] = {nullptr, nullptr};   // reusable two-frame banks of esfm_match_descriptors, one per kind
 };
 
@@ -162,5 +169,6 @@ uint64_t digest_matches(const esfm_dmatch_t* m, int n);
 void* pool_acquire(esfm_ctx* ctx, size_t bytes, size_t* got);
 void pool_release(esfm_ctx* ctx, void* ptr);
 esfm_dmatch_t* heap_segment_alloc(size_t n_matches);
+int reserve_stream_slots(esfm_ctx* ctx);     // allocate the pinned slots now (esfm_multi_init: outside any job's clock)
 
 }  // namespace esfm

@@ -114,6 +114,8 @@ extern "C" int esfm_multi_init(int n_devices, const int* device_ids, esfm_multi_
         esfm_ctx* c = nullptr;
         if (int rc = esfm_init(m->devices[(size_t)k], nullptr, &c)) { esfm_multi_destroy(m); return rc; }
         m->ctx.push_back(c);
+        // a multi-device job streams every device's matches through a few pinned slots: allocate them here, not on the job's clock
+        if (int rc = reserve_stream_slots(c)) { esfm_multi_destroy(m); return rc; }
     }
     if (n_devices > 1 && m->distinct) {
         if (int rc = load_nccl(m->nccl)) { esfm_multi_destroy(m); return rc; }
@@ -122,6 +124,23 @@ extern "C" int esfm_multi_init(int n_devices, const int* device_ids, esfm_multi_
         if (r != 0) {
             const int rc = fail(ESFM_ERR_CUDA, "ncclCommInitAll failed: %s", m->nccl.GetErrorString(r));
             m->comms.clear();
+            esfm_multi_destroy(m);
+            return rc;
+        }
+        // NCCL connects its channels lazily at the first collective (hundreds of ms): do that here with a 16-byte broadcast
+        ncclResult_t w = m->nccl.GroupStart();
+        for (int k = 0; k < n_devices && w == 0; ++k) {
+            cudaSetDevice(m->devices[(size_t)k]);
+            void* buf = m->ctx[(size_t)k]->buf[1].d_cursor;
+            w = m->nccl.Broadcast(buf, buf, 16, kNcclUint8, 0, m->comms[(size_t)k], m->ctx[(size_t)k]->stream);
+        }
+        const ncclResult_t w2 = m->nccl.GroupEnd();
+        for (int k = 0; k < n_devices; ++k) {
+            cudaSetDevice(m->devices[(size_t)k]);
+            cudaStreamSynchronize(m->ctx[(size_t)k]->stream);
+        }
+        if (w != 0 || w2 != 0) {
+            const int rc = fail(ESFM_ERR_CUDA, "NCCL warm-up broadcast failed: %s", m->nccl.GetErrorString(w != 0 ? w : w2));
             esfm_multi_destroy(m);
             return rc;
         }
