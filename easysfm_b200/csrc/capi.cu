@@ -858,6 +858,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, ChunkBuf& cb, si
     sp.col_thr = ctx->col_thr;
     sp.stride = pl.stride;
     sp.col_cap = pl.col_cap;
+    sp.need_cols = (cross_check || knn_idx) ? 1 : 0;
     if (const char* dbg = getenv("ESFM_TC_DEBUG")) sp.debug_flags = atoi(dbg);
     sp.tc_qtiles = b->kind == ESFM_KIND_B256 ? ctx->tc_qtiles_orb : ctx->tc_qtiles;
     sp.tc_kind = zmode ? kTcKindB256Z : b->kind;

@@ -44,7 +44,7 @@ constexpr int kTcWriterWarp0 = kTcEpiWarps + 4;         // warps 20..23: warp % 
 // warpgroups shrink to 40 and the four epilogue warpgroups grow to 96 (32 accumulator columns + 8 group maxima + thresholds
 // live at once).  setmaxnreg.inc can only take what setmaxnreg.dec of the SAME CTA released (the unallocated rest of the
 // register file is not in the pool -- asking for more blocks forever), hence the balance check.
-constexpr int kTcLaunchRegs = 80, kTcEpiRegs = 96, kTcServiceRegs = 40;
+constexpr int kTcLaunchRegs = 80, kTcEpiRegs = 96, kTcServiceRegs = 48;
 static_assert(256 * (kTcLaunchRegs - kTcServiceRegs) >= kTcEpiThreads * (kTcEpiRegs - kTcLaunchRegs), "setmaxnreg pool would deadlock");
 static_assert(kTcThreads * kTcLaunchRegs <= 65536 && (65536 / kTcThreads) / 8 * 8 == kTcLaunchRegs, "launch register count drifted");
 constexpr int kTcPartCols = kTile / kTcColParts;        // 32 columns per epilogue thread and stage
@@ -457,14 +457,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&accEmpty[as]);
                         if (!(p.debug_flags & 1)) {
+                            const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols);
+                            if (tt == u.ntt - 1) {       // only the last tile of a frame has pad rows (all-zero operands: z = 0)
+                                // masked IN PLACE (predicated moves): a select into new registers made the compiler copy all 32
+                                // accumulators on every pass of every tile
+    #pragma unroll
+                                for (int c = 0; c < 32; ++c)
+                                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, %2;\n\t@p mov.b32 %0, 0x7f61b1e6;\n\t}"      // kTcZNone = 3.0e38f
+                                                 : "+r"(vb[c]) : "r"((int)(col0 + c)), "r"(ft));
+                            }
                             float v[32];
     #pragma unroll
                             for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(vb[c]);
-                            const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols);
-                            if (tt == u.ntt - 1) {       // only the last tile of a frame has pad rows (all-zero operands: z = 0)
-    #pragma unroll
-                                for (int c = 0; c < 32; ++c) v[c] = (int)(col0 + c) < ft ? v[c] : kTcZNone;
-                            }
                             // ---- rows: running two smallest ----
                             if (!(p.debug_flags & 16)) {
     #pragma unroll
@@ -475,22 +479,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                             }
                             }
                             // ---- columns: 4 chains of 8 threshold tests, one vote ----
+                            if (p.need_cols) {
+                            float th[32];
+    #pragma unroll
+                            for (int c4 = 0; c4 < 8; ++c4) {
+                                const float4 x = tp[c4];
+                                th[4 * c4] = x.x; th[4 * c4 + 1] = x.y; th[4 * c4 + 2] = x.z; th[4 * c4 + 3] = x.w;
+                            }
                             bool cf[4];
     #pragma unroll
                             for (int cq = 0; cq < 4; ++cq) {
-                                const float4 x0 = tp[2 * cq], x1 = tp[2 * cq + 1];
-                                cf[cq] = qvalid & ((v[8 * cq] <= x0.x) | (v[8 * cq + 1] <= x0.y) | (v[8 * cq + 2] <= x0.z) | (v[8 * cq + 3] <= x0.w) |
-                                                   (v[8 * cq + 4] <= x1.x) | (v[8 * cq + 5] <= x1.y) | (v[8 * cq + 6] <= x1.z) | (v[8 * cq + 7] <= x1.w));
+                                bool f = false;
+    #pragma unroll
+                                for (int j = 0; j < 8; ++j) f |= v[8 * cq + j] <= th[8 * cq + j];
+                                cf[cq] = qvalid & f;
                             }
                             if (!(p.debug_flags & 8) && __any_sync(0xffffffffu, cf[0] | cf[1] | cf[2] | cf[3])) {
+                                // Column events (~1-2 per pass).  Normally the lanes that beat a threshold post their keys themselves:
+                                // per column one predicated fire-and-forget RED.MIN.64 on the packed (key, query row) + one RED.MIN.32 on
+                                // the threshold, straight from the statically indexed accumulator (the warp-wide winner election this
+                                // replaces cost ~70 instructions per event plus ~40 per chain: 35 % of the kernel's instructions).  When
+                                // MANY rows beat a chain's thresholds at once (the first query block of a pair: no bounds yet) the
+                                // election stays, or the L2 would see a thousand atomics per pass.
+                                u64* ckp = ck1 + col0;
+                                uint32_t* thp = tauc + col0;
     #pragma unroll
                                 for (int cq = 0; cq < 4; ++cq) {
-                                    if (__any_sync(0xffffffffu, cf[cq])) {
-                                        const float* thp = reinterpret_cast<const float*>(tp) + 8 * cq;
+                                    const uint32_t hm = __ballot_sync(0xffffffffu, cf[cq]);
+                                    if (hm == 0) continue;
+                                    if (__popc(hm) <= 4) {
+    #pragma unroll
+                                        for (int j = 0; j < 8; ++j) {
+                                            const float x = v[8 * cq + j];
+                                            if (qvalid && x <= th[8 * cq + j]) {
+                                                atomicMin(ckp + 8 * cq + j, make_key(__float_as_uint(x), qrow));
+                                                atomicMin(thp + 8 * cq + j, __float_as_uint(x - thr_sub));
+                                            }
+                                        }
+                                    } else {
                                         uint32_t pend = 0;
     #pragma unroll
                                         for (int j = 0; j < 8; ++j)
-                                            if (__any_sync(0xffffffffu, qvalid && v[8 * cq + j] <= thp[j])) pend |= 1u << j;
+                                            if (__any_sync(0xffffffffu, qvalid && v[8 * cq + j] <= th[8 * cq + j])) pend |= 1u << j;
     #pragma unroll 1
                                         while (pend) {
                                             const int j = __ffs(pend) - 1;
@@ -500,18 +530,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                                             const float a2 = s0 ? v[8 * cq + 5] : v[8 * cq + 4], a3 = s0 ? v[8 * cq + 7] : v[8 * cq + 6];
                                             const float b0 = s1 ? a1 : a0, b1 = s1 ? a3 : a2;
                                             const float x = s2 ? b1 : b0;
-                                            const bool hit = qvalid && x <= thp[j];
+                                            const float t0 = s0 ? th[8 * cq + 1] : th[8 * cq], t1 = s0 ? th[8 * cq + 3] : th[8 * cq + 2];
+                                            const float t2 = s0 ? th[8 * cq + 5] : th[8 * cq + 4], t3 = s0 ? th[8 * cq + 7] : th[8 * cq + 6];
+                                            const float u0 = s1 ? t1 : t0, u1 = s1 ? t3 : t2;
+                                            const bool hit = qvalid && x <= (s2 ? u1 : u0);
                                             const uint32_t bits = hit ? __float_as_uint(x) : 0xffffffffu;
                                             const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
                                             const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
                                             if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
-                                                const uint32_t gcol = col0 + 8 * cq + j;
-                                                atomicMin(ck1 + gcol, make_key(mn, qrow));
-                                                atomicMin(tauc + gcol, __float_as_uint(__uint_as_float(mn) - thr_sub));
+                                                atomicMin(ckp + 8 * cq + j, make_key(mn, qrow));
+                                                atomicMin(thp + 8 * cq + j, __float_as_uint(__uint_as_float(mn) - thr_sub));
                                             }
                                         }
                                     }
                                 }
+                            }
                             }
                         }
                         __syncwarp();
@@ -569,12 +602,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                             const bool rflag = rmax >= nb && !(p.debug_flags & 16);
                             // (A pre-test on one threshold per group of 4 columns -- 8 compares and 2 loads instead of 32 and 8 -- was
                             // tried and lost 15 %: the loosest of four thresholds lets far too many rows through to the slow path.)
-                            bool cf[4];
+                            float th[32];          // negated thresholds: a column event is v >= th
+                            bool cf[4] = {false, false, false, false};
+                            if (p.need_cols) {
     #pragma unroll
-                            for (int cq = 0; cq < 4; ++cq) {
-                                const float4 x0 = tp[2 * cq], x1 = tp[2 * cq + 1];
-                                cf[cq] = (v[8 * cq] >= -x0.x) | (v[8 * cq + 1] >= -x0.y) | (v[8 * cq + 2] >= -x0.z) | (v[8 * cq + 3] >= -x0.w) |
-                                         (v[8 * cq + 4] >= -x1.x) | (v[8 * cq + 5] >= -x1.y) | (v[8 * cq + 6] >= -x1.z) | (v[8 * cq + 7] >= -x1.w);
+                                for (int c4 = 0; c4 < 8; ++c4) {
+                                    const float4 x = tp[c4];
+                                    th[4 * c4] = -x.x; th[4 * c4 + 1] = -x.y; th[4 * c4 + 2] = -x.z; th[4 * c4 + 3] = -x.w;
+                                }
+    #pragma unroll
+                                for (int cq = 0; cq < 4; ++cq) {
+                                    bool f = false;
+    #pragma unroll
+                                    for (int j = 0; j < 8; ++j) f |= v[8 * cq + j] >= th[8 * cq + j];
+                                    cf[cq] = f;
+                                }
                             }
                             const bool cflag = (cf[0] | cf[1] | cf[2] | cf[3]) && !(p.debug_flags & 8);
                             if (__any_sync(0xffffffffu, rflag || cflag)) {
@@ -582,16 +624,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                                 const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols);
                                 // columns first (the row insertion below retires elements of v[])
                                 if (__any_sync(0xffffffffu, cflag)) {
+                                    // Few rows beat a chain's thresholds (the normal case): every such lane posts its own key -- one
+                                    // predicated fire-and-forget RED.MIN.64 on (1/2 d^2 bits, query row) + one RED.MIN.32 on the threshold
+                                    // per column, from the statically indexed accumulator.  Many rows at once (the first query block of a
+                                    // pair: no bounds yet): elect one winner per column in the warp first.
+                                    u64* ckp = ck1 + col0;
+                                    uint32_t* thp = tauc + col0;
     #pragma unroll
                                     for (int cq = 0; cq < 4; ++cq) {
-                                        if (__any_sync(0xffffffffu, cf[cq])) {
+                                        const uint32_t hm = __ballot_sync(0xffffffffu, cf[cq] && cflag);
+                                        if (hm == 0) continue;
+                                        if (__popc(hm) <= 4) {
+    #pragma unroll
+                                            for (int j = 0; j < 8; ++j) {
+                                                const float x = v[8 * cq + j];
+                                                if (x >= th[8 * cq + j]) {
+                                                    const uint32_t bits = __float_as_uint(fmaxf(-x, 0.f));
+                                                    atomicMin(ckp + 8 * cq + j, make_key(bits, qrow));
+                                                    atomicMin(thp + 8 * cq + j, bits);
+                                                }
+                                            }
+                                        } else {
                                             // which of the chain's 8 columns have a hit in some lane (warp-uniform mask), then ONE shared
                                             // event body in a loop: 32 unrolled copies of it were 19 KB of rarely executed code
-                                            const float* thp = reinterpret_cast<const float*>(tp) + 8 * cq;
                                             uint32_t pend = 0;
     #pragma unroll
                                             for (int j = 0; j < 8; ++j)
-                                                if (__any_sync(0xffffffffu, v[8 * cq + j] >= -thp[j])) pend |= 1u << j;
+                                                if (__any_sync(0xffffffffu, v[8 * cq + j] >= th[8 * cq + j])) pend |= 1u << j;
     #pragma unroll 1
                                             while (pend) {
                                                 const int j = __ffs(pend) - 1;
@@ -602,14 +661,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                                                 const float a2 = s0 ? v[8 * cq + 5] : v[8 * cq + 4], a3 = s0 ? v[8 * cq + 7] : v[8 * cq + 6];
                                                 const float b0 = s1 ? a1 : a0, b1 = s1 ? a3 : a2;
                                                 const float x = s2 ? b1 : b0;
-                                                const bool hit = x >= -thp[j];
+                                                const float t0 = s0 ? th[8 * cq + 1] : th[8 * cq], t1 = s0 ? th[8 * cq + 3] : th[8 * cq + 2];
+                                                const float t2 = s0 ? th[8 * cq + 5] : th[8 * cq + 4], t3 = s0 ? th[8 * cq + 7] : th[8 * cq + 6];
+                                                const float u0 = s1 ? t1 : t0, u1 = s1 ? t3 : t2;
+                                                const bool hit = x >= (s2 ? u1 : u0);
                                                 const uint32_t bits = hit ? __float_as_uint(fmaxf(-x, 0.f)) : 0xffffffffu;
                                                 const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
                                                 const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
                                                 if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
-                                                    const uint32_t gcol = col0 + 8 * cq + j;
-                                                    atomicMin(ck1 + gcol, make_key(mn, qrow));
-                                                    atomicMin(tauc + gcol, mn);
+                                                    atomicMin(ckp + 8 * cq + j, make_key(mn, qrow));
+                                                    atomicMin(thp + 8 * cq + j, mn);
                                                 }
                                             }
                                         }

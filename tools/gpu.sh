@@ -62,7 +62,7 @@ fulljob)
   done ;;
 sanitizer)
   for tool in memcheck racecheck; do
-    timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/sanitizer_$tool.log 2>&1
+    timeout ${SAN_TIMEOUT:-240} compute-sanitizer --tool $tool --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/sanitizer_$tool.log 2>&1
     echo "compute-sanitizer $tool exit $?"; tail -4 gpurun_out/sanitizer_$tool.log | cut -c1-200
   done ;;
 *)
