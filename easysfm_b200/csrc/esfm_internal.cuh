@@ -66,7 +66,7 @@ struct SweepParams {
     int tc_qtiles;              // TC sweep geometry: query tiles per block, 1 or 2 ($ESFM_TC_QT, $ESFM_TC_QT_ORB)
     int need_cols;              // 0: cross_check is off, nobody reads the column minima -- the tensor-core sweeps skip the column side
     int debug_flags;            // TC sweep pipeline probes ($ESFM_TC_DEBUG; results are WRONG when set): 1 = epilogue only drains,
-                                // 2 = no MMAs issued, 4 = no train-tile loads, 8 = no column events, 16 = no row selection
+                                // 2 = no MMAs issued, 4 = no train-tile loads, 8 = no column events, 16 = no row selection, 32 = column events without their atomics, 64 = column events found but not handled
 };
 
 struct FinalizeParams {
@@ -120,6 +120,14 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Arrive WITHOUT release semantics.  A releasing arrive first waits until the thread's earlier memory operations have been
+// performed -- including fire-and-forget global atomics (RED) on their way to L2, a round trip of a thousand cycles under load.
+// The tensor-core epilogue posts column minima with such atomics and then frees pipeline stages whose contents it has ALREADY
+// consumed (tcgen05.wait::ld has returned / the loaded thresholds have been compared): nothing the consumer of the barrier reads
+// depends on those atomics, so the arrive needs no ordering with them.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");

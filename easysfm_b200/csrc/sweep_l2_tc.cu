@@ -139,6 +139,68 @@ constexpr int kTcSleepProducer = 40;
 constexpr int kTcSleepIssuer = 40;
 constexpr int kTcSleepEpilogue = 0;
 
+constexpr int kTcScCols = 4;                                   // columns staged per column-event round (a group of 4 accumulator columns)
+constexpr int kTcScBytes = kTcEpiWarps * kTcScCols * 32 * 4;   // 8 KB: per epilogue warp [4 columns][32 lanes] floats
+
+// Column events of one group of 4 train columns, for the whole warp: ONE compact body, never inlined.  The selection epilogue
+// holds a query row's 32 accumulators in registers, which can only be indexed statically -- so every earlier event handler was
+// either unrolled per column (19 KB of rarely executed code: instruction-cache misses showed up as 15 % "no instruction" stalls)
+// or dug the value out of the registers with select trees and elected a winner per column in a serial loop (~70 instructions
+// and ~300 cycles of dependent latency PER EVENT; the first query block of a pair, where every column gets its first minimum,
+// ran 10x slower than the others and held 60 % of all events).  Here the caller parks the group's 4 x 32 candidate keys in a
+// per-warp shared-memory scratch (4 STS) and the warp reduces all four columns AT ONCE: 8 lanes per column, each takes 4 rows
+// (one LDS.128), then three xor-shuffle rounds of (key, row) pairs -- lowest key, lowest query row on ties -- and the 4 leader
+// lanes post their column's winner with two fire-and-forget atomics (packed key; threshold) if it beats the threshold.
+// ~45 instructions per group whatever the number of events in it.
+// Keys are "smaller = nearer" non-negative floats: the Z key itself, else max(1/2 d^2, 0) (or 2 x hamming).
+// Scratch and thresholds are 32-bit shared-window addresses (generic pointers cost a dozen 64-bit instructions per call).
+// One column's event posted by the lane itself, branch-free: if (ok && y <= t) { RED.MIN.64 ck[j] <- (y bits, qrow); RED.MIN.32
+// tau[j] <- bits(y - thr_sub) }.  Inline PTX because the compiler turns the C++ form into a branch per column (BSSY / BRA /
+// BSYNC + re-derived addresses: ~25 instructions and one more serialised decision point each); here it is 6 predicated
+// instructions with the column offset as an immediate.
+template <int J>
+__device__ __forceinline__ void tc_col_post(float y, float t, int ok, u64* ck, uint32_t* tau, uint32_t qrow, float thr_sub) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 k;\n\t.reg .f32 s;\n\t.reg .b32 yb, sb;\n\t"
+        "setp.ne.s32 q, %2, 0;\n\t"
+        "setp.le.and.f32 p, %0, %1, q;\n\t"
+        "mov.b32 yb, %0;\n\t"
+        "mov.b64 k, {%5, yb};\n\t"
+        "sub.f32 s, %0, %6;\n\t"
+        "mov.b32 sb, s;\n\t"
+        "@p red.global.min.u64 [%3 + %7], k;\n\t"
+        "@p red.global.min.u32 [%4 + %8], sb;\n\t}"
+        ::"f"(y), "f"(t), "r"(ok), "l"(ck), "l"(tau), "r"(qrow), "f"(thr_sub), "n"(J * 8), "n"(J * 4)
+        : "memory");
+}
+
+template <bool kZ>
+__device__ __noinline__ void tc_col_group(uint32_t sc_addr, uint32_t thr_addr, u64* ck, uint32_t* tau, uint32_t qrow0, float thr_sub, int dbg) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t col = lane >> 3, r4 = (lane & 7u) * 4u;
+    float y0, y1, y2, y3, t;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y0), "=f"(y1), "=f"(y2), "=f"(y3) : "r"(sc_addr + col * 128u + r4 * 4u));
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(thr_addr + col * 4u));
+    float best = y0;
+    uint32_t br = r4;
+    if (y1 < best) { best = y1; br = r4 + 1; }
+    if (y2 < best) { best = y2; br = r4 + 2; }
+    if (y3 < best) { best = y3; br = r4 + 3; }
+#pragma unroll
+    for (int d = 1; d <= 4; d <<= 1) {
+        const float oy = __shfl_xor_sync(0xffffffffu, best, d);
+        const uint32_t orow = __shfl_xor_sync(0xffffffffu, br, d);
+        const bool take = oy < best || (oy == best && orow < br);
+        best = take ? oy : best;
+        br = take ? orow : br;
+    }
+    if ((lane & 7u) == 0 && best <= t && !(dbg & 32)) {
+        const uint32_t bits = __float_as_uint(best);
+        atomicMin(ck + col, make_key(bits, qrow0 + br));
+        atomicMin(tau + col, kZ ? __float_as_uint(best - thr_sub) : bits);
+    }
+}
+
 }  // namespace
 
 template <int kTcQTiles, int KIND>
@@ -162,7 +224,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
     unsigned char* Thr = Qa + kTcQTiles * kTcAugBytes;          // kTcThrStages x 128 column thresholds
     u64* mkey = reinterpret_cast<u64*>(Thr + kTcThrStages * kTcThrBytes);          // [tile h][best, second][128] merged row keys
     uint32_t* sbound = reinterpret_cast<uint32_t*>(mkey + kTcQTiles * 2 * kTile);  // [tile h][128] row bound shared by a row's parts
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sbound + kTcQTiles * kTile);
+    float* colsc = reinterpret_cast<float*>(sbound + kTcQTiles * kTile);          // [epilogue warp][4 columns][32 lanes] column-event scratch
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(colsc) + kTcScBytes);
     uint64_t* fullQ = bars;                      // [kTcQTiles]
     uint64_t* fullT = fullQ + kTcQTiles;
     uint64_t* emptyT = fullT + kTcStages;
@@ -455,7 +518,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                         tmem_ld_wait();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&accEmpty[as]);
+                        if (lane == 0) mbar_arrive_relaxed(&accEmpty[as]);
                         if (!(p.debug_flags & 1)) {
                             const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols);
                             if (tt == u.ntt - 1) {       // only the last tile of a frame has pad rows (all-zero operands: z = 0)
@@ -480,75 +543,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                             }
                             // ---- columns: 4 chains of 8 threshold tests, one vote ----
                             if (p.need_cols) {
-                            float th[32];
-    #pragma unroll
-                            for (int c4 = 0; c4 < 8; ++c4) {
-                                const float4 x = tp[c4];
-                                th[4 * c4] = x.x; th[4 * c4 + 1] = x.y; th[4 * c4 + 2] = x.z; th[4 * c4 + 3] = x.w;
-                            }
                             bool cf[4];
     #pragma unroll
                             for (int cq = 0; cq < 4; ++cq) {
-                                bool f = false;
-    #pragma unroll
-                                for (int j = 0; j < 8; ++j) f |= v[8 * cq + j] <= th[8 * cq + j];
-                                cf[cq] = qvalid & f;
+                                const float4 x0 = tp[2 * cq], x1 = tp[2 * cq + 1];
+                                cf[cq] = qvalid & ((v[8 * cq] <= x0.x) | (v[8 * cq + 1] <= x0.y) | (v[8 * cq + 2] <= x0.z) | (v[8 * cq + 3] <= x0.w) |
+                                                   (v[8 * cq + 4] <= x1.x) | (v[8 * cq + 5] <= x1.y) | (v[8 * cq + 6] <= x1.z) | (v[8 * cq + 7] <= x1.w));
                             }
                             if (!(p.debug_flags & 8) && __any_sync(0xffffffffu, cf[0] | cf[1] | cf[2] | cf[3])) {
-                                // Column events (~1-2 per pass).  Normally the lanes that beat a threshold post their keys themselves:
-                                // per column one predicated fire-and-forget RED.MIN.64 on the packed (key, query row) + one RED.MIN.32 on
-                                // the threshold, straight from the statically indexed accumulator (the warp-wide winner election this
-                                // replaces cost ~70 instructions per event plus ~40 per chain: 35 % of the kernel's instructions).  When
-                                // MANY rows beat a chain's thresholds at once (the first query block of a pair: no bounds yet) the
-                                // election stays, or the L2 would see a thousand atomics per pass.
-                                u64* ckp = ck1 + col0;
-                                uint32_t* thp = tauc + col0;
+                                // Column events: ~0.7 per pass, plus 32 per pass in the first query block of a pair (every column gets its
+                                // first minimum there: 60 % of all events).  Per group of 4 columns with a hit: park the group in the
+                                // warp's scratch, then ONE segmented warp reduction over its four columns (tc_col_group).
+                                const uint32_t sc_addr = smem_u32(colsc) + (uint32_t)warp * (kTcScCols * 32 * 4);
+                                const uint32_t thr_addr = smem_u32(tp);
+                                u64* ckb = ck1 + col0;
+                                uint32_t* taub = tauc + col0;
+                                asm volatile("" : "+l"(ckb), "+l"(taub));          // computed once per pass, not once per group
+                                const uint32_t qrow0 = (uint32_t)(qt * kTile + quarter * 32);
     #pragma unroll
                                 for (int cq = 0; cq < 4; ++cq) {
                                     const uint32_t hm = __ballot_sync(0xffffffffu, cf[cq]);
                                     if (hm == 0) continue;
                                     if (__popc(hm) <= 4) {
+                                        // few rows beat this chain's thresholds (the steady state): each posts its own keys, straight-line
+                                        const float4 x0 = tp[2 * cq], x1 = tp[2 * cq + 1];
+                                        u64* ckc = ckb + 8 * cq;
+                                        uint32_t* tac = taub + 8 * cq;
+                                        tc_col_post<0>(v[8 * cq], x0.x, qvalid, ckc, tac, qrow, thr_sub);
+                                        tc_col_post<1>(v[8 * cq + 1], x0.y, qvalid, ckc, tac, qrow, thr_sub);
+                                        tc_col_post<2>(v[8 * cq + 2], x0.z, qvalid, ckc, tac, qrow, thr_sub);
+                                        tc_col_post<3>(v[8 * cq + 3], x0.w, qvalid, ckc, tac, qrow, thr_sub);
+                                        tc_col_post<4>(v[8 * cq + 4], x1.x, qvalid, ckc, tac, qrow, thr_sub);
+                                        tc_col_post<5>(v[8 * cq + 5], x1.y, qvalid, ckc, tac, qrow, thr_sub);
+                                        tc_col_post<6>(v[8 * cq + 6], x1.z, qvalid, ckc, tac, qrow, thr_sub);
+                                        tc_col_post<7>(v[8 * cq + 7], x1.w, qvalid, ckc, tac, qrow, thr_sub);
+                                        continue;
+                                    }
+                                    // many rows at once (the first query block of a pair: no bounds yet): one winner per column and warp
     #pragma unroll
-                                        for (int j = 0; j < 8; ++j) {
-                                            const float x = v[8 * cq + j];
-                                            if (qvalid && x <= th[8 * cq + j]) {
-                                                atomicMin(ckp + 8 * cq + j, make_key(__float_as_uint(x), qrow));
-                                                atomicMin(thp + 8 * cq + j, __float_as_uint(x - thr_sub));
-                                            }
-                                        }
-                                    } else {
-                                        uint32_t pend = 0;
+                                    for (int g2 = 0; g2 < 2; ++g2) {
+                                        const int gq = 2 * cq + g2;
     #pragma unroll
-                                        for (int j = 0; j < 8; ++j)
-                                            if (__any_sync(0xffffffffu, qvalid && v[8 * cq + j] <= th[8 * cq + j])) pend |= 1u << j;
-    #pragma unroll 1
-                                        while (pend) {
-                                            const int j = __ffs(pend) - 1;
-                                            pend &= pend - 1;
-                                            const bool s0 = j & 1, s1 = j & 2, s2 = j & 4;
-                                            const float a0 = s0 ? v[8 * cq + 1] : v[8 * cq], a1 = s0 ? v[8 * cq + 3] : v[8 * cq + 2];
-                                            const float a2 = s0 ? v[8 * cq + 5] : v[8 * cq + 4], a3 = s0 ? v[8 * cq + 7] : v[8 * cq + 6];
-                                            const float b0 = s1 ? a1 : a0, b1 = s1 ? a3 : a2;
-                                            const float x = s2 ? b1 : b0;
-                                            const float t0 = s0 ? th[8 * cq + 1] : th[8 * cq], t1 = s0 ? th[8 * cq + 3] : th[8 * cq + 2];
-                                            const float t2 = s0 ? th[8 * cq + 5] : th[8 * cq + 4], t3 = s0 ? th[8 * cq + 7] : th[8 * cq + 6];
-                                            const float u0 = s1 ? t1 : t0, u1 = s1 ? t3 : t2;
-                                            const bool hit = qvalid && x <= (s2 ? u1 : u0);
-                                            const uint32_t bits = hit ? __float_as_uint(x) : 0xffffffffu;
-                                            const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
-                                            const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
-                                            if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
-                                                atomicMin(ckp + 8 * cq + j, make_key(mn, qrow));
-                                                atomicMin(thp + 8 * cq + j, __float_as_uint(__uint_as_float(mn) - thr_sub));
-                                            }
-                                        }
+                                        for (int e = 0; e < 4; ++e)     // pad query rows (z = Z0 + 2^22 + column) must never win a column
+                                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sc_addr + (uint32_t)(e * 128) + (uint32_t)lane * 4u), "f"(qvalid ? v[4 * gq + e] : kTcZNone) : "memory");
+                                        __syncwarp();
+                                        if (!(p.debug_flags & 64)) tc_col_group<true>(sc_addr, thr_addr + 16u * gq, ckb + 4 * gq, taub + 4 * gq, qrow0, thr_sub, p.debug_flags);
+                                        __syncwarp();
                                     }
                                 }
                             }
                             }
                         }
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&thrEmpty[ts]);      // last read of this threshold snapshot
+                        if (lane == 0) mbar_arrive_relaxed(&thrEmpty[ts]);      // last read of this threshold snapshot
                     }
                     // merge the four column parts of the row: two smallest keys of (up to) eight; the column comes out of the key
     #pragma unroll
@@ -588,7 +635,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                             tmem_ld_wait();
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&accEmpty[as]);
+                            if (lane == 0) mbar_arrive_relaxed(&accEmpty[as]);
                             if (p.debug_flags & 1) continue;
                             float v[32];
     #pragma unroll
@@ -602,20 +649,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                             const bool rflag = rmax >= nb && !(p.debug_flags & 16);
                             // (A pre-test on one threshold per group of 4 columns -- 8 compares and 2 loads instead of 32 and 8 -- was
                             // tried and lost 15 %: the loosest of four thresholds lets far too many rows through to the slow path.)
-                            float th[32];          // negated thresholds: a column event is v >= th
                             bool cf[4] = {false, false, false, false};
                             if (p.need_cols) {
     #pragma unroll
-                                for (int c4 = 0; c4 < 8; ++c4) {
-                                    const float4 x = tp[c4];
-                                    th[4 * c4] = -x.x; th[4 * c4 + 1] = -x.y; th[4 * c4 + 2] = -x.z; th[4 * c4 + 3] = -x.w;
-                                }
-    #pragma unroll
                                 for (int cq = 0; cq < 4; ++cq) {
-                                    bool f = false;
-    #pragma unroll
-                                    for (int j = 0; j < 8; ++j) f |= v[8 * cq + j] >= th[8 * cq + j];
-                                    cf[cq] = f;
+                                    const float4 x0 = tp[2 * cq], x1 = tp[2 * cq + 1];
+                                    cf[cq] = (v[8 * cq] >= -x0.x) | (v[8 * cq + 1] >= -x0.y) | (v[8 * cq + 2] >= -x0.z) | (v[8 * cq + 3] >= -x0.w) |
+                                             (v[8 * cq + 4] >= -x1.x) | (v[8 * cq + 5] >= -x1.y) | (v[8 * cq + 6] >= -x1.z) | (v[8 * cq + 7] >= -x1.w);
                                 }
                             }
                             const bool cflag = (cf[0] | cf[1] | cf[2] | cf[3]) && !(p.debug_flags & 8);
@@ -624,55 +664,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                                 const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols);
                                 // columns first (the row insertion below retires elements of v[])
                                 if (__any_sync(0xffffffffu, cflag)) {
-                                    // Few rows beat a chain's thresholds (the normal case): every such lane posts its own key -- one
-                                    // predicated fire-and-forget RED.MIN.64 on (1/2 d^2 bits, query row) + one RED.MIN.32 on the threshold
-                                    // per column, from the statically indexed accumulator.  Many rows at once (the first query block of a
-                                    // pair: no bounds yet): elect one winner per column in the warp first.
-                                    u64* ckp = ck1 + col0;
-                                    uint32_t* thp = tauc + col0;
+                                    // per group of 4 columns with a hit: park the group in the warp's scratch, then the compact shared
+                                    // segmented warp reduction (tc_col_group; ~0.5 events per pass + 32 per pass in the first query block of a pair)
+                                    const uint32_t sc_addr = smem_u32(colsc) + (uint32_t)warp * (kTcScCols * 32 * 4);
+                                    const uint32_t thr_addr = smem_u32(tp);
+                                    u64* ckb = ck1 + col0;
+                                    uint32_t* taub = tauc + col0;
+                                    asm volatile("" : "+l"(ckb), "+l"(taub));      // computed once per pass, not once per group
+                                    const uint32_t qrow0 = qrow - (uint32_t)lane;
     #pragma unroll
                                     for (int cq = 0; cq < 4; ++cq) {
                                         const uint32_t hm = __ballot_sync(0xffffffffu, cf[cq] && cflag);
                                         if (hm == 0) continue;
                                         if (__popc(hm) <= 4) {
+                                            // few rows beat this chain's thresholds (the steady state): each posts its own keys, straight-line
+                                            const float4 x0 = tp[2 * cq], x1 = tp[2 * cq + 1];
+                                            u64* ckc = ckb + 8 * cq;
+                                            uint32_t* tac = taub + 8 * cq;
+                                            tc_col_post<0>(fmaxf(-v[8 * cq], 0.f), x0.x, 1, ckc, tac, qrow, 0.f);
+                                            tc_col_post<1>(fmaxf(-v[8 * cq + 1], 0.f), x0.y, 1, ckc, tac, qrow, 0.f);
+                                            tc_col_post<2>(fmaxf(-v[8 * cq + 2], 0.f), x0.z, 1, ckc, tac, qrow, 0.f);
+                                            tc_col_post<3>(fmaxf(-v[8 * cq + 3], 0.f), x0.w, 1, ckc, tac, qrow, 0.f);
+                                            tc_col_post<4>(fmaxf(-v[8 * cq + 4], 0.f), x1.x, 1, ckc, tac, qrow, 0.f);
+                                            tc_col_post<5>(fmaxf(-v[8 * cq + 5], 0.f), x1.y, 1, ckc, tac, qrow, 0.f);
+                                            tc_col_post<6>(fmaxf(-v[8 * cq + 6], 0.f), x1.z, 1, ckc, tac, qrow, 0.f);
+                                            tc_col_post<7>(fmaxf(-v[8 * cq + 7], 0.f), x1.w, 1, ckc, tac, qrow, 0.f);
+                                            continue;
+                                        }
+                                        // many rows at once (the first query block of a pair: no bounds yet): one winner per column and warp
     #pragma unroll
-                                            for (int j = 0; j < 8; ++j) {
-                                                const float x = v[8 * cq + j];
-                                                if (x >= th[8 * cq + j]) {
-                                                    const uint32_t bits = __float_as_uint(fmaxf(-x, 0.f));
-                                                    atomicMin(ckp + 8 * cq + j, make_key(bits, qrow));
-                                                    atomicMin(thp + 8 * cq + j, bits);
-                                                }
-                                            }
-                                        } else {
-                                            // which of the chain's 8 columns have a hit in some lane (warp-uniform mask), then ONE shared
-                                            // event body in a loop: 32 unrolled copies of it were 19 KB of rarely executed code
-                                            uint32_t pend = 0;
+                                        for (int g2 = 0; g2 < 2; ++g2) {
+                                            const int gq = 2 * cq + g2;
     #pragma unroll
-                                            for (int j = 0; j < 8; ++j)
-                                                if (__any_sync(0xffffffffu, v[8 * cq + j] >= th[8 * cq + j])) pend |= 1u << j;
-    #pragma unroll 1
-                                            while (pend) {
-                                                const int j = __ffs(pend) - 1;
-                                                pend &= pend - 1;
-                                                // v[8 cq + j] for a warp-uniform j: three levels of selects
-                                                const bool s0 = j & 1, s1 = j & 2, s2 = j & 4;
-                                                const float a0 = s0 ? v[8 * cq + 1] : v[8 * cq], a1 = s0 ? v[8 * cq + 3] : v[8 * cq + 2];
-                                                const float a2 = s0 ? v[8 * cq + 5] : v[8 * cq + 4], a3 = s0 ? v[8 * cq + 7] : v[8 * cq + 6];
-                                                const float b0 = s1 ? a1 : a0, b1 = s1 ? a3 : a2;
-                                                const float x = s2 ? b1 : b0;
-                                                const float t0 = s0 ? th[8 * cq + 1] : th[8 * cq], t1 = s0 ? th[8 * cq + 3] : th[8 * cq + 2];
-                                                const float t2 = s0 ? th[8 * cq + 5] : th[8 * cq + 4], t3 = s0 ? th[8 * cq + 7] : th[8 * cq + 6];
-                                                const float u0 = s1 ? t1 : t0, u1 = s1 ? t3 : t2;
-                                                const bool hit = x >= (s2 ? u1 : u0);
-                                                const uint32_t bits = hit ? __float_as_uint(fmaxf(-x, 0.f)) : 0xffffffffu;
-                                                const uint32_t mn = __reduce_min_sync(0xffffffffu, bits);
-                                                const uint32_t win = __ballot_sync(0xffffffffu, bits == mn);
-                                                if (lane == __ffs(win) - 1) {     // lowest lane = lowest query row among equals
-                                                    atomicMin(ckp + 8 * cq + j, make_key(mn, qrow));
-                                                    atomicMin(thp + 8 * cq + j, mn);
-                                                }
-                                            }
+                                            for (int e = 0; e < 4; ++e)     // keys: 1/2 d^2 clamped at 0 (pad query rows: 1e30, never a winner)
+                                                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sc_addr + (uint32_t)(e * 128) + (uint32_t)lane * 4u), "f"(fmaxf(-v[4 * gq + e], 0.f)) : "memory");
+                                            __syncwarp();
+                                            if (!(p.debug_flags & 64)) tc_col_group<false>(sc_addr, thr_addr + 16u * gq, ckb + 4 * gq, taub + 4 * gq, qrow0, 0.f, p.debug_flags);
+                                            __syncwarp();
                                         }
                                     }
                                 }
@@ -711,7 +739,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_l2_tc_kernel(const SweepP
                             }
                         }
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&thrEmpty[ts]);      // last read of this threshold snapshot
+                        if (lane == 0) mbar_arrive_relaxed(&thrEmpty[ts]);      // last read of this threshold snapshot
                     }
                     // ---- end of the sweep for this query block: merge the column parts of every row, publish ----
                     // 64-bit shared-memory atomics on packed keys: the smallest key ends in mkey[.][0], the smallest of all the
@@ -757,7 +785,7 @@ size_t sweep_tc_smem_bytes(int qt, int kind) {
     const size_t tile = tc_kind_is_f32(kind) ? (size_t)kTcTileBytes : (size_t)kTc8TileBytes;
     const int acc = (512 - qt * (tc_kind_is_f32(kind) ? 128 : 64)) / 128;
     return 1024 + (size_t)kTcStages * tile + (size_t)qt * kTcAugBytes + (size_t)kTcThrStages * kTcThrBytes +
-           (size_t)qt * 2 * kTile * sizeof(u64) + (size_t)qt * kTile * 4 +
+           (size_t)qt * 2 * kTile * sizeof(u64) + (size_t)qt * kTile * 4 + (size_t)kTcScBytes +
            (qt + 2 * kTcStages + 2 * acc + 2 * kTcThrStages) * 8 + 16;
 }
 
@@ -767,12 +795,12 @@ cudaError_t launch_sweep_l2_tc(const SweepParams& p, int sm_count, cudaStream_t 
     if (n_units <= 0) return cudaSuccess;
     const int grid = n_units < sm_count ? n_units : sm_count;
     const int kind = p.tc_kind == kTcKindB256Z ? p.tc_kind : (p.tc_kind == ESFM_KIND_B256 ? ESFM_KIND_B256 : ESFM_KIND_F32X64);
-    const int qt = (p.tc_qtiles == 2 && kind != kTcKindB256Z) ? 2 : 1;
+    const int qt = 1;      // (two query tiles per block, $ESFM_TC_QT=2 in round 1: measured slower, and its shared memory has no room
+                           //  for the column-event scratch; the template parameter stays, the instantiations are gone)
     const size_t smem = sweep_tc_smem_bytes(qt, kind);
     void (*kern)(const SweepParams) =
         kind == kTcKindB256Z ? sweep_l2_tc_kernel<1, kTcKindB256Z>
-        : kind == ESFM_KIND_B256 ? (qt == 2 ? sweep_l2_tc_kernel<2, ESFM_KIND_B256> : sweep_l2_tc_kernel<1, ESFM_KIND_B256>)
-                               : (qt == 2 ? sweep_l2_tc_kernel<2, ESFM_KIND_F32X64> : sweep_l2_tc_kernel<1, ESFM_KIND_F32X64>);
+        : kind == ESFM_KIND_B256 ? sweep_l2_tc_kernel<1, ESFM_KIND_B256> : sweep_l2_tc_kernel<1, ESFM_KIND_F32X64>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kTcThreads, smem, s>>>(p);
