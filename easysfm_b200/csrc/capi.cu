@@ -257,8 +257,6 @@ extern "C" int esfm_init(int device, void* cuda_stream, esfm_ctx_t** out) {
     if (!ctx) return fail(ESFM_ERR_NOMEM, "esfm_init: out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char* qt = getenv("ESFM_TC_QT")) ctx->tc_qtiles = atoi(qt) == 2 ? 2 : 1;
-    if (const char* qt = getenv("ESFM_TC_QT_ORB")) ctx->tc_qtiles_orb = atoi(qt) == 2 ? 2 : 1;
     if (const char* z = getenv("ESFM_ORB_Z")) ctx->orb_z = atoi(z) != 0;
     if (const char* eng = getenv("ESFM_HAMMING_ENGINE")) {
         if (!strcmp(eng, "tc") || !strcmp(eng, "tensor")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_TC;
@@ -860,7 +858,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, ChunkBuf& cb, si
     sp.col_cap = pl.col_cap;
     sp.need_cols = (cross_check || knn_idx) ? 1 : 0;
     if (const char* dbg = getenv("ESFM_TC_DEBUG")) sp.debug_flags = atoi(dbg);
-    sp.tc_qtiles = b->kind == ESFM_KIND_B256 ? ctx->tc_qtiles_orb : ctx->tc_qtiles;
+    sp.tc_qtiles = 1;
     sp.tc_kind = zmode ? kTcKindB256Z : b->kind;
     if (ctx->profiling) CUDA_TRY(cudaEventRecord(cb.ev_t0, ctx->stream));
     cudaError_t e = tc ? launch_sweep_l2_tc(sp, ctx->sm_count, ctx->stream)

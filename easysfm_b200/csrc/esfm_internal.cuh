@@ -63,7 +63,7 @@ struct SweepParams {
     int col_cap;                // Hamming sweep: smem column-minimum capacity in entries
     int tc_kind;                // TC sweep: ESFM_KIND_F32X64 (3xTF32 L2), ESFM_KIND_B256 (FP8 Hamming) or kTcKindB256Z (FP8 Hamming, packed
                                 // (distance, column) keys from the MMA); tc_main holds that kind's images
-    int tc_qtiles;              // TC sweep geometry: query tiles per block, 1 or 2 ($ESFM_TC_QT, $ESFM_TC_QT_ORB)
+    int tc_qtiles;              // TC sweep geometry: query tiles per block (always 1: the two-tile variant of round 1 is no longer built)
     int need_cols;              // 0: cross_check is off, nobody reads the column minima -- the tensor-core sweeps skip the column side
     int debug_flags;            // TC sweep pipeline probes ($ESFM_TC_DEBUG; results are WRONG when set): 1 = epilogue only drains,
                                 // 2 = no MMAs issued, 4 = no train-tile loads, 8 = no column events, 16 = no row selection, 32 = column events without their atomics, 64 = column events found but not handled

@@ -74,8 +74,6 @@ struct esfm_ctx {
     cudaMemPool_t mempool = nullptr;       // private stream-ordered pool for banks: freed blocks stay cached, and die with the ctx
     int sm_count = 0;
     bool profiling = true;
-    int tc_qtiles = 1;                     // TC sweep geometry, SURF: query tiles per block (1 or 2; $ESFM_TC_QT)
-    int tc_qtiles_orb = 1;                 // TC sweep geometry, ORB (1 or 2; $ESFM_TC_QT_ORB): 3 accumulator stages either way
     int orb_z = 1;                         // ORB tensor-core sweep with the "Z" operand encoding (packed keys from the MMA): default;
                                            // $ESFM_ORB_Z=0 selects the +-1 encoding with the generic epilogue
     int hamming_engine = ESFM_HAMMING_ENGINE_TC;
