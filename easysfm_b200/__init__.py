@@ -23,6 +23,7 @@ from .capi import (  # noqa: F401
     MultiBank,
     MultiContext,
     Results,
+    Tracks,
     library_path,
     load_library,
     load_results,

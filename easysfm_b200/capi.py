@@ -120,6 +120,17 @@ SIGNATURES = {
     "esfm_results_pair_layout": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int64)]),
     "esfm_results_device_matches": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64)]),
     "esfm_results_device_layout": (c_int, [c_void_p, POINTER(c_int64)]),
+    "esfm_tracks_create": (c_int, [c_int, POINTER(c_int32), POINTER(c_void_p)]),
+    "esfm_tracks_destroy": (c_int, [c_void_p]),
+    "esfm_tracks_add_pair": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int]),
+    "esfm_tracks_finish_frame": (c_int, [c_void_p, c_int]),
+    "esfm_tracks_build": (c_int, [c_void_p, c_void_p, c_int]),
+    "esfm_tracks_frame": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int)]),
+    "esfm_tracks_counts": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int64)]),
+    "esfm_tracks_pair_scores": (c_int, [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_double)]),
+    "esfm_tracks_find_init_pair": (c_int, [c_void_p, c_void_p, POINTER(c_double), c_int, c_double, POINTER(c_int), POINTER(c_int),
+                                           POINTER(c_double), POINTER(c_int64), POINTER(c_int)]),
+    "esfm_tracks_find_next_frame": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_uint8), POINTER(c_int32), c_int64, POINTER(c_int), POINTER(c_int)]),
     "esfm_multi_init": (c_int, [c_int, POINTER(c_int), POINTER(c_void_p)]),
     "esfm_multi_destroy": (c_int, [c_void_p]),
     "esfm_multi_device_count": (c_int, [c_void_p, POINTER(c_int)]),
@@ -682,3 +693,81 @@ class MultiBank:
         _check(self._lib.esfm_multi_match_pairs(self._h, p.ctypes.data, p.shape[0], float(ratio), int(bool(cross_check)), int(keep),
                                                 ctypes.byref(h)))
         return Results(self._lib, h, self.multi)
+
+
+class Tracks:
+    """Unique point ids of every keypoint + co-visibility scoring (esfm_tracks_t; reference: sfm.cpp:140-217,
+    feature_matching.cpp:160-268).  Building the tracks is host work and needs no device."""
+
+    def __init__(self, keypoints_per_frame):
+        self._lib = load_library()
+        kp = np.ascontiguousarray(keypoints_per_frame, dtype=np.int32)
+        self.keypoints = kp
+        self.n_frames = len(kp)
+        h = c_void_p()
+        _check(self._lib.esfm_tracks_create(len(kp), kp.ctypes.data_as(POINTER(c_int32)), ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.esfm_tracks_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_pair(self, frame_i: int, frame_j: int, inlier_matches):
+        m = np.ascontiguousarray(inlier_matches, dtype=DMATCH_DTYPE)
+        _check(self._lib.esfm_tracks_add_pair(self._h, int(frame_i), int(frame_j), m.ctypes.data if len(m) else None, len(m)))
+
+    def finish_frame(self, frame_i: int):
+        _check(self._lib.esfm_tracks_finish_frame(self._h, int(frame_i)))
+
+    def build(self, results: "Results", min_pair_matches: int = 20):
+        _check(self._lib.esfm_tracks_build(self._h, results._h, int(min_pair_matches)))
+
+    def frame(self, f: int):
+        """(unique_pixel_ids int32 [n], unique_pixel_has_match uint8 [n]) of frame f (copies)."""
+        pi, ph, n = c_void_p(), c_void_p(), c_int()
+        _check(self._lib.esfm_tracks_frame(self._h, int(f), ctypes.byref(pi), ctypes.byref(ph), ctypes.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, np.int32), np.zeros(0, np.uint8)
+        ids = np.frombuffer((ctypes.c_char * (4 * n.value)).from_address(pi.value), np.int32, n.value).copy()
+        has = np.frombuffer((ctypes.c_char * n.value).from_address(ph.value), np.uint8, n.value).copy()
+        return ids, has
+
+    def counts(self):
+        """(frames finished, unique points so far)."""
+        d, p = c_int(), c_int64()
+        _check(self._lib.esfm_tracks_counts(self._h, ctypes.byref(d), ctypes.byref(p)))
+        return d.value, p.value
+
+    def pair_scores(self, ctx: Context):
+        """Co-visibility score of every pair in loop order (device kernel) -> (int64 [n_pairs], kernel ms)."""
+        n = self.n_frames * (self.n_frames - 1) // 2
+        out = np.zeros(max(n, 1), np.int64)
+        ms = c_double()
+        _check(self._lib.esfm_tracks_pair_scores(ctx._h, self._h, out.ctypes.data_as(POINTER(c_int64)), ctypes.byref(ms)))
+        return out[:n], ms.value
+
+    def find_init_pair(self, ctx: Context, appro_depth=None, min_track_num_init: int = 100, max_depth_baseline_ratio_init: float = 50.0):
+        """findInitializeFramePair -> (found, frame_1, frame_2, depth_init, best_score)."""
+        d = None if appro_depth is None else np.ascontiguousarray(appro_depth, dtype=np.float64)
+        f1, f2, di, best, found = c_int(), c_int(), c_double(), c_int64(), c_int()
+        _check(self._lib.esfm_tracks_find_init_pair(ctx._h, self._h, None if d is None else d.ctypes.data_as(POINTER(c_double)),
+                                                    int(min_track_num_init), float(max_depth_baseline_ratio_init), ctypes.byref(f1),
+                                                    ctypes.byref(f2), ctypes.byref(di), ctypes.byref(best), ctypes.byref(found)))
+        return bool(found.value), f1.value, f2.value, di.value, best.value
+
+    def find_next_frame(self, frames_to_process, point_ids, next_frame: int = -1):
+        """findNextFrame -> (next_frame, common points)."""
+        tp = np.ascontiguousarray(frames_to_process, dtype=np.uint8)
+        pid = np.ascontiguousarray(point_ids, dtype=np.int32)
+        nf, common = c_int(int(next_frame)), c_int()
+        _check(self._lib.esfm_tracks_find_next_frame(self._h, tp.ctypes.data_as(POINTER(ctypes.c_uint8)),
+                                                     pid.ctypes.data_as(POINTER(c_int32)) if len(pid) else None, len(pid),
+                                                     ctypes.byref(nf), ctypes.byref(common)))
+        return nf.value, common.value

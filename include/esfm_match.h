@@ -242,6 +242,42 @@ int esfm_results_frame_rows(esfm_results_t* results, int32_t* rows, int cap, int
  * every match index inside its frames' rows.  Call it after esfm_results_load before trusting the indices. */
 int esfm_results_validate(esfm_results_t* results, int n_frames, const int32_t* rows);
 
+/* ---- track building and co-visibility (what consumes the matches next) ---------------------------------
+ * cpp_code/test/sfm.cpp:140-217: every keypoint gets a unique point id; the inlier matches of pair (i, j) label frame i's
+ * keypoints with frame j's ids unless that id is already used in frame i; unlabelled keypoints get fresh ids after the row.
+ * The labelling is order-dependent, so pairs must be fed in the reference's loop order (i ascending, j < i ascending).
+ * cpp_code/src/feature_matching.cpp:160-233 (findInitializeFramePair) then scores EVERY frame pair by the points both see,
+ * weighted by how many frames see each point -- O(N^2 P) on a dense bool matrix in the reference, one CUDA kernel over sorted
+ * id lists here -- and :235-268 (findNextFrame) picks the frame that sees most of the current 3D points.
+ * Integer work: results are identical to the reference's loops (oracle/tracks_oracle.c, tests/test_tracks.py). */
+typedef struct esfm_tracks esfm_tracks_t;
+int esfm_tracks_create(int n_frames, const int32_t* keypoints_per_frame, esfm_tracks_t** tracks);
+int esfm_tracks_destroy(esfm_tracks_t* tracks);
+/* The inlier matches of pair (frame_i = query, frame_j = train), sfm.cpp:172-194.  frame_i must be the frame in progress. */
+int esfm_tracks_add_pair(esfm_tracks_t* tracks, int frame_i, int frame_j, const esfm_dmatch_t* inlier_matches, int n);
+/* End of frame_i's row: fresh ids for its unlabelled keypoints, its row of the track matrix (sfm.cpp:199-213). */
+int esfm_tracks_finish_frame(esfm_tracks_t* tracks, int frame_i);
+/* The whole loop over a batch holding all pairs in loop order (esfm_match_all_pairs / esfm_multi_match_all_pairs): pairs with
+ * more than min_pair_matches matches (sfm.cpp:163: 20) contribute all their matches -- the reference first thins them with its
+ * 5-point RANSAC (estimate_motion.cpp:27-97), which this library does not replace. */
+int esfm_tracks_build(esfm_tracks_t* tracks, esfm_results_t* results, int min_pair_matches);
+/* frame_t::unique_pixel_ids / unique_pixel_has_match of one frame (library-owned, n = its keypoints). */
+int esfm_tracks_frame(esfm_tracks_t* tracks, int frame, const int32_t** unique_pixel_ids, const uint8_t** unique_pixel_has_match, int* n);
+int esfm_tracks_counts(esfm_tracks_t* tracks, int* frames_done, int64_t* n_unique_points);
+/* Co-visibility score of every pair in loop order (n_frames (n_frames - 1) / 2 values), computed on ctx's device;
+ * kernel_ms (optional) = device time of the scoring kernel. */
+int esfm_tracks_pair_scores(esfm_ctx_t* ctx, esfm_tracks_t* tracks, int64_t* scores, double* kernel_ms);
+/* findInitializeFramePair (defaults of feature_matching.h:26-27: min_track_num_init 100, max_depth_baseline_ratio_init 50.0).
+ * appro_depth = frame_pair_t::appro_depth per pair in loop order, or NULL (1.0).  *found = 0: no pair qualified, the reference's
+ * fallback (1, 0) is returned. */
+int esfm_tracks_find_init_pair(esfm_ctx_t* ctx, esfm_tracks_t* tracks, const double* appro_depth, int min_track_num_init,
+                               double max_depth_baseline_ratio_init, int* frame_1, int* frame_2, double* depth_init,
+                               int64_t* best_score, int* found);
+/* findNextFrame: among frames with frames_to_process[f] != 0 the one that sees most of point_ids (first best wins; *next_frame
+ * is left untouched when none sees any). */
+int esfm_tracks_find_next_frame(esfm_tracks_t* tracks, const uint8_t* frames_to_process, const int32_t* point_ids, int64_t n_ids,
+                                int* next_frame, int* common_points);
+
 /* ---- several GPUs of one box, one host process (caller: the single-threaded pair loop sfm.cpp:140-161) -----
  * esfm_multi_init binds n devices (ids = NULL: devices 0..n-1).  A multi bank is fed like a bank (set_frame x N, or through
  * its primary replica on device 0); esfm_multi_bank_commit uploads it to device 0, replicates the raw descriptors on the other
