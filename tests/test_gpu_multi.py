@@ -171,3 +171,26 @@ def test_bank_frames_set_out_of_order_and_twice(ctx):
     b2.alloc_device()
     with pytest.raises(esfm.EsfmError):
         b2.commit()                        # rows declared without host data: esfm_bank_commit_device is the way
+
+
+def test_hamming_frame_limit_is_a_whole_tile():
+    """The XOR + POPC sweep keeps a frame's column minima in shared memory, sized by the TILE-PADDED row count: the bank must
+    refuse exactly the frames the launch could not take (round-1 advisor: 49,793..49,904 rows were accepted, then failed)."""
+    import easysfm_b200 as esfm
+    from easysfm_b200 import synth
+    with esfm.Context(0) as c:
+        c.set_hamming_engine("popc")
+        lim = None
+        b = c.bank(esfm.KIND_B256, 1)
+        for rows in range(49792, 49920, 16):
+            try:
+                b.set_frame_rows(0, rows)
+                lim = rows
+            except esfm.EsfmError:
+                break
+        assert lim is not None and lim % 128 == 0
+        with pytest.raises(esfm.EsfmError):
+            c.bank(esfm.KIND_B256, 1).set_frame(0, np.zeros((lim + 1, 32), np.uint8))
+        big, small = synth.orb_like(2, [lim, 300], seed=77)
+        got = c.match_descriptors(small, big, 0.8, True)            # train frame at the limit: must launch and be exact
+        assert_matches_equal(got, oracle.match(small, big, 0.8, True))
