@@ -23,8 +23,10 @@ PAIR_DTYPE = np.dtype([("query", "<i4"), ("train", "<i4")])
 
 L2_ENGINE_FFMA = 0
 L2_ENGINE_TC = 1
+L2_ENGINE_TC16 = 2
 HAMMING_ENGINE_POPC = 0
 HAMMING_ENGINE_TC = 1
+HAMMING_ENGINE_TC16 = 2
 KEEP_MATCHES = 0
 KEEP_DIGESTS = 1
 
@@ -248,24 +250,25 @@ class Context:
         return n.value
 
     def set_l2_engine(self, engine):
-        """'ffma' (exact-FP32 FMA pipe) or 'tc' (3xTF32 on the tcgen05 tensor cores) for the SURF / L2 sweep."""
-        code = {"ffma": L2_ENGINE_FFMA, "tc": L2_ENGINE_TC}.get(engine, engine)
+        """'ffma' (exact-FP32 FMA pipe), 'tc' (3xTF32 on the tcgen05 tensor cores) or 'tc16' (two-term FP16 split, slice keys) for the SURF / L2 sweep."""
+        code = {"ffma": L2_ENGINE_FFMA, "tc": L2_ENGINE_TC, "tc16": L2_ENGINE_TC16}.get(engine, engine)
         _check(self._lib.esfm_set_l2_engine(self._h, int(code)))
 
     def l2_engine(self) -> str:
         e = c_int(0)
         _check(self._lib.esfm_get_l2_engine(self._h, ctypes.byref(e)))
-        return {L2_ENGINE_FFMA: "ffma", L2_ENGINE_TC: "tc"}[e.value]
+        return {L2_ENGINE_FFMA: "ffma", L2_ENGINE_TC: "tc", L2_ENGINE_TC16: "tc16"}[e.value]
 
     def set_hamming_engine(self, engine):
-        """'popc' (XOR + POPC on the integer pipes) or 'tc' (exact FP8 +-1 dot product on the tensor cores) for the ORB sweep."""
-        code = {"popc": HAMMING_ENGINE_POPC, "tc": HAMMING_ENGINE_TC}.get(engine, engine)
+        """'popc' (XOR + POPC on the integer pipes), 'tc' (exact FP8 dot product on the tensor cores, packed keys) or 'tc16' (FP8 dot product
+        with FP16 accumulators, packed-half epilogue, slice keys) for the ORB sweep."""
+        code = {"popc": HAMMING_ENGINE_POPC, "tc": HAMMING_ENGINE_TC, "tc16": HAMMING_ENGINE_TC16}.get(engine, engine)
         _check(self._lib.esfm_set_hamming_engine(self._h, int(code)))
 
     def hamming_engine(self) -> str:
         e = c_int(0)
         _check(self._lib.esfm_get_hamming_engine(self._h, ctypes.byref(e)))
-        return {HAMMING_ENGINE_POPC: "popc", HAMMING_ENGINE_TC: "tc"}[e.value]
+        return {HAMMING_ENGINE_POPC: "popc", HAMMING_ENGINE_TC: "tc", HAMMING_ENGINE_TC16: "tc16"}[e.value]
 
     def bank(self, kind: int, n_frames: int) -> "Bank":
         return Bank(self, kind, n_frames)

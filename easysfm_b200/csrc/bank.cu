@@ -111,6 +111,65 @@ cudaError_t launch_pack_tc(const float* rows, const int* frame_rows, const int* 
     return cudaGetLastError();
 }
 
+// F32X64 -> the 16-bit split ("H") images of tc_layout.cuh for sweep_win.cu: per 128-row tile 16 groups x 2048 B = [a k0..63][b k0..63]
+// SWIZZLE_128B atoms of fp16 (a = fp16(x), b = fp16(x - a)) + the same 16 x 256 B augmented TF32 columns as the 3xTF32 image.
+// One block per tile, one thread per (row, 8 dims = one 16-byte chunk of each atom); byte-for-byte tch_pack_row_host.
+__global__ void __launch_bounds__(256) pack_tch_kernel(const float* __restrict__ rows, const int* __restrict__ frame_rows,
+                                                       const int* __restrict__ frame_row_off,
+                                                       const int* __restrict__ frame_tile_off, int n_frames,
+                                                       unsigned char* __restrict__ tc_main) {
+    __shared__ float tile[kTile][kDim + 4];
+    const int t = blockIdx.x;
+    int lo = 0, hi = n_frames - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (frame_tile_off[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const int f = lo;
+    const int row0 = (t - frame_tile_off[f]) * kTile;
+    int valid = frame_rows[f] - row0;
+    valid = valid < 0 ? 0 : (valid > kTile ? kTile : valid);
+    const float4* src = reinterpret_cast<const float4*>(rows + ((size_t)frame_row_off[f] + row0) * kDim);
+    unsigned char* out = tc_main + (size_t)t * kTchTileBytes;
+    for (int idx = threadIdx.x; idx < kTile * (kDim / 8); idx += blockDim.x) {
+        const int r = idx / (kDim / 8), c8 = idx % (kDim / 8);
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (r < valid) { v0 = src[(size_t)r * (kDim / 4) + 2 * c8]; v1 = src[(size_t)r * (kDim / 4) + 2 * c8 + 1]; }
+        *reinterpret_cast<float4*>(&tile[r][c8 * 8]) = v0;
+        *reinterpret_cast<float4*>(&tile[r][c8 * 8 + 4]) = v1;
+        const float xs[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        uint32_t a[8], b[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a[j] = tch_f2h(xs[j]);
+            b[j] = tch_f2h(xs[j] - tch_h2f(a[j]));
+        }
+        const int off = (r >> 3) * kTchGroupBytes + tch_sw128_off(r & 7, c8 * 8);
+        *reinterpret_cast<uint4*>(out + off) = make_uint4(a[0] | (a[1] << 16), a[2] | (a[3] << 16), a[4] | (a[5] << 16), a[6] | (a[7] << 16));
+        *reinterpret_cast<uint4*>(out + off + 1024) = make_uint4(b[0] | (b[1] << 16), b[2] | (b[3] << 16), b[4] | (b[5] << 16), b[6] | (b[7] << 16));
+    }
+    __syncthreads();
+    if (threadIdx.x < kTile) {
+        const int r = threadIdx.x;
+        float s = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < kDim; ++k) s = __fmaf_rn(tile[r][k], tile[r][k], s);
+        const float h = (r < valid) ? 0.5f * s : kTcPadNorm;
+        float hh, hm, hl;
+        tc_split3(h, hh, hm, hl);
+        unsigned char* a = out + kTchMainBytes + (r >> 3) * kTcAugGroupBytes + (r & 7) * 16;
+        *reinterpret_cast<float4*>(a) = make_float4(-hh, -hm, -hl, -1.f);
+        *reinterpret_cast<float4*>(a + 128) = make_float4(-1.f, -1.f, 0.f, 0.f);
+    }
+}
+
+cudaError_t launch_pack_tch(const float* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
+                            int n_frames, int n_tiles_total, unsigned char* tc_main, cudaStream_t s) {
+    if (n_tiles_total <= 0) return cudaSuccess;
+    pack_tch_kernel<<<n_tiles_total, 256, 0, s>>>(rows, frame_rows, frame_row_off, frame_tile_off, n_frames, tc_main);
+    return cudaGetLastError();
+}
+
 // B256 -> the FP8 tile images of tc_layout.cuh (Hamming on the tensor cores): one block per 128-row tile, one thread per
 // (row, 32-bit word): 32 bits -> 32 bytes of +-1.0 (E4M3), written as two 16-byte chunks into the SWIZZLE_128B atoms.
 __global__ void __launch_bounds__(256) pack_tc8_kernel(const uint32_t* __restrict__ rows, const int* __restrict__ frame_rows,

@@ -260,13 +260,15 @@ extern "C" int esfm_init(int device, void* cuda_stream, esfm_ctx_t** out) {
     if (const char* z = getenv("ESFM_ORB_Z")) ctx->orb_z = atoi(z) != 0;
     if (const char* eng = getenv("ESFM_HAMMING_ENGINE")) {
         if (!strcmp(eng, "tc") || !strcmp(eng, "tensor")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_TC;
+        else if (!strcmp(eng, "tc16")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_TC16;
         else if (!strcmp(eng, "popc")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_POPC;
-        else { delete ctx; return fail(ESFM_ERR_INVALID, "ESFM_HAMMING_ENGINE=%s: expected 'popc' or 'tc'", eng); }
+        else { delete ctx; return fail(ESFM_ERR_INVALID, "ESFM_HAMMING_ENGINE=%s: expected 'popc', 'tc' or 'tc16'", eng); }
     }
     if (const char* eng = getenv("ESFM_L2_ENGINE")) {
         if (!strcmp(eng, "tc") || !strcmp(eng, "tensor")) ctx->l2_engine = ESFM_L2_ENGINE_TC;
+        else if (!strcmp(eng, "tc16")) ctx->l2_engine = ESFM_L2_ENGINE_TC16;
         else if (!strcmp(eng, "ffma")) ctx->l2_engine = ESFM_L2_ENGINE_FFMA;
-        else { delete ctx; return fail(ESFM_ERR_INVALID, "ESFM_L2_ENGINE=%s: expected 'ffma' or 'tc'", eng); }
+        else { delete ctx; return fail(ESFM_ERR_INVALID, "ESFM_L2_ENGINE=%s: expected 'ffma', 'tc' or 'tc16'", eng); }
     }
     auto bail = [&](int code, const char* what, cudaError_t err) {
         const int rc = fail(code, "esfm_init: %s failed: %s", what, cudaGetErrorString(err));
@@ -370,14 +372,14 @@ extern "C" int esfm_set_profiling(esfm_ctx_t* ctx, int enabled) {
 
 extern "C" int esfm_set_l2_engine(esfm_ctx_t* ctx, int engine) {
     if (!ctx) return fail(ESFM_ERR_INVALID, "ctx is NULL");
-    if (engine != ESFM_L2_ENGINE_FFMA && engine != ESFM_L2_ENGINE_TC) return fail(ESFM_ERR_INVALID, "unknown L2 engine %d", engine);
+    if (engine != ESFM_L2_ENGINE_FFMA && engine != ESFM_L2_ENGINE_TC && engine != ESFM_L2_ENGINE_TC16) return fail(ESFM_ERR_INVALID, "unknown L2 engine %d", engine);
     ctx->l2_engine = engine;
     return ESFM_OK;
 }
 
 extern "C" int esfm_set_hamming_engine(esfm_ctx_t* ctx, int engine) {
     if (!ctx) return fail(ESFM_ERR_INVALID, "ctx is NULL");
-    if (engine != ESFM_HAMMING_ENGINE_POPC && engine != ESFM_HAMMING_ENGINE_TC) return fail(ESFM_ERR_INVALID, "unknown Hamming engine %d", engine);
+    if (engine != ESFM_HAMMING_ENGINE_POPC && engine != ESFM_HAMMING_ENGINE_TC && engine != ESFM_HAMMING_ENGINE_TC16) return fail(ESFM_ERR_INVALID, "unknown Hamming engine %d", engine);
     ctx->hamming_engine = engine;
     return ESFM_OK;
 }
@@ -727,8 +729,13 @@ struct ChunkPlan {
     size_t chunk_pairs;
 };
 
+// any tensor-core sweep (they share the scratch layout: column thresholds, one query tile per block)
 bool use_tc(const esfm_ctx* ctx, const esfm_bank* b) {
-    return b->kind == ESFM_KIND_F32X64 ? ctx->l2_engine == ESFM_L2_ENGINE_TC : ctx->hamming_engine == ESFM_HAMMING_ENGINE_TC;
+    return b->kind == ESFM_KIND_F32X64 ? ctx->l2_engine != ESFM_L2_ENGINE_FFMA : ctx->hamming_engine != ESFM_HAMMING_ENGINE_POPC;
+}
+// the 16-bit sweeps of sweep_win.cu (row keys carry a slice of columns)
+bool use_win(const esfm_ctx* ctx, const esfm_bank* b) {
+    return b->kind == ESFM_KIND_F32X64 ? ctx->l2_engine == ESFM_L2_ENGINE_TC16 : ctx->hamming_engine == ESFM_HAMMING_ENGINE_TC16;
 }
 
 ChunkPlan plan_chunks(const esfm_bank* b, int64_t n_pairs) {
@@ -795,12 +802,13 @@ int ensure_kmajor_layout(esfm_ctx* ctx, esfm_bank* b) {
     return ESFM_OK;
 }
 
-// Tensor-core engines: the operand images of tc_layout.cuh (3xTF32 hi/lo images for F32X64, FP8 images for B256).
+// Tensor-core engines: the operand images of tc_layout.cuh.  z_mode: F32X64: 0 = 3xTF32 hi/lo images, 2 = the 16-bit split ("H")
+// images of sweep_win.cu; B256: 0 = +-1 FP8 images (also what sweep_win.cu reads), 1 = "Z" encoding.
 int ensure_tc_layout(esfm_ctx* ctx, esfm_bank* b, int z_mode) {
     if (b->tc_built && b->tc_z == z_mode) return ESFM_OK;
     b->tc_z = z_mode;
     const int n_tiles = b->tile_off[b->n_frames];
-    b->tc_bytes = ((size_t)n_tiles + 1) * (b->kind == ESFM_KIND_F32X64 ? (size_t)kTcTileBytes : (size_t)kTc8TileBytes);
+    b->tc_bytes = ((size_t)n_tiles + 1) * (b->kind == ESFM_KIND_F32X64 && z_mode != 2 ? (size_t)kTcTileBytes : (size_t)kTc8TileBytes);
     if (!b->d_tc || b->tc_cap < b->tc_bytes) {
         if (b->d_tc) cudaFreeAsync(b->d_tc, ctx->stream);   // (stream-ordered: earlier sweeps have been enqueued before)
         b->d_tc = nullptr;
@@ -809,7 +817,8 @@ int ensure_tc_layout(esfm_ctx* ctx, esfm_bank* b, int z_mode) {
         b->tc_cap = b->tc_bytes;
     }
     cudaError_t e = b->kind == ESFM_KIND_F32X64
-            ? launch_pack_tc((const float*)b->d_rows, b->d_frame_rows, b->d_row_off, b->d_tile_off, b->n_frames, n_tiles, b->d_tc, ctx->stream)
+            ? (z_mode == 2 ? launch_pack_tch((const float*)b->d_rows, b->d_frame_rows, b->d_row_off, b->d_tile_off, b->n_frames, n_tiles, b->d_tc, ctx->stream)
+                           : launch_pack_tc((const float*)b->d_rows, b->d_frame_rows, b->d_row_off, b->d_tile_off, b->n_frames, n_tiles, b->d_tc, ctx->stream))
             : launch_pack_tc8((const uint32_t*)b->d_rows, b->d_frame_rows, b->d_row_off, b->d_tile_off, b->n_frames, n_tiles, b->d_tc, z_mode, ctx->stream);
     if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "tensor-core pack kernel launch failed: %s", cudaGetErrorString(e));
     if (n_tiles > 0) ctx->stats.kernel_launches += 1;
@@ -832,14 +841,16 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, ChunkBuf& cb, si
     CUDA_TRY(cudaMemsetAsync(cb.d_cursor, 0, 2 * sizeof(unsigned long long), ctx->stream));
     const bool tc = use_tc(ctx, b);
     // ORB "Z" encoding: the column index rides in the key, so every frame must have at most 2^15 rows; else the +-1 encoding
-    const int zmode = (tc && b->kind == ESFM_KIND_B256 && ctx->orb_z && b->max_rows <= kTcZMaxRows) ? 1 : 0;
-    if (tc) { if (int rc = ensure_tc_layout(ctx, b, zmode)) return rc; }
+    const bool win = tc && use_win(ctx, b);
+    const int zmode = (tc && !win && b->kind == ESFM_KIND_B256 && ctx->orb_z && b->max_rows <= kTcZMaxRows) ? 1 : 0;
+    if (tc) { if (int rc = ensure_tc_layout(ctx, b, win && b->kind == ESFM_KIND_F32X64 ? 2 : zmode)) return rc; }
     else if (b->kind == ESFM_KIND_F32X64) { if (int rc = ensure_kmajor_layout(ctx, b)) return rc; }
     if (b->kind == ESFM_KIND_F32X64 || tc)
         // column thresholds start at "no bound yet" (a repeated byte): FFMA engine 0x7f7f7f7f = 3.39e38f; tensor-core engines
         // 0x6f6f6f6f = 7.4e28f for SURF (below its 1e30 pad-row norm), 0x47474747 = 51015f for ORB +-1 (above every real
-        // value, below the pad rows), 0x4b4b4b4b = 1.33e7f for ORB "Z" (above every key)
-        CUDA_TRY(cudaMemsetAsync(ctx->col_thr, tc ? (b->kind == ESFM_KIND_F32X64 ? 0x6F : (zmode ? 0x4B : 0x47)) : 0x7F,
+        // value, below the pad rows), 0x4b4b4b4b = 1.33e7f for ORB "Z" (above every key); the FP16-accumulator ORB sweep keeps
+        // fp16 thresholds: 0x6060 = 560 (above every 2 * hamming)
+        CUDA_TRY(cudaMemsetAsync(ctx->col_thr, tc ? (b->kind == ESFM_KIND_F32X64 ? 0x6F : (win ? 0x60 : (zmode ? 0x4B : 0x47))) : 0x7F,
                                  n * (size_t)pl.stride * sizeof(uint32_t), ctx->stream));
     SweepParams sp{};
     sp.kmajor = b->d_kmajor;
@@ -861,7 +872,8 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, ChunkBuf& cb, si
     sp.tc_qtiles = 1;
     sp.tc_kind = zmode ? kTcKindB256Z : b->kind;
     if (ctx->profiling) CUDA_TRY(cudaEventRecord(cb.ev_t0, ctx->stream));
-    cudaError_t e = tc ? launch_sweep_l2_tc(sp, ctx->sm_count, ctx->stream)
+    cudaError_t e = win ? launch_sweep_win(sp, ctx->sm_count, ctx->stream)
+                  : tc ? launch_sweep_l2_tc(sp, ctx->sm_count, ctx->stream)
                        : (b->kind == ESFM_KIND_F32X64 ? launch_sweep_l2(sp, ctx->sm_count, ctx->stream)
                                                       : launch_sweep_hamming(sp, ctx->sm_count, ctx->stream));
     if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(e));
@@ -879,6 +891,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, ChunkBuf& cb, si
     fp.ratio = ratio;
     fp.cross_check = cross_check ? 1 : 0;
     fp.b256_float_keys = (tc && b->kind == ESFM_KIND_B256) ? (zmode ? 2 : 1) : 0;
+    fp.win_keys = win ? 1 : 0;
     fp.arena = cb.arena;
     fp.arena_cap = cb.arena_cap;
     fp.cursor = cb.d_cursor;

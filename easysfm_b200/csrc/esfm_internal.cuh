@@ -61,7 +61,7 @@ struct SweepParams {
     uint32_t* col_thr;          // [n_pairs][stride] running column thresholds (float bits), L2 sweeps only
     int stride;                 // keys per array (>= padded rows of the largest frame in the chunk)
     int col_cap;                // Hamming sweep: smem column-minimum capacity in entries
-    int tc_kind;                // TC sweep: ESFM_KIND_F32X64 (3xTF32 L2), ESFM_KIND_B256 (FP8 Hamming) or kTcKindB256Z (FP8 Hamming, packed
+    int tc_kind;                // TC sweeps: ESFM_KIND_F32X64 (3xTF32 L2; sweep_win: 16-bit split), ESFM_KIND_B256 (FP8 Hamming) or kTcKindB256Z (FP8 Hamming, packed
                                 // (distance, column) keys from the MMA); tc_main holds that kind's images
     int tc_qtiles;              // TC sweep geometry: query tiles per block (always 1: the two-tile variant of round 1 is no longer built)
     int need_cols;              // 0: cross_check is off, nobody reads the column minima -- the tensor-core sweeps skip the column side
@@ -89,6 +89,7 @@ struct FinalizeParams {
     int* overflow;              // set to 1 if the arena was too small
     int b256_float_keys;        // B256 keys from the tensor-core sweeps: 1 = high word is the float bits of 2 * hamming, 2 = of the packed key
                                 // z = kTcZ0 + 2^15 * hamming + column (tc_layout.cuh); 0 = the integer distance (XOR + POPC sweep)
+    int win_keys;               // row keys carry a WINDOW of train columns instead of a column (sweep_win.cu; see finalize.cu)
     // optional raw knn output for one pair (esfm_knn2_pair)
     int32_t* knn_idx;
     float* knn_dist;
@@ -101,7 +102,10 @@ cudaError_t launch_pack_tc8(const uint32_t* rows, const int* frame_rows, const i
                             int n_frames, int n_tiles_total, unsigned char* tc_main, int z_mode, cudaStream_t s);
 cudaError_t launch_pack_tc(const float* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
                            int n_frames, int n_tiles_total, unsigned char* tc_main, cudaStream_t s);
+cudaError_t launch_pack_tch(const float* rows, const int* frame_rows, const int* frame_row_off, const int* frame_tile_off,
+                            int n_frames, int n_tiles_total, unsigned char* tc_main, cudaStream_t s);
 cudaError_t launch_sweep_l2(const SweepParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_sweep_win(const SweepParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_sweep_l2_tc(const SweepParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_sweep_hamming(const SweepParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t s);

@@ -99,6 +99,119 @@ __device__ __forceinline__ RowResult eval_row(const FinalizeParams& p, const u64
     return r;
 }
 
+// ---- window keys (sweep_win.cu): a row key's low word names a slice of train columns instead of one column ----
+//     id = (first column / 8) << 1 | wide         wide = 0: 8 columns, 1: 32 columns
+// The column itself is found HERE, by evaluating the slice exactly -- and only for rows that can still pass the ratio test.
+__device__ __forceinline__ void win_range(u64 key, int ft, int& c0, int& c1) {
+    const uint32_t id = (uint32_t)key;
+    c0 = (int)(id >> 1) * 8;
+    c1 = min(c0 + ((id & 1u) ? 32 : 8), ft);
+}
+__device__ __forceinline__ int b256_hamming(const uint4& a0, const uint4& a1, const uint4* __restrict__ t) {
+    const uint4 b0 = __ldg(t), b1 = __ldg(t + 1);
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+// lowest column of [c0, c1) at Hamming distance `want` from the query row, skipping column `skip`
+__device__ __forceinline__ int b256_find(const uint4& a0, const uint4& a1, const uint4* __restrict__ tbits, int c0, int c1, int want, int skip) {
+    for (int c = c0; c < c1; ++c)
+        if (c != skip && b256_hamming(a0, a1, tbits + (size_t)c * 2) == want) return c;
+    return -1;
+}
+// exact top-2 by (distance, index) of the columns [c0, c1) merged into (d1, i1, d2, i2)
+__device__ __forceinline__ void l2_scan(const float* __restrict__ qrow, const float* __restrict__ trows, int c0, int c1, float& d1, int& i1, float& d2, int& i2) {
+    for (int c = c0; c < c1; ++c) {
+        const float d = l2_direct(qrow, trows + (size_t)c * kDim);
+        if (d < d1 || (d == d1 && c < i1)) {
+            d2 = d1; i2 = i1;
+            d1 = d; i1 = c;
+        } else if (d < d2 || (d == d2 && c < i2)) {
+            d2 = d; i2 = c;
+        }
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ RowResult eval_row_win(const FinalizeParams& p, const u64* rk1, const u64* rk2, const u64* ck1, const float* qrows,
+                                                  const float* trows, const uint4* qbits, const uint4* tbits, int q, int ft, int32_t* knn_idx,
+                                                  float* knn_dist) {
+    RowResult r;
+    r.keep = false;
+    r.t1 = -1;
+    r.d1 = 0.f;
+    const u64 k1 = rk1[q], k2 = rk2[q];
+    const bool has1 = k1 != kKeyInit, has2 = k2 != kKeyInit;
+    const bool no_ratio = p.ratio == __longlong_as_double(0x7ff0000000000000LL);
+    const float inf = __int_as_float(0x7f800000);
+    int i1 = -1, i2 = -1;
+    float d1 = inf, d2 = inf;
+    bool pass = false;
+    if (has1) {
+        int a0, a1, b0 = 0, b1 = 0;
+        win_range(k1, ft, a0, a1);
+        if (has2) win_range(k2, ft, b0, b1);
+        if (KIND == ESFM_KIND_B256) {
+            // the sweep's integer distances are exact: only the column has to be found
+            d1 = 0.5f * __uint_as_float((uint32_t)(k1 >> 32));
+            if (has2) d2 = 0.5f * __uint_as_float((uint32_t)(k2 >> 32));
+            pass = no_ratio || (has2 && (double)d1 < p.ratio * (double)d2);
+            if (pass || knn_idx) {
+                const uint4 q0 = __ldg(qbits + (size_t)q * 2), q1 = __ldg(qbits + (size_t)q * 2 + 1);
+                i1 = b256_find(q0, q1, tbits, a0, a1, (int)d1, -1);
+                if (knn_idx && has2) i2 = b256_find(q0, q1, tbits, b0, b1, (int)d2, i1);
+                if (i1 < 0) pass = false;       // (cannot happen: the sweep saw this distance in this window)
+            }
+        } else {
+            // the sweep ranked 1/2 d^2 in expansion form (error ~4e-7 absolute): decide far-from-the-boundary rows on those values,
+            // evaluate the rest -- and every reported distance -- in direct form
+            const float s1 = __uint_as_float((uint32_t)(k1 >> 32)), s2 = has2 ? __uint_as_float((uint32_t)(k2 >> 32)) : inf;
+            bool scan2 = knn_idx != nullptr && has2, skip = false;
+            if (!no_ratio) {
+                if (!has2) skip = true;
+                else if (!(p.ratio > 0.0)) skip = true;
+                else {
+                    const float r2 = (float)(p.ratio * p.ratio);
+                    const bool clear_fail = s1 > r2 * s2 * 1.001f + 4e-6f;
+                    const bool clear_pass = s1 < r2 * s2 * 0.999f - 4e-6f;
+                    if (clear_fail) skip = true;
+                    else if (!clear_pass) scan2 = true;
+                    else pass = true;
+                }
+            } else pass = true;
+            if (!skip || knn_idx) {
+                const float* qrow = qrows + (size_t)q * kDim;
+                const bool contained = scan2 && a0 >= b0 && a1 <= b1;
+                if (!contained) l2_scan(qrow, trows, a0, a1, d1, i1, d2, i2);
+                if (scan2) {
+                    l2_scan(qrow, trows, b0, b1, d1, i1, d2, i2);
+                    if (!no_ratio && !skip) pass = i2 >= 0 && (double)d1 < p.ratio * (double)d2;
+                }
+                if (i1 < 0) pass = false;
+            }
+            if (skip) pass = false;
+        }
+    }
+    if (knn_idx) {
+        knn_idx[2 * q] = i1; knn_idx[2 * q + 1] = i2;
+        knn_dist[2 * q] = d1; knn_dist[2 * q + 1] = d2;
+    }
+    if (!pass) return r;
+    if (p.cross_check) {
+        const u64 c1 = ck1[i1];
+        if (c1 == kKeyInit) return r;
+        const int best = (int)(uint32_t)c1;
+        if (best != q) {
+            if (KIND != ESFM_KIND_F32X64) return r;
+            const float db = l2_direct(qrows + (size_t)best * kDim, trows + (size_t)i1 * kDim);
+            if (!(d1 < db || (d1 == db && q < best))) return r;
+        }
+    }
+    r.keep = true;
+    r.t1 = i1;
+    r.d1 = d1;
+    return r;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizeParams p) {
     const int pair = blockIdx.x;
@@ -110,9 +223,14 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizePar
     const u64* ck2 = ck1 + p.stride;
     const float* qrows = nullptr;
     const float* trows = nullptr;
+    const uint4* qbits = nullptr;
+    const uint4* tbits = nullptr;
     if (KIND == ESFM_KIND_F32X64) {
         qrows = p.rows_f32 + (size_t)p.frame_row_off[pd.q_frame] * kDim;
         trows = p.rows_f32 + (size_t)p.frame_row_off[pd.t_frame] * kDim;
+    } else {
+        qbits = p.rows_b256 + (size_t)p.frame_row_off[pd.q_frame] * 2;
+        tbits = p.rows_b256 + (size_t)p.frame_row_off[pd.t_frame] * 2;
     }
     __shared__ unsigned int s_warp[kFinThreads / 32];
     __shared__ unsigned long long s_base;
@@ -123,7 +241,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizePar
     if (fq == 0 || ft < (no_ratio ? 1 : 2)) {  // F7: no second neighbour exists
         if (p.knn_idx) {
             for (int q = threadIdx.x; q < fq; q += kFinThreads) {
-                RowResult r = eval_row<KIND>(p, rk1, rk2, ck1, ck2, qrows, trows, q, fq, p.knn_idx, p.knn_dist);
+                RowResult r = p.win_keys ? eval_row_win<KIND>(p, rk1, rk2, ck1, qrows, trows, qbits, tbits, q, ft, p.knn_idx, p.knn_dist)
+                                         : eval_row<KIND>(p, rk1, rk2, ck1, ck2, qrows, trows, q, fq, p.knn_idx, p.knn_dist);
                 (void)r;
             }
         }
@@ -137,7 +256,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizePar
     // pass 1: evaluate every query row; stash the verdict in the row's first key slot
     unsigned int mine = 0;
     for (int q = threadIdx.x; q < fq; q += kFinThreads) {
-        const RowResult r = eval_row<KIND>(p, rk1, rk2, ck1, ck2, qrows, trows, q, fq, p.knn_idx, p.knn_dist);
+        const RowResult r = p.win_keys ? eval_row_win<KIND>(p, rk1, rk2, ck1, qrows, trows, qbits, tbits, q, ft, p.knn_idx, p.knn_dist)
+                                       : eval_row<KIND>(p, rk1, rk2, ck1, ck2, qrows, trows, q, fq, p.knn_idx, p.knn_dist);
         rk1[q] = r.keep ? make_key(__float_as_uint(r.d1), (uint32_t)r.t1) : kKeyInit;
         mine += r.keep ? 1u : 0u;
     }

@@ -83,6 +83,109 @@ inline void tc_pack_row_host(const float* x, bool valid, bool query_role, uint8_
     for (int j = 0; j < 8; ++j) memcpy(tile + kTcMainBytes + g * kTcAugGroupBytes + tc_aug_off(rr, j), &a[j], 4);
 }
 
+// ---- SURF on kind::f16: the two-term 16-bit split ("H" layout) -----------------------------------------------------------
+// The same idea as 3xTF32 at half the tensor-pipe time: every fp32 operand x is stored as
+//     a = fp16(x)  (11 significant bits, round to nearest),   b = fp16(x - a)  (11 more; for |x| < 0.25 the residual is an fp16
+//     SUBNORMAL, quantum 2^-24: the tensor core honours them -- csrc/microbench/h16_probe.cu -- so |x - a - b| <= 2^-25)
+// and  q.t ~= b_q.a_t + a_q.b_t + a_q.a_t  = 3 terms x 4 MMAs of K = 16 (kind::f16, fp32 accumulation; a 16 x 16-bit k-step is
+// the same 32 bytes of a SWIZZLE_128B row as a TF32 K = 8 step).  Dropped term b.b <= 2^-24 |q||t|; measured on unit-norm
+// SURF-like rows: max |error| 4.1e-7 on 1/2 d^2, rms 1e-7 -- the same as 3xTF32 (3.6e-7).  (kind::f16 with A = fp16 and B = bf16
+// in ONE instruction is an illegal instruction on sm_100a: measured; both operands must share the format.)  The half norms are
+// added by the SAME exact K = 8 kind::tf32 MMA over the augmented columns as in the 3xTF32 layout (the kind is per instruction).
+// Image per 128-row tile (kTchTileBytes = 36864, the geometry of the FP8 images): 16 groups x 2048 B = [a k0..63][b k0..63],
+// each ONE 1024-byte SWIZZLE_128B K-major atom (8 rows x 128 B = 64 16-bit values), then the 16 x 256 B augmented blocks.
+constexpr int kTchGroupBytes = 2048;
+constexpr int kTchMainBytes = 16 * kTchGroupBytes;            // 32768
+constexpr int kTchTileBytes = kTchMainBytes + kTcAugBytes;    // 36864
+// fp16 / bf16 codes of a float, round to nearest even (host + device, no cuda_fp16.h types in the interfaces)
+__host__ __device__ __forceinline__ uint32_t tch_f2h(float x) {
+#ifdef __CUDA_ARCH__
+    unsigned short h;
+    asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+    return h;
+#else
+    uint32_t b;
+    memcpy(&b, &x, 4);
+    const uint32_t sign = (b >> 16) & 0x8000u;
+    const int e = (int)((b >> 23) & 0xff) - 127 + 15;
+    uint32_t m = b & 0x7fffffu;
+    if (((b >> 23) & 0xff) == 0xff) return sign | 0x7c00u | (m ? 0x200u : 0u);
+    if (e >= 31) return sign | 0x7c00u;
+    if (e <= 0) {
+        if (e < -10) return sign;
+        m |= 0x800000u;
+        const int sh = 14 - e;                       // 14 .. 24
+        uint32_t r = m >> sh;
+        const uint32_t rem = m & ((1u << sh) - 1u), half = 1u << (sh - 1);
+        if (rem > half || (rem == half && (r & 1u))) ++r;
+        return sign | r;
+    }
+    uint32_t r = ((uint32_t)e << 10) | (m >> 13);
+    const uint32_t rem = m & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (r & 1u))) ++r;
+    return sign | r;
+#endif
+}
+__host__ __device__ __forceinline__ float tch_h2f(uint32_t h) {
+#ifdef __CUDA_ARCH__
+    float f;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"((unsigned short)h));
+    return f;
+#else
+    const uint32_t sign = (h & 0x8000u) << 16;
+    uint32_t e = (h >> 10) & 0x1fu, m = h & 0x3ffu, b;
+    if (e == 0) {
+        if (m == 0) b = sign;
+        else {
+            int sh = 0;
+            while (!(m & 0x400u)) { m <<= 1; ++sh; }
+            b = sign | ((uint32_t)(127 - 15 + 1 - sh) << 23) | ((m & 0x3ffu) << 13);
+        }
+    } else if (e == 31) b = sign | 0x7f800000u | (m << 13);
+    else b = sign | ((e + 112u) << 23) | (m << 13);
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t tch_f2bf(float x) {
+    uint32_t b;
+#ifdef __CUDA_ARCH__
+    b = __float_as_uint(x);
+#else
+    memcpy(&b, &x, 4);
+#endif
+    return (b + 0x7fffu + ((b >> 16) & 1u)) >> 16;            // finite inputs only
+}
+// (a, b) codes of x: a = fp16(x), b = fp16(x - a)
+__host__ __device__ __forceinline__ void tch_split(float x, uint32_t& a, uint32_t& b) {
+    a = tch_f2h(x);
+    b = tch_f2h(x - tch_h2f(a));
+}
+// byte offset of 16-bit element k in [0,64) of row rr in [0,8) inside one 1024-byte SWIZZLE_128B atom
+__host__ __device__ __forceinline__ int tch_sw128_off(int rr, int k) { return rr * 128 + ((((k >> 3) ^ rr) & 7) << 4) + ((k & 7) << 1); }
+
+// Host reference of the H packing (probe + tests); bank.cu's pack kernel writes the same bytes.  Train role only: the query
+// operand is built by the sweep's writer warps in tensor memory.
+inline void tch_pack_row_host(const float* x, bool valid, uint8_t* tile, int r) {
+    const int g = r >> 3, rr = r & 7;
+    float s = 0.f;
+    for (int k = 0; k < kDim; ++k) s = fmaf(x[k], x[k], s);
+    const float h = valid ? 0.5f * s : kTcPadNorm;
+    for (int k = 0; k < kDim; ++k) {
+        uint32_t a, b;
+        tch_split(valid ? x[k] : 0.f, a, b);
+        const uint16_t a16 = (uint16_t)a, b16 = (uint16_t)b;
+        const int off = g * kTchGroupBytes + tch_sw128_off(rr, k);
+        memcpy(tile + off, &a16, 2);
+        memcpy(tile + off + 1024, &b16, 2);
+    }
+    float hh, hm, hl;
+    tc_split3(h, hh, hm, hl);
+    const float a[8] = {-hh, -hm, -hl, -1.f, -1.f, -1.f, 0.f, 0.f};
+    for (int j = 0; j < 8; ++j) memcpy(tile + kTchMainBytes + g * kTcAugGroupBytes + tc_aug_off(rr, j), &a[j], 4);
+}
+
 // ---- ORB / Hamming on the tensor cores: 256 bits -> 256 FP8 (E4M3) values +-1 ----------------------------------------
 // bit 0 -> +1.0 (0x38), bit 1 -> -1.0 (0xB8): the dot product of two such rows is 256 - 2 * hamming, an exact small integer in
 // the fp32 accumulator.  One more K = 32 MMA over augmented columns adds -256 and pushes pad rows out of reach:
@@ -162,6 +265,15 @@ __host__ __device__ constexpr uint32_t tc_idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// kind::f16: D = F32, A / B format 0 = F16, 1 = BF16 (independent), both K-major
+__host__ __device__ constexpr uint32_t tc_idesc_f16(int m, int n, int a_bf16, int b_bf16) {
+    return (1u << 4) | ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// kind::f8f6f4, A = B = E4M3, D = F16: sums of +-1 products are small integers, exact in fp16; the accumulator still takes one
+// 32-bit tensor-memory column per element, tcgen05.ld.pack::16b returns two columns per register
+__host__ __device__ constexpr uint32_t tc_idesc_e4m3_h(int m, int n) {
+    return ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 // kind::f8f6f4 with A = B = E4M3 (format code 0), D = F32
 __host__ __device__ constexpr uint32_t tc_idesc_e4m3(int m, int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -197,6 +309,15 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// kind::f16, operand A from tensor memory (lane = row m, TWO consecutive k per 32-bit column, lower k in the low half)
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
 }
@@ -240,6 +361,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+// 32 lanes x 32 consecutive columns holding 16-bit values (fp16 accumulators), two columns packed per register: register i =
+// column 2 i (low half) | column 2 i + 1 (high half)
+__device__ __forceinline__ void tmem_ld16_pack(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)

@@ -109,18 +109,26 @@ int esfm_device_sm_count(esfm_ctx_t* ctx, int* sms);
  * re-evaluation (the reference's arithmetic, BFMatcher(NORM_L2): feature_match.py:33-34); they differ in how the
  * RANKING distance is computed:
  *   ESFM_L2_ENGINE_FFMA  exact-FP32 FFMA expansion  1/2|q|^2 + 1/2|t|^2 - q.t  on the FP32 pipe;
- *   ESFM_L2_ENGINE_TC    the same quantity as a 3xTF32 split product on the tcgen05 tensor cores.
- * Default: $ESFM_L2_ENGINE ("ffma" | "tc") at esfm_init, else ESFM_L2_ENGINE_TC. */
+ *   ESFM_L2_ENGINE_TC    the same quantity as a 3xTF32 split product on the tcgen05 tensor cores;
+ *   ESFM_L2_ENGINE_TC16  the same quantity as a two-term FP16 split product (kind::f16, fp32 accumulation: the error of 3xTF32 at
+ *                        half the tensor-pipe time and half the operand bytes), rows reported as (value, slice of columns) and
+ *                        resolved exactly by the finalize pass.
+ * Default: $ESFM_L2_ENGINE ("ffma" | "tc" | "tc16") at esfm_init, else ESFM_L2_ENGINE_TC16. */
 #define ESFM_L2_ENGINE_FFMA 0
 #define ESFM_L2_ENGINE_TC 1
+#define ESFM_L2_ENGINE_TC16 2
 int esfm_set_l2_engine(esfm_ctx_t* ctx, int engine);
 int esfm_get_l2_engine(esfm_ctx_t* ctx, int* engine);
 /* Which kernel serves ESFM_KIND_B256: XOR + POPC on the integer pipes (the north-star design), or the same Hamming
  * distance as an exact FP8 dot product on the tcgen05 tensor cores (bits become +-2^k, the fp32 accumulator holds the
- * integer 20480 + 2^15 * hamming + column exactly; 2.3x faster).  Both are bit-exact against OpenCV and against each other;
- * default: $ESFM_HAMMING_ENGINE ("popc" | "tc") at esfm_init, else ESFM_HAMMING_ENGINE_TC. */
+ * integer 20480 + 2^15 * hamming + column exactly; 2.3x faster).
+ * ESFM_HAMMING_ENGINE_TC16: the FP8 +-1 dot product with FP16 accumulators (-2 * hamming, exact), a selection epilogue on packed
+ * halves, rows reported as (distance, slice of 32 columns) and resolved with XOR + POPC by the finalize pass.  All three are
+ * bit-exact against OpenCV and against each other;
+ * default: $ESFM_HAMMING_ENGINE ("popc" | "tc" | "tc16") at esfm_init, else ESFM_HAMMING_ENGINE_TC16. */
 #define ESFM_HAMMING_ENGINE_POPC 0
 #define ESFM_HAMMING_ENGINE_TC 1
+#define ESFM_HAMMING_ENGINE_TC16 2
 int esfm_set_hamming_engine(esfm_ctx_t* ctx, int engine);
 int esfm_get_hamming_engine(esfm_ctx_t* ctx, int* engine);
 

@@ -223,7 +223,7 @@ def test_hamming_engines_are_byte_identical(ctx):
     keep = ctx.hamming_engine()
     out = {}
     try:
-        for eng in ("popc", "tc"):
+        for eng in ("popc", "tc", "tc16"):
             ctx.set_hamming_engine(eng)
             bank = ctx.bank_from_frames(frames)
             per = []
@@ -238,6 +238,7 @@ def test_hamming_engines_are_byte_identical(ctx):
     finally:
         ctx.set_hamming_engine(keep)
     assert out["popc"] == out["tc"]
+    assert out["popc"] == out["tc16"]
     # the +-1 operand encoding with the generic epilogue ($ESFM_ORB_Z=0, read at esfm_init): what frames with more than 32768
     # rows fall back to (the default Z encoding packs the column index into 15 bits of the accumulator)
     import os

@@ -6,9 +6,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import easysfm_b200 as esfm
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-from golden_util import load_fountain
+from golden_util import load, frames_of
 
-frames = load_fountain()
+frames = frames_of(load("fountain_orb.npz"))
 ctx = esfm.Context(0)
 pairs = [(i, j) for i in range(len(frames)) for j in range(i)]
 out = {}

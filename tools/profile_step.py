@@ -15,7 +15,7 @@ engine = sys.argv[5] if len(sys.argv) > 5 else None
 dev = torch.device("cuda:0")
 ctx = esfm.Context(0)
 if engine:
-    ctx.set_l2_engine(engine)
+    (ctx.set_l2_engine if kind == "surf" else ctx.set_hamming_engine)(engine)
 bank = ctx.bank(esfm.KIND_F32X64 if kind == "surf" else esfm.KIND_B256, n_images)
 for f in range(n_images):
     bank.set_frame_rows(f, n_feat)
@@ -36,7 +36,7 @@ for r in range(repeats):
     ctx.synchronize()
     dt = time.perf_counter() - t0
     st = ctx.stats()
-    print(f"{kind} engine={ctx.l2_engine() if kind == 'surf' else '-'} {len(pairs)} pairs of {n_feat}x{n_feat}: {n} matches, {dt * 1e3:.1f} ms wall, "
+    print(f"{kind} engine={ctx.l2_engine() if kind == 'surf' else ctx.hamming_engine()} {len(pairs)} pairs of {n_feat}x{n_feat}: {n} matches, {dt * 1e3:.1f} ms wall, "
           f"finalize {st['last_finalize_ms']:.2f} ms, sweep {st['last_sweep_ms']:.2f} ms -> {len(pairs) * n_feat * n_feat / (st['last_sweep_ms'] * 1e-3):.3e} cmp/s", flush=True)
 bank.close()
 ctx.close()
