@@ -228,8 +228,9 @@ def workload_config(kind, pairs_per_step, e2e_frames):
 
 def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budget_s, engine=None, e2e_arm=True):
     """Returns the result dict for one descriptor kind (device-resident value, e2e, roofline, cpu baseline).
-    `engine` selects the sweep kernel: SURF 'tc' (tcgen05 3xTF32) | 'ffma' (exact-FP32 FMA pipe); ORB 'tc' (tcgen05 FP8 dot
-    product delivering packed keys) | 'popc' (XOR + POPC); None = library default."""
+    `engine` selects the sweep kernel: SURF 'tc16' (tcgen05 FP16 split, slice keys) | 'tc' (tcgen05 3xTF32) | 'ffma' (exact-FP32 FMA pipe);
+    ORB 'tc16' (tcgen05 FP8 dot product, FP16 accumulators, slice keys) | 'tc' (FP8 dot product delivering packed keys) | 'popc' (XOR + POPC);
+    None = library default (tc16)."""
     import torch
     from easysfm_b200 import scheduler
     import easysfm_b200 as esfm
@@ -426,7 +427,12 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
     peaks, peak_src = _peaks()
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     fp32_pipe_peak = sms * SM_LANES_FP32 * 2 * sm_max * 1e6 / 1e12
-    if kind == "surf" and engine == "tc":
+    if kind == "surf" and engine == "tc16":
+        unit_ops, unit = 128.0, "TFLOP/s"                      # algorithmic: 64 FMA = 128 FLOP per comparison
+        peak = float(peaks.get("bf16_tflops", 1590.0))         # kind::f16 operands: the measured dense 16-bit tensor rate
+        bound = "tensor"
+        kern = "sweep_win_kernel<ESFM_KIND_F32X64>"
+    elif kind == "surf" and engine == "tc":
         unit_ops, unit = 128.0, "TFLOP/s"                      # algorithmic: 64 FMA = 128 FLOP per comparison
         peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0   # dense TF32 = half the measured dense bf16 rate
         bound = "tensor"
@@ -436,11 +442,11 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
         peak = fp32_pipe_peak
         bound = "fp32-fma-pipe"
         kern = "sweep_l2_kernel"
-    elif engine == "tc":
+    elif engine in ("tc", "tc16"):
         unit_ops, unit = 8.0, "TPOPC/s"                        # algorithmic: 8 x 32-bit POPC per comparison (north_star)
         peak = sms * POPC_LANES * sm_max * 1e6 / 1e12          # ... against the pipe the XOR+POPC design is bound by
         bound = "tensor"
-        kern = "sweep_l2_tc_kernel<1, kTcKindB256Z>"
+        kern = "sweep_l2_tc_kernel<1, kTcKindB256Z>" if engine == "tc" else "sweep_win_kernel<ESFM_KIND_B256>"
     else:
         unit_ops, unit = 8.0, "TPOPC/s"                        # 8 x 32-bit POPC per comparison (algorithmic, north_star)
         peak = sms * POPC_LANES * sm_max * 1e6 / 1e12
@@ -448,8 +454,12 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
         kern = "sweep_hamming_kernel"
     achieved = comps_per_launch * unit_ops / (sweep_ms * 1e-3) / 1e12
     roofline = {"bound": bound, "kernel": kern, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-                "peak_source": (f"dense TF32 tensor peak = bf16_tflops / 2 of MEASURED_PEAKS.json ({peak_src}: "
-                                f"{peaks.get('bf16_tflops', 1590.0):.0f} TFLOP/s bf16)") if bound == "tensor" else
+                "peak_source": ((f"dense 16-bit tensor peak = bf16_tflops of MEASURED_PEAKS.json ({peak_src}): the sweep's MMAs are kind::f16"
+                                 if engine == "tc16" else
+                                 f"dense TF32 tensor peak = bf16_tflops / 2 of MEASURED_PEAKS.json ({peak_src}: "
+                                 f"{peaks.get('bf16_tflops', 1590.0):.0f} TFLOP/s bf16)") if kind == "surf" else
+                                f"{sms} SMs x 16 POPC lanes x {sm_max:.0f} MHz: the pipe the north star's XOR + POPC design is bound by "
+                                f"(sm_max_mhz {peak_src})") if bound == "tensor" else
                                f"{sms} SMs x {'128 FFMA lanes x 2 FLOP' if kind == 'surf' else '16 POPC lanes'} x {sm_max:.0f} MHz "
                                f"(sm_max_mhz {peak_src}; lanes/clk measured by csrc/microbench/pipes.cu, profiles/pipes_r1.txt)",
                 "kernel_ms": sweep_ms, "comparisons_per_launch": comps_per_launch,
@@ -464,10 +474,27 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
         roofline["executed_tflops"] = (comps_per_launch / (sweep_ms * 1e-3)) * TC8_FLOP_PER_CMP / 1e12
         roofline["frac_executed"] = roofline["executed_tflops"] / fp8_peak
         roofline["tensor_peak_tflops"] = fp8_peak
-        roofline["note"] = ("Hamming as an exact FP8 dot product on tcgen05 (kind::f8f6f4) that yields packed (distance, column) keys: "
+        roofline["note"] = (("Hamming as an exact FP8 dot product on tcgen05 (kind::f8f6f4) with FP16 accumulators (-2 hamming), selection on packed halves: "
+                             if engine == "tc16" else
+                             "Hamming as an exact FP8 dot product on tcgen05 (kind::f8f6f4) that yields packed (distance, column) keys: ") +
                             "576 tensor FLOP per comparison; frac is the algorithmic 8-POPC rate over the POPC-pipe peak; the kernel is bound by "
-                            "its selection epilogue and by the 64 B/clk tensor-memory read-out (4.65e12 comparisons/s), not by the tensor pipe")
-    if bound == "tensor" and kind == "surf":
+                            "the instruction issue of its selection epilogue (column events above all), not by the tensor pipe: 9 MMAs = 577 clk per "
+                            "128 x 128 tile would be 8.3e12 comparisons/s")
+        roofline["mma_bound_cmp_per_s"] = sms * sm_max * 1e6 * 16384 / (9 * 64.1)
+        roofline["frac_of_mma_bound"] = (comps_per_launch / (sweep_ms * 1e-3)) / roofline["mma_bound_cmp_per_s"]
+    if bound == "tensor" and kind == "surf" and engine == "tc16":
+        # `achieved`/`frac`: ALGORITHMIC 128 FLOP per comparison over the dense 16-bit tensor peak.  Executed: 3 x 64 x 2 FLOP on kind::f16
+        # + 16 on kind::tf32 = 13 MMA slots of 64 clk per 128 x 128 tile (h16_probe: 64.1 clk per MMA); `frac_of_mma_bound` = how close the
+        # sweep is to that issue-rate ceiling.  What binds it is the selection epilogue's instruction issue, not the tensor pipe.
+        roofline["executed_tflops"] = achieved * 400.0 / 128.0
+        roofline["frac_executed"] = achieved * (384.0 / 128.0) / peak + achieved * (16.0 / 128.0) / (peak / 2.0)
+        roofline["mma_bound_cmp_per_s"] = sms * sm_max * 1e6 * 16384 / (13 * 64.1)
+        roofline["frac_of_mma_bound"] = (comps_per_launch / (sweep_ms * 1e-3)) / roofline["mma_bound_cmp_per_s"]
+        roofline["frac_vs_tf32_peak"] = achieved / (peak / 2.0)
+        roofline["frac_of_fp32_pipe_roofline"] = achieved / fp32_pipe_peak
+        roofline["note"] = ("two-term FP16 split product (b.a + a.b + a.a over 64 dims on kind::f16, + one exact K=8 kind::tf32 step adding the norms) "
+                            "on tcgen05: 13 MMA slots per tile instead of the 25 of 3xTF32; frac_vs_tf32_peak is the round-1 denominator (bf16 / 2)")
+    if bound == "tensor" and kind == "surf" and engine == "tc":
         # `achieved`/`frac` use the ALGORITHMIC 128 FLOP per comparison.  The tensor cores execute 3.125x that
         # (3xTF32 split over 64 dims + 8 augmented columns); `frac_executed` is that executed rate over the same peak (= tensor-pipe utilisation),
         # and `frac_of_fp32_pipe_roofline` compares the algorithmic rate with the FP32-FFMA pipe peak the FFMA engine is bound by.
@@ -476,7 +503,7 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
         roofline["frac_of_fp32_pipe_roofline"] = achieved / fp32_pipe_peak
         roofline["note"] = ("3xTF32 split product (lo.hi + hi.lo + hi.hi over 64 dims, + one K=8 step adding the norms) on tcgen05; "
                             f"{TC_FLOP_PER_CMP} tensor FLOP executed per 128 algorithmic FLOP")
-    if kind == "orb" and engine != "tc":
+    if kind == "orb" and engine == "popc":
         # The kernel compresses the 8 xor words with carry-save adders and issues only 4 POPC per comparison, so it can
         # exceed the algorithmic 8-POPC roofline; what binds it is instruction issue (~36 warp-instructions per 32
         # comparisons, 4 issue slots per clock per SM; profiles/sass_hamming_loop_r1.txt).
@@ -488,13 +515,14 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
     # algorithmic HBM bytes: every pair reads both frames once + writes its matches
     # (SURF rows: 260 B in the FFMA engine's k-major bank; tensor-core engine: 544 B per train row = hi + lo images + augmented
     #  columns, 256 B per query row = the fp32 rows the sweep converts on the fly)
-    bytes_per_pair = n_feat * (((544 + 256) if engine == "tc" else 520) if kind == "surf" else ((288 + 32) if engine == "tc" else 64))
+    bytes_per_pair = n_feat * ((((544 if engine == "tc" else 288) + 256) if engine in ("tc", "tc16") else 520) if kind == "surf"
+                               else ((288 + 32) if engine in ("tc", "tc16") else 64))
     roofline["hbm_gbs_algorithmic"] = (comps_per_launch / (n_feat * n_feat)) * bytes_per_pair / (sweep_ms * 1e-3) / 1e9
     roofline["hbm_peak_gbs"] = peaks.get("hbm_gbs")
     # measured DRAM traffic of this kernel on this command (one ncu pass, committed under profiles/): far BELOW the per-pair
     # algorithmic bytes because pairs launched together share their train frame in L2 (capi.cu sorts a chunk by train frame)
     import glob
-    tkey = {"surf": "surf_tc", "orb": "orb_tc"}[kind] if engine == "tc" else kind
+    tkey = {"surf": "surf_", "orb": "orb_"}[kind] + engine if engine in ("tc", "tc16") else kind
     for tpath in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_traffic_r*.json")), reverse=True):    # newest round that has this kernel
         try:
             with open(tpath) as f:
@@ -546,9 +574,9 @@ def main():
     ap.add_argument("--images", type=int, default=0, help="override the number of images (smoke runs)")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--ref-pairs-per-step", type=int, default=4)
-    ap.add_argument("--l2-engine", default=None, choices=["tc", "ffma"],
+    ap.add_argument("--l2-engine", default=None, choices=["tc16", "tc", "ffma"],
                     help="SURF sweep kernel: tcgen05 3xTF32 ('tc', library default) or exact-FP32 FMA pipe ('ffma')")
-    ap.add_argument("--hamming-engine", default=None, choices=["tc", "popc"],
+    ap.add_argument("--hamming-engine", default=None, choices=["tc16", "tc", "popc"],
                     help="ORB sweep kernel: tcgen05 FP8 +-1 dot product ('tc') or XOR + POPC ('popc'); default = library default")
     ap.add_argument("--no-alt-engine", action="store_true", help="skip the short run of the other engine of each kind")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of a sample of the timed step (runs under ncu)")
@@ -586,7 +614,7 @@ def main():
     ctx = esfm.Context(local_rank, stream=stream.cuda_stream)
 
     engines = {"surf": args.l2_engine or ctx.l2_engine(), "orb": args.hamming_engine or ctx.hamming_engine()}
-    other_engine = {"surf": {"tc": "ffma", "ffma": "tc"}, "orb": {"tc": "popc", "popc": "tc"}}
+    other_engine = {"surf": {"tc16": "ffma", "tc": "ffma", "ffma": "tc16"}, "orb": {"tc16": "popc", "tc": "popc", "popc": "tc16"}}
 
     def alt_run(kind):
         # the other engine of this kind on the same workload, device-resident arm only (short: it is context, not the headline)

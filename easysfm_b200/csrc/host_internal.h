@@ -76,8 +76,8 @@ struct esfm_ctx {
     bool profiling = true;
     int orb_z = 1;                         // ORB tensor-core sweep with the "Z" operand encoding (packed keys from the MMA): default;
                                            // $ESFM_ORB_Z=0 selects the +-1 encoding with the generic epilogue
-    int hamming_engine = ESFM_HAMMING_ENGINE_TC;
-    int l2_engine = ESFM_L2_ENGINE_TC;
+    int hamming_engine = ESFM_HAMMING_ENGINE_TC16;
+    int l2_engine = ESFM_L2_ENGINE_TC16;
     esfm_stats_t stats{};
     // device scratch, grown on demand
     esfm::u64* keys = nullptr;     size_t keys_bytes = 0;

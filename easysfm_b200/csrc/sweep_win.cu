@@ -72,7 +72,7 @@ __device__ __forceinline__ void win_col_post2(uint32_t v, uint32_t e, u64* ck, u
 
 // The many-rows case (first query block of a pair): 4 columns parked in the warp's scratch as floats y = 2 * hamming, one segmented
 // warp reduction (8 lanes per column), the 4 leaders post.  Thresholds are fp16 S values at thr_addr (shared window), 2 bytes each.
-__device__ __noinline__ void win_col_group_h(uint32_t sc_addr, uint32_t thr_addr, u64* ck, unsigned short* tau, uint32_t qrow0, float s_add) {
+__device__ __forceinline__ void win_col_group_h(uint32_t sc_addr, uint32_t thr_addr, u64* ck, unsigned short* tau, uint32_t qrow0, float s_add) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t col = lane >> 3, r4 = (lane & 7u) * 4u;
     float y0, y1, y2, y3;
@@ -101,6 +101,30 @@ __device__ __noinline__ void win_col_group_h(uint32_t sc_addr, uint32_t thr_addr
     }
 }
 
+// ---- ORB: compact, never-inlined event handlers: ONE copy of each in the instruction stream (the unrolled per-chain copies were 23 KB
+//      of rarely executed code; "no instruction" was 31 % of the stalls inside them, profiles/ncu_orb_tc16_r2.txt).  The SURF epilogue
+//      keeps its handlers inline: a call while 32 accumulators are live costs more in register moves than the code size saves
+//      (measured: 22.8 -> 24.2 ms) ----
+// ORB: one chain of 8 columns = 4 registers of the calling lane (only lanes with a hit call this)
+__device__ __noinline__ void win_chain_post_h(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t thr_addr, u64* ck, unsigned short* tau,
+                                              uint32_t qrow, uint32_t s_add) {
+    uint32_t s0, s1, s2, s3;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3) : "r"(thr_addr));
+    win_col_post2<0>(x0, hadd2_relu(x0, s0), ck, tau, qrow, s_add);
+    win_col_post2<1>(x1, hadd2_relu(x1, s1), ck, tau, qrow, s_add);
+    win_col_post2<2>(x2, hadd2_relu(x2, s2), ck, tau, qrow, s_add);
+    win_col_post2<3>(x3, hadd2_relu(x3, s3), ck, tau, qrow, s_add);
+}
+// ORB: one group of 4 columns = 2 registers of EVERY lane (whole warp): park, reduce, post
+__device__ __noinline__ void win_group_h(uint32_t x0, uint32_t x1, uint32_t sc_addr, uint32_t thr_addr, u64* ck, unsigned short* tau, uint32_t qrow0, float s_add) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const float y[4] = {fabsf(h_lo(x0)), fabsf(h_hi(x0)), fabsf(h_lo(x1)), fabsf(h_hi(x1))};      // pads: +inf, never a winner
+#pragma unroll
+    for (int c = 0; c < 4; ++c) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sc_addr + (uint32_t)(c * 128) + lane * 4u), "f"(y[c]) : "memory");
+    __syncwarp();
+    win_col_group_h(sc_addr, thr_addr, ck, tau, qrow0, s_add);
+    __syncwarp();
+}
 // merge the pass's two largest values (p1 >= p2, found in the column slices id1 / id2) into the running (k1, w1, k2, w2): strict
 // comparisons, so of equal values the one found first (the lower slice = the lower column) stays in front
 __device__ __forceinline__ void win_merge(float p1, int id1, float p2, int id2, float& k1, int& w1, float& k2, int& w2) {
@@ -388,37 +412,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
                                     e[4 * cq + 2] = hadd2_relu(hb[4 * cq + 2], s.z); e[4 * cq + 3] = hadd2_relu(hb[4 * cq + 3], s.w);
                                     cf[cq] = (e[4 * cq] | e[4 * cq + 1]) | (e[4 * cq + 2] | e[4 * cq + 3]);
                                 }
-                                if (!(p.debug_flags & 8) && __any_sync(0xffffffffu, ((cf[0] | cf[1]) | (cf[2] | cf[3])) != 0u)) {
+                                const uint32_t cfa = (cf[0] | cf[1]) | (cf[2] | cf[3]);
+                                const uint32_t hm = __ballot_sync(0xffffffffu, cfa != 0u);
+                                if (!(p.debug_flags & 8) && hm != 0u) {
+                                    // Column events: ~0.7 per pass in the steady state, 32 per pass in the first query block of a pair.
                                     u64* ckb = ck1 + col0;
                                     unsigned short* taub = reinterpret_cast<unsigned short*>(p.col_thr) + (size_t)u.pair * p.stride + col0;
-                                    asm volatile("" : "+l"(ckb), "+l"(taub));
                                     const uint32_t thr_addr = smem_u32(tp);
                                     const bool strict = p.units_per_pair == 1;
-#pragma unroll
-                                    for (int cq = 0; cq < 4; ++cq) {
-                                        const uint32_t hm = __ballot_sync(0xffffffffu, cf[cq] != 0u);
-                                        if (hm == 0) continue;
-                                        if (__popc(hm) <= 4) {
-                                            // few rows beat this chain's thresholds (the steady state): each posts its own keys
+                                    if (__popc(hm) <= 6) {
+                                        // few rows beat a threshold (the steady state): each posts its own keys, no further votes
+                                        if (cfa != 0u) {
                                             const uint32_t s_add = strict ? 0u : 0x3c003c00u;
-                                            win_col_post2<0>(hb[4 * cq], e[4 * cq], ckb + 8 * cq, taub + 8 * cq, qrow, s_add);
-                                            win_col_post2<1>(hb[4 * cq + 1], e[4 * cq + 1], ckb + 8 * cq, taub + 8 * cq, qrow, s_add);
-                                            win_col_post2<2>(hb[4 * cq + 2], e[4 * cq + 2], ckb + 8 * cq, taub + 8 * cq, qrow, s_add);
-                                            win_col_post2<3>(hb[4 * cq + 3], e[4 * cq + 3], ckb + 8 * cq, taub + 8 * cq, qrow, s_add);
-                                            continue;
+#pragma unroll
+                                            for (int cq = 0; cq < 4; ++cq)
+                                                if (cf[cq] != 0u)
+                                                    win_chain_post_h(hb[4 * cq], hb[4 * cq + 1], hb[4 * cq + 2], hb[4 * cq + 3], thr_addr + 16u * cq, ckb + 8 * cq, taub + 8 * cq, qrow, s_add);
                                         }
+                                    } else {
                                         // many rows at once (the first query block of a pair): one winner per column and warp
+#pragma unroll 1
+                                        for (int gq = 0; gq < 8; ++gq) {
+                                            uint32_t x0 = hb[0], x1 = hb[1], cfg = cf[0];
 #pragma unroll
-                                        for (int g2 = 0; g2 < 2; ++g2) {
-                                            const uint32_t x0 = hb[4 * cq + 2 * g2], x1 = hb[4 * cq + 2 * g2 + 1];
-                                            const float y[4] = {fabsf(h_lo(x0)), fabsf(h_hi(x0)), fabsf(h_lo(x1)), fabsf(h_hi(x1))};      // pads: +inf, never a winner
-#pragma unroll
-                                            for (int c = 0; c < 4; ++c)
-                                                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sc_addr + (uint32_t)(c * 128) + (uint32_t)lane * 4u), "f"(y[c]) : "memory");
-                                            __syncwarp();
-                                            const int gq = 2 * cq + g2;
-                                            win_col_group_h(sc_addr, thr_addr + 8u * gq, ckb + 4 * gq, taub + 4 * gq, qrow0, strict ? 0.f : 1.f);
-                                            __syncwarp();
+                                            for (int k = 1; k < 8; ++k)
+                                                if (gq == k) { x0 = hb[2 * k]; x1 = hb[2 * k + 1]; cfg = cf[k >> 1]; }
+                                            if (__ballot_sync(0xffffffffu, cfg != 0u) == 0u) continue;
+                                            win_group_h(x0, x1, sc_addr, thr_addr + 8u * gq, ckb + 4 * gq, taub + 4 * gq, qrow0, strict ? 0.f : 1.f);
                                         }
                                     }
                                 }

@@ -8,8 +8,8 @@
 #   tests       pytest -m gpu            (TESTS_K="expr" restricts with -k)
 #   bench       python bench.py          (BENCH_ARGS="..." appended)
 #   launches    short bench under ncu: per-launch device time + DRAM bytes (launches.csv)
-#   ncu_surf    ncu --set full of the SURF tensor-core sweep at 2346 pairs of 8000 x 8000 (units_per_pair == 1)
-#   ncu_orb     ncu --set full of the ORB tensor-core sweep at 9453 pairs of 4000 x 4000
+#   ncu_surf    ncu --set full of the SURF tensor-core sweep (ENGINE=tc16|tc) at 2346 pairs of 8000 x 8000 (units_per_pair == 1)
+#   ncu_orb     ncu --set full of the ORB tensor-core sweep (ENGINE=tc16|tc) at 9453 pairs of 4000 x 4000
 #   zprobe      tools/orb_z_probe.py with the drain-only probe
 #   probes      pipeline probes ($ESFM_TC_DEBUG) of both tensor-core sweeps
 #   multi       N-device tests + N-rank bench (N = $N, default 2): use with gpurun --gpus N
@@ -32,22 +32,22 @@ bench)
   ( time BENCH_E2E_DEBUG=1 timeout 420 python bench.py $BENCH_ARGS ) > gpurun_out/bench.json 2> gpurun_out/bench.err
   cut -c1-400 gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
 launches)
-  timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k 'regex:^(sweep_|finalize|pack_)' -c 120 --csv \
+  timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "regex:^(sweep_|finalize|pack_)" -c 120 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --cpu-budget-s 0 --no-alt-engine --no-parity > gpurun_out/bench_under_ncu.log 2>&1
   tail -2 gpurun_out/launches.csv | cut -c1-200 ;;
 ncu_surf)
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:^sweep_l2_tc -c 1 -f -o gpurun_out/prof_l2_tc \
-      python tools/profile_step.py surf 69 8000 1 tc > gpurun_out/ncu_l2_tc.log 2>&1; tail -2 gpurun_out/ncu_l2_tc.log | cut -c1-200 ;;
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:^sweep_ -c 1 -f -o gpurun_out/prof_surf_${ENGINE:-tc16} \
+      python tools/profile_step.py surf 69 8000 1 ${ENGINE:-tc16} > gpurun_out/ncu_surf.log 2>&1; tail -2 gpurun_out/ncu_surf.log | cut -c1-200 ;;
 ncu_orb)
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:^sweep_l2_tc -c 1 -f -o gpurun_out/prof_ham_z \
-      python tools/profile_step.py orb 138 4000 1 > gpurun_out/ncu_ham_z.log 2>&1; tail -2 gpurun_out/ncu_ham_z.log | cut -c1-200 ;;
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:^sweep_ -c 1 -f -o gpurun_out/prof_orb_${ENGINE:-tc16} \
+      python tools/profile_step.py orb 138 4000 1 ${ENGINE:-tc16} > gpurun_out/ncu_orb.log 2>&1; tail -2 gpurun_out/ncu_orb.log | cut -c1-200 ;;
 zprobe)
   ORB_Z_PROBE_MODES=${ORB_Z_PROBE_MODES:-1} ORB_Z_PROBE_DRAIN=1 timeout 150 python tools/orb_z_probe.py > gpurun_out/orb_z_probe.txt 2>&1; cat gpurun_out/orb_z_probe.txt ;;
 probes)
   rm -f gpurun_out/tc_probes.txt
   for d in ${PROBE_FLAGS:-0 1 8 16 24}; do
-    ESFM_TC_DEBUG=$d timeout 60 python tools/profile_step.py surf 38 8000 3 tc 2>&1 | tail -1 | sed "s/^/surf debug=$d /" >> gpurun_out/tc_probes.txt
-    ESFM_TC_DEBUG=$d timeout 60 python tools/profile_step.py orb 60 4000 3 2>&1 | tail -1 | sed "s/^/orb  debug=$d /" >> gpurun_out/tc_probes.txt
+    ESFM_TC_DEBUG=$d timeout 60 python tools/profile_step.py surf 38 8000 3 ${ENGINE:-tc16} 2>&1 | tail -1 | sed "s/^/surf debug=$d /" >> gpurun_out/tc_probes.txt
+    ESFM_TC_DEBUG=$d timeout 60 python tools/profile_step.py orb 60 4000 3 ${ENGINE:-tc16} 2>&1 | tail -1 | sed "s/^/orb  debug=$d /" >> gpurun_out/tc_probes.txt
   done
   cat gpurun_out/tc_probes.txt ;;
 multi)

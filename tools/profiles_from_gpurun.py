@@ -36,7 +36,9 @@ if os.path.exists(lp):
         print(f"{k:46s} {v / 1e6:9.2f} ms {100 * v / s:5.1f}%")
     # device-resident sweep launches = the ones followed by a finalize whose grid is pairs_per_step (148 * 16 SURF, 148 * 64 ORB)
     traffic = {}
-    for key, name, fin_grid, pairs, alg in (("surf_tc", "sweep_l2_tc_kernel<1, 0>", "(2368, 1, 1)", 2368, 8000 * (544 + 256)),
+    for key, name, fin_grid, pairs, alg in (("surf_tc16", "sweep_win_kernel<0>", "(2368, 1, 1)", 2368, 8000 * (288 + 256)),
+                                            ("orb_tc16", "sweep_win_kernel<1>", "(9472, 1, 1)", 9472, 4000 * (288 + 32)),
+                                            ("surf_tc", "sweep_l2_tc_kernel<1, 0>", "(2368, 1, 1)", 2368, 8000 * (544 + 256)),
                                             ("orb_tc", "sweep_l2_tc_kernel<1, 2>", "(9472, 1, 1)", 9472, 4000 * (288 + 32)),
                                             ("surf", "sweep_l2_kernel", "(2368, 1, 1)", 2368, 8000 * 520),
                                             ("orb", "sweep_hamming_kernel", "(9472, 1, 1)", 9472, 4000 * 64)):
