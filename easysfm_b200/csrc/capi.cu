@@ -258,6 +258,7 @@ extern "C" int esfm_init(int device, void* cuda_stream, esfm_ctx_t** out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* z = getenv("ESFM_ORB_Z")) ctx->orb_z = atoi(z) != 0;
+    if (const char* z = getenv("ESFM_TWO_PHASE")) ctx->two_phase = atoi(z) != 0;
     if (const char* eng = getenv("ESFM_HAMMING_ENGINE")) {
         if (!strcmp(eng, "tc") || !strcmp(eng, "tensor")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_TC;
         else if (!strcmp(eng, "tc16")) ctx->hamming_engine = ESFM_HAMMING_ENGINE_TC16;
@@ -285,7 +286,7 @@ extern "C" int esfm_init(int device, void* cuda_stream, esfm_ctx_t** out) {
     e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) return bail(ESFM_ERR_CUDA, "cudaStreamCreate", e);
     for (ChunkBuf& cb : ctx->buf) {
-        for (cudaEvent_t* ev : {&cb.ev_t0, &cb.ev_t1, &cb.ev_t2}) {
+        for (cudaEvent_t* ev : {&cb.ev_t0, &cb.ev_t1, &cb.ev_t2, &cb.ev_v0, &cb.ev_v1}) {
             e = cudaEventCreate(ev);
             if (e != cudaSuccess) return bail(ESFM_ERR_CUDA, "cudaEventCreate", e);
         }
@@ -328,11 +329,12 @@ extern "C" int esfm_destroy(esfm_ctx_t* ctx) {
     }
     cudaFree(ctx->keys);
     cudaFree(ctx->col_thr);
+    cudaFree(ctx->gather_cnt);
     for (ChunkBuf& cb : ctx->buf) {
         cudaFree(cb.d_pairs); cudaFree(cb.d_pair_off); cudaFree(cb.d_pair_cnt); cudaFree(cb.d_cursor); cudaFree(cb.arena);
         if (cb.h_pairs) cudaFreeHost(cb.h_pairs);
         if (cb.h_meta) cudaFreeHost(cb.h_meta);
-        for (cudaEvent_t ev : {cb.ev_t0, cb.ev_t1, cb.ev_t2, cb.ev_meta, cb.ev_copied})
+        for (cudaEvent_t ev : {cb.ev_t0, cb.ev_t1, cb.ev_t2, cb.ev_v0, cb.ev_v1, cb.ev_meta, cb.ev_copied})
             if (ev) cudaEventDestroy(ev);
     }
     for (auto& b : ctx->pool) cudaFreeHost(b.ptr);
@@ -760,6 +762,8 @@ int ensure_scratch(esfm_ctx* ctx, const esfm_bank* b, const ChunkPlan& pl, int n
     ctx->keys_bytes = cap * sizeof(u64);
     if (b->kind == ESFM_KIND_F32X64 || use_tc(ctx, b))
         if (int rc = grow(&ctx->col_thr, &ctx->col_thr_elems, pl.chunk_pairs * (size_t)pl.stride)) return rc;
+    if (use_win(ctx, b))
+        if (int rc = grow(&ctx->gather_cnt, &ctx->gather_cnt_elems, pl.chunk_pairs)) return rc;
     const size_t arena_need = pl.chunk_pairs * (size_t)std::max(b->max_rows, 1);
     for (int k = 0; k < n_bufs; ++k) {
         ChunkBuf& cb = ctx->buf[k];
@@ -842,10 +846,14 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, ChunkBuf& cb, si
     const bool tc = use_tc(ctx, b);
     // ORB "Z" encoding: the column index rides in the key, so every frame must have at most 2^15 rows; else the +-1 encoding
     const bool win = tc && use_win(ctx, b);
+    // tc16 sweeps, cross-check in TWO PHASES: (1) a rows-only sweep + ratio test, (2) a second rows-only sweep with the roles swapped
+    // over just the train rows the survivors point at (gathered into the query operand), whose answer -- the nearest query row of
+    // each -- decides the cross-check.  The column minima, their thresholds and their events leave the hot sweep altogether.
+    const bool two_phase = win && cross_check && !knn_idx && ctx->two_phase;
     const int zmode = (tc && !win && b->kind == ESFM_KIND_B256 && ctx->orb_z && b->max_rows <= kTcZMaxRows) ? 1 : 0;
     if (tc) { if (int rc = ensure_tc_layout(ctx, b, win && b->kind == ESFM_KIND_F32X64 ? 2 : zmode)) return rc; }
     else if (b->kind == ESFM_KIND_F32X64) { if (int rc = ensure_kmajor_layout(ctx, b)) return rc; }
-    if (b->kind == ESFM_KIND_F32X64 || tc)
+    if ((b->kind == ESFM_KIND_F32X64 || tc) && !two_phase)
         // column thresholds start at "no bound yet" (a repeated byte): FFMA engine 0x7f7f7f7f = 3.39e38f; tensor-core engines
         // 0x6f6f6f6f = 7.4e28f for SURF (below its 1e30 pad-row norm), 0x47474747 = 51015f for ORB +-1 (above every real
         // value, below the pad rows), 0x4b4b4b4b = 1.33e7f for ORB "Z" (above every key); the FP16-accumulator ORB sweep keeps
@@ -867,7 +875,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, ChunkBuf& cb, si
     sp.col_thr = ctx->col_thr;
     sp.stride = pl.stride;
     sp.col_cap = pl.col_cap;
-    sp.need_cols = (cross_check || knn_idx) ? 1 : 0;
+    sp.need_cols = ((cross_check && !two_phase) || knn_idx) ? 1 : 0;
     if (const char* dbg = getenv("ESFM_TC_DEBUG")) sp.debug_flags = atoi(dbg);
     sp.tc_qtiles = 1;
     sp.tc_kind = zmode ? kTcKindB256Z : b->kind;
@@ -892,6 +900,9 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, ChunkBuf& cb, si
     fp.cross_check = cross_check ? 1 : 0;
     fp.b256_float_keys = (tc && b->kind == ESFM_KIND_B256) ? (zmode ? 2 : 1) : 0;
     fp.win_keys = win ? 1 : 0;
+    fp.phase = two_phase ? 1 : 0;
+    fp.gather = reinterpret_cast<int*>(ctx->col_thr);
+    fp.gather_cnt = ctx->gather_cnt;
     fp.arena = cb.arena;
     fp.arena_cap = cb.arena_cap;
     fp.cursor = cb.d_cursor;
@@ -902,6 +913,21 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, ChunkBuf& cb, si
     fp.knn_dist = knn_dist;
     e = launch_finalize(fp, ctx->stream);
     if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "finalize kernel launch failed: %s", cudaGetErrorString(e));
+    cb.two_phase = two_phase;
+    if (two_phase) {
+        SweepParams vp = sp;
+        vp.gather = fp.gather;
+        vp.gather_cnt = fp.gather_cnt;
+        if (ctx->profiling) CUDA_TRY(cudaEventRecord(cb.ev_v0, ctx->stream));
+        e = launch_sweep_win(vp, ctx->sm_count, ctx->stream);
+        if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "verification sweep launch failed: %s", cudaGetErrorString(e));
+        if (ctx->profiling) CUDA_TRY(cudaEventRecord(cb.ev_v1, ctx->stream));
+        fp.phase = 2;
+        e = launch_finalize(fp, ctx->stream);
+        if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "finalize (phase 2) kernel launch failed: %s", cudaGetErrorString(e));
+        ctx->stats.kernel_launches += 2;
+        ctx->stats.sweep_launches += 1;
+    }
     CUDA_TRY(cudaEventRecord(cb.ev_t2, ctx->stream));
     ctx->stats.kernel_launches += 2;
     ctx->stats.sweep_launches += 1;
@@ -914,6 +940,12 @@ int collect_timing(esfm_ctx* ctx, ChunkBuf& cb) {
     float a = 0.f, c = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&a, cb.ev_t0, cb.ev_t1));
     CUDA_TRY(cudaEventElapsedTime(&c, cb.ev_t1, cb.ev_t2));
+    if (cb.two_phase) {       // the verification sweep counts as sweep time, the two finalize launches as finalize time
+        float v = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&v, cb.ev_v0, cb.ev_v1));
+        a += v;
+        c -= v;
+    }
     ctx->stats.last_sweep_ms = a;
     ctx->stats.last_finalize_ms = c;
     ctx->stats.sweep_ms_total += a;

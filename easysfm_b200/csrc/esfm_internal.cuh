@@ -65,6 +65,11 @@ struct SweepParams {
                                 // (distance, column) keys from the MMA); tc_main holds that kind's images
     int tc_qtiles;              // TC sweep geometry: query tiles per block (always 1: the two-tile variant of round 1 is no longer built)
     int need_cols;              // 0: cross_check is off, nobody reads the column minima -- the tensor-core sweeps skip the column side
+    // sweep_win.cu, verification pass of the two-phase cross-check: the query operand is a GATHERED subset of the pair's TRAIN frame
+    // (gather[pair * stride + slot] = row of the train frame, gather_cnt[pair] rows), swept against the pair's QUERY frame; the best
+    // (value, slice) of every gathered row lands in the pair's 4th key array at [slot].  NULL = a normal sweep.
+    const int* gather;
+    const int* gather_cnt;
     int debug_flags;            // TC sweep pipeline probes ($ESFM_TC_DEBUG; results are WRONG when set): 1 = epilogue only drains,
                                 // 2 = no MMAs issued, 4 = no train-tile loads, 8 = no column events, 16 = no row selection, 32 = column events without their atomics, 64 = column events found but not handled
 };
@@ -90,6 +95,10 @@ struct FinalizeParams {
     int b256_float_keys;        // B256 keys from the tensor-core sweeps: 1 = high word is the float bits of 2 * hamming, 2 = of the packed key
                                 // z = kTcZ0 + 2^15 * hamming + column (tc_layout.cuh); 0 = the integer distance (XOR + POPC sweep)
     int win_keys;               // row keys carry a WINDOW of train columns instead of a column (sweep_win.cu; see finalize.cu)
+    int phase;                  // 0 = everything in one launch; two-phase cross-check (finalize.cu): 1 = ratio test + list of the train rows to verify,
+                                // 2 = verdicts of the verification sweep + compaction
+    int* gather;                // [n_pairs][stride] phase 1 out / the verification sweep's input
+    int* gather_cnt;            // [n_pairs]
     // optional raw knn output for one pair (esfm_knn2_pair)
     int32_t* knn_idx;
     float* knn_dist;

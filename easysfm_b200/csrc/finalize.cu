@@ -134,7 +134,7 @@ __device__ __forceinline__ void l2_scan(const float* __restrict__ qrow, const fl
 template <int KIND>
 __device__ __forceinline__ RowResult eval_row_win(const FinalizeParams& p, const u64* rk1, const u64* rk2, const u64* ck1, const float* qrows,
                                                   const float* trows, const uint4* qbits, const uint4* tbits, int q, int ft, int32_t* knn_idx,
-                                                  float* knn_dist) {
+                                                  float* knn_dist, bool with_cross_check = true) {
     RowResult r;
     r.keep = false;
     r.t1 = -1;
@@ -196,7 +196,7 @@ __device__ __forceinline__ RowResult eval_row_win(const FinalizeParams& p, const
         knn_dist[2 * q] = d1; knn_dist[2 * q + 1] = d2;
     }
     if (!pass) return r;
-    if (p.cross_check) {
+    if (p.cross_check && with_cross_check) {
         const u64 c1 = ck1[i1];
         if (c1 == kKeyInit) return r;
         const int best = (int)(uint32_t)c1;
@@ -210,6 +210,35 @@ __device__ __forceinline__ RowResult eval_row_win(const FinalizeParams& p, const
     r.t1 = i1;
     r.d1 = d1;
     return r;
+}
+
+// Two-phase cross-check, phase 2: is query row q (at exact distance d1) the nearest query row of train row t1, lowest index on ties?
+// `vk` = what the verification sweep found for t1: (value bits, slice of QUERY rows holding the first row at the column minimum).
+template <int KIND>
+__device__ __forceinline__ bool verify_col(u64 vk, int q, int t1, float d1, const float* qrows, const float* trows, const uint4* qbits,
+                                           const uint4* tbits, int fq) {
+    if (vk == kKeyInit) return false;       // (cannot happen: the sweep saw at least row q)
+    int c0, c1;
+    win_range(vk, fq, c0, c1);
+    if (KIND == ESFM_KIND_B256) {
+        const float cv = 0.5f * __uint_as_float((uint32_t)(vk >> 32));
+        if (cv < d1) return false;          // another query row is nearer
+        if (cv > d1 || q < c0) return true; // (cannot happen: q itself is at d1)
+        if (q >= c1) return false;          // the first row at this distance is in an earlier slice
+        const uint4 t0 = __ldg(tbits + (size_t)t1 * 2), t1b = __ldg(tbits + (size_t)t1 * 2 + 1);
+        for (int r = c0; r < q; ++r)
+            if (b256_hamming(t0, t1b, qbits + (size_t)r * 2) == (int)d1) return false;
+        return true;
+    } else {
+        // the sweep ranked the column in expansion form: decide between its winner's slice and q in direct form, (distance, index) order
+        const float* trow = trows + (size_t)t1 * kDim;
+        for (int r = c0; r < c1; ++r) {
+            if (r == q) continue;
+            const float d = l2_direct(qrows + (size_t)r * kDim, trow);
+            if (d < d1 || (d == d1 && r < q)) return false;
+        }
+        return true;
+    }
 }
 
 template <int KIND>
@@ -238,7 +267,9 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizePar
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     const bool no_ratio = p.ratio == __longlong_as_double(0x7ff0000000000000LL);
+    __shared__ unsigned int s_targets;
     if (fq == 0 || ft < (no_ratio ? 1 : 2)) {  // F7: no second neighbour exists
+        if (p.phase == 1 && threadIdx.x == 0) p.gather_cnt[pair] = 0;
         if (p.knn_idx) {
             for (int q = threadIdx.x; q < fq; q += kFinThreads) {
                 RowResult r = p.win_keys ? eval_row_win<KIND>(p, rk1, rk2, ck1, qrows, trows, qbits, tbits, q, ft, p.knn_idx, p.knn_dist)
@@ -255,11 +286,46 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizePar
 
     // pass 1: evaluate every query row; stash the verdict in the row's first key slot
     unsigned int mine = 0;
+    if (p.phase == 2) {
+        // Two-phase cross-check, phase 2: the survivors of phase 1 against what the verification sweep found for their train rows
+        // (ck1[t] = 2^40 | slot of train row t in the gather list, 4th key array [slot] = the sweep's answer)
+        for (int q = threadIdx.x; q < fq; q += kFinThreads) {
+            const u64 v = rk1[q];
+            if (v == kKeyInit) continue;
+            const int t1 = (int)(uint32_t)v;
+            const float d1 = __uint_as_float((uint32_t)(v >> 32));
+            const u64 vk = ck2[(uint32_t)ck1[t1]];
+            if (verify_col<KIND>(vk, q, t1, d1, qrows, trows, qbits, tbits, fq)) mine += 1u;
+            else rk1[q] = kKeyInit;
+        }
+    } else {
     for (int q = threadIdx.x; q < fq; q += kFinThreads) {
-        const RowResult r = p.win_keys ? eval_row_win<KIND>(p, rk1, rk2, ck1, qrows, trows, qbits, tbits, q, ft, p.knn_idx, p.knn_dist)
+        const RowResult r = p.win_keys ? eval_row_win<KIND>(p, rk1, rk2, ck1, qrows, trows, qbits, tbits, q, ft, p.knn_idx, p.knn_dist, p.phase == 0)
                                        : eval_row<KIND>(p, rk1, rk2, ck1, ck2, qrows, trows, q, fq, p.knn_idx, p.knn_dist);
         rk1[q] = r.keep ? make_key(__float_as_uint(r.d1), (uint32_t)r.t1) : kKeyInit;
         mine += r.keep ? 1u : 0u;
+        // phase 1: every train row some survivor points at is claimed by its lowest such query row ...
+        if (p.phase == 1 && r.keep) atomicMin(const_cast<u64*>(ck1) + r.t1, (u64)q);
+    }
+    }
+    if (p.phase == 1) {
+        // ... and the claimants put their train rows on the pair's list for the verification sweep (any order: the slot is looked up)
+        if (threadIdx.x == 0) s_targets = 0;
+        __syncthreads();
+        int* gl = p.gather + (size_t)pair * p.stride;
+        for (int q = threadIdx.x; q < fq; q += kFinThreads) {
+            const u64 v = rk1[q];
+            if (v == kKeyInit) continue;
+            const int t1 = (int)(uint32_t)v;
+            if (ck1[t1] == (u64)q) {
+                const unsigned int slot = atomicAdd(&s_targets, 1u);
+                gl[slot] = t1;
+                const_cast<u64*>(ck1)[t1] = (1ull << 40) | slot;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) p.gather_cnt[pair] = (int)s_targets;
+        return;
     }
     // block total -> one arena allocation per pair
     unsigned int wsum = __reduce_add_sync(0xffffffffu, mine);

@@ -60,6 +60,8 @@ struct ChunkBuf {
     PairDesc* h_pairs = nullptr;   size_t h_pairs_cap = 0;     // launch-ordered pair list (upload)
     unsigned char* h_meta = nullptr; size_t h_meta_bytes = 0;  // cursor + offsets + counts (download)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_t2 = nullptr;   // sweep start / sweep end / finalize end
+    cudaEvent_t ev_v0 = nullptr, ev_v1 = nullptr;                    // two-phase cross-check: verification sweep start / end
+    bool two_phase = false;                      // the chunk last run here had a verification sweep (ev_v0 / ev_v1 are valid)
     cudaEvent_t ev_meta = nullptr, ev_copied = nullptr;
     bool copy_pending = false;                   // a device->host copy of the arena may still be in flight (ev_copied)
 };
@@ -82,6 +84,9 @@ struct esfm_ctx {
     // device scratch, grown on demand
     esfm::u64* keys = nullptr;     size_t keys_bytes = 0;
     uint32_t* col_thr = nullptr;   size_t col_thr_elems = 0;
+    int* gather_cnt = nullptr;     size_t gather_cnt_elems = 0;     // two-phase cross-check: train rows to verify, per pair of the chunk
+    int two_phase = 1;                     // cross-check of the tc16 sweeps as ratio test -> verification sweep over the surviving train rows
+                                           // ($ESFM_TWO_PHASE=0: column minima inside the one sweep, as the other engines do)
     esfm::ChunkBuf buf[2];
     // a pool of large pinned buffers that banks (upload staging) and results (downloaded matches) borrow, so steady-state
     // calls never allocate or zero-fill host memory

@@ -138,6 +138,38 @@ __device__ __forceinline__ void win_merge(float p1, int id1, float p2, int id2, 
     k1 = fmaxf(k1, p1);
 }
 
+// work decoding: a normal sweep takes (query frame, train frame) from the pair list; the verification sweep of the two-phase
+// cross-check swaps the roles and reads its query rows through the pair's gather list
+struct WinUnit {
+    int pair, q_frame, t_frame;
+    int fq;              // query rows of this unit's pair (gathered rows in a verification sweep)
+    int ntt;
+    int qb0, qb1;        // query TILES [qb0, qb1) of this unit
+};
+__device__ __forceinline__ WinUnit win_decode_unit(const SweepParams& p, int unit) {
+    WinUnit u;
+    u.pair = unit / p.units_per_pair;
+    const int part = unit - u.pair * p.units_per_pair;
+    const PairDesc pd = p.pairs[u.pair];
+    int nqt;
+    if (p.gather) {
+        u.q_frame = pd.t_frame;
+        u.t_frame = pd.q_frame;
+        u.fq = p.gather_cnt[u.pair];
+        nqt = (u.fq + kTile - 1) / kTile;
+    } else {
+        u.q_frame = pd.q_frame;
+        u.t_frame = pd.t_frame;
+        u.fq = p.frame_rows[pd.q_frame];
+        nqt = p.frame_tile_off[pd.q_frame + 1] - p.frame_tile_off[pd.q_frame];
+    }
+    u.ntt = p.frame_tile_off[u.t_frame + 1] - p.frame_tile_off[u.t_frame];
+    u.qb0 = (int)((long long)nqt * part / p.units_per_pair);
+    u.qb1 = (int)((long long)nqt * (part + 1) / p.units_per_pair);
+    if (p.frame_rows[u.t_frame] < 1) u.qb1 = u.qb0;
+    return u;
+}
+
 }  // namespace
 
 template <int KIND>
@@ -194,7 +226,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
         if (lane == 0) {
             uint32_t g = 0;
             for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-                const TcUnit u = tc_decode_unit(p, unit);
+                const WinUnit u = win_decode_unit(p, unit);
                 const unsigned char* timg = p.tc_main + (size_t)p.frame_tile_off[u.t_frame] * kWinTileBytes;
                 const unsigned char* tauc = reinterpret_cast<const unsigned char*>(p.col_thr) + (size_t)u.pair * p.stride * (kOrb ? 2 : 4);
                 for (int qt = u.qb0; qt < u.qb1; ++qt) {
@@ -207,10 +239,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
                         else
                             bulk_g2s(Ts + (size_t)st * kWinTileBytes, timg + (size_t)tt * kWinTileBytes, kWinTileBytes, &fullT[st]);
                         // the running column thresholds of this tile ride along in their own ring (a stale snapshot is only looser)
-                        const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
-                        if (nosleep) mbar_wait_sleep<0>(&thrEmpty[ts], tph ^ 1); else mbar_wait_sleep<kTcSleepProducer>(&thrEmpty[ts], tph ^ 1);
-                        mbar_arrive_expect_tx(&thrFull[ts], kThrBytes);
-                        bulk_g2s(Thr + ts * kTcThrBytes, tauc + (size_t)tt * kThrBytes, kThrBytes, &thrFull[ts]);
+                        if (p.need_cols) {
+                            const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
+                            if (nosleep) mbar_wait_sleep<0>(&thrEmpty[ts], tph ^ 1); else mbar_wait_sleep<kTcSleepProducer>(&thrEmpty[ts], tph ^ 1);
+                            mbar_arrive_expect_tx(&thrFull[ts], kThrBytes);
+                            bulk_g2s(Thr + ts * kTcThrBytes, tauc + (size_t)tt * kThrBytes, kThrBytes, &thrFull[ts]);
+                        }
                     }
                 }
             }
@@ -224,7 +258,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
         const uint64_t tad0 = tc_desc_nosw(smem_u32(Ts) + kWinMainBytes, 128, kTcAugGroupBytes);
         uint32_t g = 0, qn = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const TcUnit u = tc_decode_unit(p, unit);
+            const WinUnit u = win_decode_unit(p, unit);
             for (int qt = u.qb0; qt < u.qb1; ++qt, ++qn) {
                 for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                     const uint32_t st = g % kWinStages, ph = (g / kWinStages) & 1;
@@ -272,11 +306,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
         unsigned char* qa = Qa + (trow >> 3) * kTcAugGroupBytes + (trow & 7) * 16;
         uint32_t quse = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const TcUnit u = tc_decode_unit(p, unit);
-            const int fq = p.frame_rows[u.q_frame];
+            const WinUnit u = win_decode_unit(p, unit);
+            const int fq = u.fq;
+            const int* gl = p.gather ? p.gather + (size_t)u.pair * p.stride : nullptr;
             for (int qt = u.qb0; qt < u.qb1; ++qt) {
-                const int r = qt * kTile + trow;
-                const bool valid = r < fq;
+                const int slot = qt * kTile + trow;
+                const bool valid = slot < fq;
+                const int r = (gl && valid) ? __ldg(gl + slot) : slot;      // verification sweep: the slot's row of the (original) train frame
                 if (kOrb) {
                     const uint4* qbits = p.rows_b256 + (size_t)p.frame_row_off[u.q_frame] * 2;
                     uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
@@ -356,7 +392,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
         const uint32_t sc_addr = smem_u32(colsc) + (uint32_t)warp * (kTcScCols * 32 * 4);
         uint32_t g = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const TcUnit u = tc_decode_unit(p, unit);
+            const WinUnit u = win_decode_unit(p, unit);
             u64* rk1 = p.keys + (size_t)u.pair * 4 * p.stride;
             u64* rk2 = rk1 + p.stride;
             u64* ck1 = rk2 + p.stride;
@@ -367,7 +403,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
                 int w1 = -1, w2 = -1;
                 for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                     const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
-                    mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);
+                    if (p.need_cols) mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);       // (no cross-check: no thresholds travel)
                     const uint32_t as = g % kWinAccStages, aph = (g / kWinAccStages) & 1;
                     mbar_wait_sleep<kTcSleepEpilogue>(&accFull[as], aph);
                     if (warp == 0 && tt == u.ntt - 1) named_bar_arrive(2, 128 + 32);     // the query slot may be refilled (see the writers)
@@ -527,7 +563,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_relaxed(&thrEmpty[ts]);      // last read of this threshold snapshot
+                    if (p.need_cols && lane == 0) mbar_arrive_relaxed(&thrEmpty[ts]);      // last read of this threshold snapshot
                 }
                 // ---- end of the sweep for this query block: merge the four column parts of every row (64-bit shared-memory atomics
                 //      on packed keys, "smaller = nearer": the smallest ends in mkey[0], the smallest of all the losers in mkey[1]) ----
@@ -543,8 +579,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");
                 if (part == 0) {
-                    rk1[qrow] = mkey[trow];
-                    rk2[qrow] = mkey[kTile + trow];
+                    if (p.gather) {
+                        rk1[3 * (size_t)p.stride + qrow] = mkey[trow];      // verification sweep: the best (value, slice) of gathered row `qrow`
+                    } else {
+                        rk1[qrow] = mkey[trow];
+                        rk2[qrow] = mkey[kTile + trow];
+                    }
                     mkey[trow] = kKeyInit;
                     mkey[kTile + trow] = kKeyInit;
                 }

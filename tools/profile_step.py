@@ -30,7 +30,7 @@ bank.commit_device()
 pairs = scheduler.all_pairs(n_images)
 for r in range(repeats):
     t0 = time.perf_counter()
-    res = bank.match_pairs(pairs, 0.8, True, device_resident=True)
+    res = bank.match_pairs(pairs, 0.8, os.environ.get("PROFILE_CROSS_CHECK", "1") != "0", device_resident=True)
     n = res.n_matches
     res.close()
     ctx.synchronize()
