@@ -925,8 +925,7 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, ChunkBuf& cb, si
         fp.phase = 2;
         e = launch_finalize(fp, ctx->stream);
         if (e != cudaSuccess) return fail(ESFM_ERR_CUDA, "finalize (phase 2) kernel launch failed: %s", cudaGetErrorString(e));
-        ctx->stats.kernel_launches += 2;
-        ctx->stats.sweep_launches += 1;
+        ctx->stats.kernel_launches += 2;      // (sweep_launches counts chunks swept: the verification sweep's time is added to its chunk's)
     }
     CUDA_TRY(cudaEventRecord(cb.ev_t2, ctx->stream));
     ctx->stats.kernel_launches += 2;

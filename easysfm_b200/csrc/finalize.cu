@@ -19,6 +19,13 @@ namespace esfm {
 namespace {
 
 constexpr int kFinThreads = 256;
+constexpr int kFinBuckets = 1024;      // two-phase cross-check: histogram buckets of the sweep's ranking values
+// ORB: value = 2 * hamming -> bucket = hamming (exact); SURF: value = 1/2 d^2 in [0, 2] for unit-norm rows -> 512 buckets per unit,
+// everything beyond in the last one (conservative: a coarser bucket only sends more train rows to the verification sweep)
+template <int KIND> __device__ __forceinline__ int fin_bucket(float v) {
+    if (KIND == ESFM_KIND_B256) return min(kFinBuckets - 1, max(0, (int)(0.5f * v)));
+    return min(kFinBuckets - 1, max(0, (int)(v * 512.f)));
+}
 
 struct RowResult {
     int t1;
@@ -268,6 +275,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizePar
 
     const bool no_ratio = p.ratio == __longlong_as_double(0x7ff0000000000000LL);
     __shared__ unsigned int s_targets;
+    __shared__ unsigned int s_hist[2][kFinBuckets];
     if (fq == 0 || ft < (no_ratio ? 1 : 2)) {  // F7: no second neighbour exists
         if (p.phase == 1 && threadIdx.x == 0) p.gather_cnt[pair] = 0;
         if (p.knn_idx) {
@@ -294,34 +302,72 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizePar
             if (v == kKeyInit) continue;
             const int t1 = (int)(uint32_t)v;
             const float d1 = __uint_as_float((uint32_t)(v >> 32));
+            if (rk2[q] == 1) { mine += 1u; continue; }           // decided in phase 1
             const u64 vk = ck2[(uint32_t)ck1[t1]];
             if (verify_col<KIND>(vk, q, t1, d1, qrows, trows, qbits, tbits, fq)) mine += 1u;
             else rk1[q] = kKeyInit;
         }
     } else {
+    if (p.phase == 1) {
+        for (int i = threadIdx.x; i < 2 * kFinBuckets; i += kFinThreads) (&s_hist[0][0])[i] = 0u;
+        if (threadIdx.x == 0) s_targets = 0;
+        __syncthreads();
+    }
     for (int q = threadIdx.x; q < fq; q += kFinThreads) {
+        u64 k1 = kKeyInit, k2 = kKeyInit;
+        if (p.phase == 1) { k1 = rk1[q]; k2 = rk2[q]; }        // (eval_row_win overwrites nothing; read before rk1[q] is restated below)
         const RowResult r = p.win_keys ? eval_row_win<KIND>(p, rk1, rk2, ck1, qrows, trows, qbits, tbits, q, ft, p.knn_idx, p.knn_dist, p.phase == 0)
                                        : eval_row<KIND>(p, rk1, rk2, ck1, ck2, qrows, trows, q, fq, p.knn_idx, p.knn_dist);
         rk1[q] = r.keep ? make_key(__float_as_uint(r.d1), (uint32_t)r.t1) : kKeyInit;
         mine += r.keep ? 1u : 0u;
-        // phase 1: every train row some survivor points at is claimed by its lowest such query row ...
-        if (p.phase == 1 && r.keep) atomicMin(const_cast<u64*>(ck1) + r.t1, (u64)q);
+        if (p.phase == 1) {
+            // Who could beat a survivor (q, t) at its own train row t?  A row whose NEAREST train row is t (another survivor: settled by
+            // the claims below; a row that failed the ratio test: counted in histogram A by its best value), or a row for which t is at
+            // best second (then its second-best value is <= its distance to t: histogram B, every row).  A survivor whose distance
+            // lies below every such value needs no verification sweep.
+            if (k2 != kKeyInit) atomicAdd(&s_hist[1][fin_bucket<KIND>(__uint_as_float((uint32_t)(k2 >> 32)))], 1u);
+            if (!r.keep && k1 != kKeyInit) atomicAdd(&s_hist[0][fin_bucket<KIND>(__uint_as_float((uint32_t)(k1 >> 32)))], 1u);
+            // every train row some survivor points at is claimed by the nearest such query row (lowest index on ties)
+            if (r.keep) atomicMin(const_cast<u64*>(ck1) + r.t1, make_key(__float_as_uint(r.d1), (uint32_t)q));
+        }
     }
     }
     if (p.phase == 1) {
-        // ... and the claimants put their train rows on the pair's list for the verification sweep (any order: the slot is looked up)
-        if (threadIdx.x == 0) s_targets = 0;
         __syncthreads();
+        // inclusive prefix sums of (A + B) over the buckets: s_hist[0][b] = rows that may be at least as near as bucket b
+        if (warp == 0) {
+            constexpr int kPer = kFinBuckets / 32;
+            unsigned int loc = 0;
+            for (int i = 0; i < kPer; ++i) loc += s_hist[0][lane * kPer + i] + s_hist[1][lane * kPer + i];
+            unsigned int incl = loc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            unsigned int run = incl - loc;
+            for (int i = 0; i < kPer; ++i) {
+                run += s_hist[0][lane * kPer + i] + s_hist[1][lane * kPer + i];
+                s_hist[0][lane * kPer + i] = run;
+            }
+        }
+        __syncthreads();
+        // survivors: beaten by another survivor -> dropped; below every possible rival -> decided (state 1); else its train row goes on
+        // the pair's list for the verification sweep (state 2; any order: the slot is looked up through ck1)
         int* gl = p.gather + (size_t)pair * p.stride;
         for (int q = threadIdx.x; q < fq; q += kFinThreads) {
             const u64 v = rk1[q];
             if (v == kKeyInit) continue;
             const int t1 = (int)(uint32_t)v;
-            if (ck1[t1] == (u64)q) {
-                const unsigned int slot = atomicAdd(&s_targets, 1u);
-                gl[slot] = t1;
-                const_cast<u64*>(ck1)[t1] = (1ull << 40) | slot;
-            }
+            const float d1 = __uint_as_float((uint32_t)(v >> 32));
+            if (ck1[t1] != make_key((uint32_t)(v >> 32), (uint32_t)q)) { rk1[q] = kKeyInit; continue; }
+            // (SURF: the histograms hold sweep-form 1/2 d^2, within ~1e-6 of the direct form: compare with a margin)
+            const float mine_v = KIND == ESFM_KIND_B256 ? 2.f * d1 : 0.5f * d1 * d1 + 1e-5f;
+            if (s_hist[0][fin_bucket<KIND>(mine_v)] == 0u) { rk2[q] = 1; continue; }
+            const unsigned int slot = atomicAdd(&s_targets, 1u);
+            gl[slot] = t1;
+            const_cast<u64*>(ck1)[t1] = (1ull << 40) | slot;
+            rk2[q] = 2;
         }
         __syncthreads();
         if (threadIdx.x == 0) p.gather_cnt[pair] = (int)s_targets;

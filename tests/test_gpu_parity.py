@@ -263,3 +263,75 @@ def test_hamming_engines_are_byte_identical(ctx):
         else:
             os.environ["ESFM_ORB_Z"] = old
     assert per == out["popc"]
+
+
+# --------------------------------------------------------------------------------------------------
+# cross-check under contention: many query rows compete for the same train rows
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["orb", "surf"])
+def test_cross_check_contention(ctx, kind):
+    """The tc16 sweeps decide the cross-check without column minima: survivors of the ratio test claim their train row, histograms
+    of every row's best / second-best value tell which survivors could still be beaten, and only those go through a verification
+    sweep (finalize.cu, two-phase).  Here several query rows -- also ones that FAIL the ratio test, and ones whose second neighbour
+    is the contested train row -- sit at graded distances from the same train rows, and exact duplicates tie: every path must agree
+    with the oracle, for all engines, with and without the ratio test."""
+    rng = np.random.default_rng(17)
+    nt, nq = 1100, 1500
+    if kind == "orb":
+        T = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+        Q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+
+        def flip(row, nbits):
+            r = row.copy()
+            for b in rng.choice(256, nbits, replace=False):
+                r[b >> 3] ^= np.uint8(1 << (b & 7))
+            return r
+        for k in range(300):                      # 2-5 queries per contested train row, at 0..60 flipped bits
+            t = int(rng.integers(0, 200))
+            Q[int(rng.integers(0, nq))] = flip(T[t], int(rng.integers(0, 60)))
+        for k in range(40):                       # exact duplicates of one train row in several query rows (index tie-break)
+            Q[int(rng.integers(0, nq))] = T[int(rng.integers(200, 220))]
+        for k in range(60):                       # a query between TWO train rows: fails the ratio test but is near both
+            a, b = int(rng.integers(0, 200)), int(rng.integers(220, 260))
+            T[b] = flip(T[a], 6)
+            Q[int(rng.integers(0, nq))] = flip(T[a], 3)
+    else:
+        T = rng.standard_normal((nt, 64)).astype(np.float32)
+        T /= np.linalg.norm(T, axis=1, keepdims=True)
+        Q = rng.standard_normal((nq, 64)).astype(np.float32)
+        Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+
+        def jitter(row, s):
+            r = row + s * rng.standard_normal(64).astype(np.float32)
+            return (r / np.linalg.norm(r)).astype(np.float32)
+        for k in range(300):
+            t = int(rng.integers(0, 200))
+            Q[int(rng.integers(0, nq))] = jitter(T[t], float(rng.uniform(0.0, 0.12)))
+        for k in range(40):
+            Q[int(rng.integers(0, nq))] = T[int(rng.integers(200, 220))]
+        for k in range(60):
+            a, b = int(rng.integers(0, 200)), int(rng.integers(220, 260))
+            T[b] = jitter(T[a], 0.01)
+            Q[int(rng.integers(0, nq))] = jitter(T[a], 0.005)
+    removed = 0
+    for ratio in (0.8, 1.0, float("inf")):
+        ref = oracle.match(Q, T, ratio, True)
+        got = ctx.match_descriptors(Q, T, ratio, True)
+        if kind == "orb":
+            assert_matches_equal(got, ref)
+        else:
+            justify_l2(Q, T, ratio, True, got, ref)
+        removed += len(oracle.match(Q, T, ratio, False)) - len(ref)
+    assert removed > 300          # the cross-check really had something to remove
+    # all pairs of a small bank built from the same rows (one launch, several pairs, both orientations of the contention)
+    frames = [Q[:700], T[:500], Q[700:], T[500:]]
+    bank = ctx.bank_from_frames(frames)
+    res = bank.match_all_pairs(0.8, True)
+    for k in range(res.n_pairs):
+        i, j, m = res.pair_at(k)
+        ref = oracle.match(frames[i], frames[j], 0.8, True)
+        if kind == "orb":
+            assert_matches_equal(m, ref)
+        else:
+            justify_l2(frames[i], frames[j], 0.8, True, m, ref)
+    bank.close()
