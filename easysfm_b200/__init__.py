@@ -32,5 +32,6 @@ from .capi import (  # noqa: F401
 )
 from .feature_matching import FeatureMatching, Frame, pairwise_match_descriptors  # noqa: F401
 from .scheduler import all_pairs, match_all_pairs, shard_pairs  # noqa: F401
+from .motion import MotionEstimator  # noqa: F401
 
 __version__ = "0.2.0"

@@ -69,6 +69,20 @@ class MultiTiming(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class TwoViewParams(ctypes.Structure):
+    _fields_ = [("ransac_thre", c_double), ("ransac_prob", c_double), ("cheirality_dist", c_double), ("seed", c_uint64), ("first_pair", c_uint64),
+                ("max_iters", c_int32), ("random_rate", c_int32)]
+
+
+class TwoView(ctypes.Structure):
+    _fields_ = [("E", c_double * 9), ("R", c_double * 9), ("t", c_double * 3), ("depth", c_double), ("n_matches", c_int32), ("n_inliers", c_int32),
+                ("n_good", c_int32), ("iters", c_int32), ("ok", c_int32), ("reserved", c_int32)]
+
+
+TWO_VIEW_DTYPE = np.dtype([("E", "<f8", (3, 3)), ("R", "<f8", (3, 3)), ("t", "<f8", (3,)), ("depth", "<f8"), ("n_matches", "<i4"), ("n_inliers", "<i4"),
+                           ("n_good", "<i4"), ("iters", "<i4"), ("ok", "<i4"), ("reserved", "<i4")])
+assert TWO_VIEW_DTYPE.itemsize == ctypes.sizeof(TwoView)
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header.
 SIGNATURES = {
     "esfm_abi_version": (c_int, []),
@@ -118,6 +132,8 @@ SIGNATURES = {
     "esfm_results_copy_all": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int64)]),
     "esfm_results_digests": (c_int, [c_void_p, POINTER(c_uint64)]),
     "esfm_results_segment_count": (c_int, [c_void_p, POINTER(c_int)]),
+    "esfm_two_view_default_params": (c_int, [POINTER(TwoViewParams)]),
+    "esfm_two_view_batch": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(TwoViewParams), c_void_p, c_void_p]),
     "esfm_results_segment_at": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_int64)]),
     "esfm_results_pair_layout": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int64)]),
     "esfm_results_device_matches": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64)]),
@@ -272,6 +288,32 @@ class Context:
 
     def bank(self, kind: int, n_frames: int) -> "Bank":
         return Bank(self, kind, n_frames)
+
+    def two_view_batch(self, pair_off, pts1, pts2, K, ransac_thre=1.0, ransac_prob=0.99, max_iters=1000, seed=0, first_pair=0, random_rate=1,
+                       cheirality_dist=50.0):
+        """esfm_two_view_batch: the reference's estimate2D2D_E5P_RANSAC + getDepthFast for a batch of image pairs.
+        pair_off: int64[n_pairs + 1]; pts1 / pts2: float32[total, 2] matched pixel coordinates (query / train keypoints of every match, all
+        pairs back to back); K: 3 x 3 (one camera) or n_pairs x 3 x 3.  Returns (inlier mask uint8[total], per-pair structured array)."""
+        pair_off = np.ascontiguousarray(pair_off, np.int64)
+        n_pairs = len(pair_off) - 1
+        pts1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        pts2 = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+        K = np.ascontiguousarray(K, np.float64)
+        k_per_pair = 1 if K.ndim == 3 else 0
+        if k_per_pair and K.shape[0] != n_pairs:
+            raise ValueError("K must be 3 x 3 or n_pairs x 3 x 3")
+        total = int(pair_off[-1]) if n_pairs >= 0 and len(pair_off) else 0
+        if len(pts1) != total or len(pts2) != total:
+            raise ValueError("pts1 / pts2 must have pair_off[-1] rows")
+        prm = TwoViewParams()
+        _check(self._lib.esfm_two_view_default_params(ctypes.byref(prm)))
+        prm.ransac_thre, prm.ransac_prob, prm.cheirality_dist = float(ransac_thre), float(ransac_prob), float(cheirality_dist)
+        prm.seed, prm.first_pair, prm.max_iters, prm.random_rate = int(seed), int(first_pair), int(max_iters), int(random_rate)
+        mask = np.zeros(max(total, 1), np.uint8)
+        out = np.zeros(max(n_pairs, 1), TWO_VIEW_DTYPE)
+        _check(self._lib.esfm_two_view_batch(self._h, n_pairs, pair_off.ctypes.data, pts1.ctypes.data, pts2.ctypes.data, K.ctypes.data, k_per_pair,
+                                             ctypes.byref(prm), mask.ctypes.data, out.ctypes.data))
+        return mask[:total], out[:n_pairs]
 
     def bank_from_frames(self, frames) -> "Bank":
         """frames: sequence of 2-D numpy arrays (all float32 x64 or all uint8 x32)."""

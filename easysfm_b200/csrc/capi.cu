@@ -158,7 +158,7 @@ uint64_t digest_matches(const esfm_dmatch_t* m, int n) {
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
-static int set_device(esfm_ctx* ctx) {
+int esfm::set_device(esfm_ctx* ctx) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     return ESFM_OK;
 }

@@ -18,6 +18,7 @@ namespace esfm {
 // ---- error plumbing: one message per host thread (esfm_last_error) -------------------------------------------------
 extern thread_local std::string g_last_error;
 int fail(int code, const char* fmt, ...);
+int set_device(struct ::esfm_ctx* ctx);
 
 #define CUDA_TRY(expr)                                                                                          \
     do {                                                                                                        \

@@ -326,6 +326,41 @@ int esfm_multi_match_all_pairs(esfm_multi_bank_t* bank, double ratio, int cross_
 int esfm_multi_match_pairs(esfm_multi_bank_t* bank, const esfm_pair_t* pairs, int64_t n_pairs, double ratio, int cross_check,
                            int keep, esfm_results_t** results);
 
+/* ---- two-view geometric verification of the matches, batched over image pairs ------------------------------------------
+ * Replaces MotionEstimator::estimate2D2D_E5P_RANSAC (cpp_code/src/estimate_motion.cpp:27-97; decl cpp_code/include/estimate_motion.h:17-20:
+ * cv::findEssentialMat(pts1, pts2, K, RANSAC, ransac_prob, ransac_thre, mask) + cv::recoverPose) and MotionEstimator::getDepthFast
+ * (:234-283) as called per pair at cpp_code/test/sfm.cpp:163-166.  The caller gathers the matched keypoint coordinates exactly as the
+ * reference does (:36-40: pts1[k] = frame_1.keypoints[matches[k].queryIdx].pt, pts2[k] = frame_2.keypoints[matches[k].trainIdx].pt), for
+ * all pairs back to back: pair p owns points [pair_off[p], pair_off[p + 1]).  K is the 3 x 3 camera matrix, row-major (frame_t::K_cam):
+ * one for all pairs (k_per_pair = 0) or one per pair.  Outputs: inlier_mask[k] = 1 iff match k is an inlier of the essential matrix
+ * (what the reference copies into inlier_matches, :54-60), and per pair E, the recovered pose T_21 = [R | t], the inlier / cheirality
+ * counts and getDepthFast's mean relative depth.  The RANSAC is OpenCV's (5-point minimal solver, Sampson error, threshold scaled by the
+ * mean focal length, adaptive iteration count, first best model wins) except for its random sample sequence, which cannot be restated:
+ * hypothesis h of pair p draws its five matches from a counter-based generator keyed by (seed, first_pair + p, h), so results are
+ * reproducible and independent of batching.  Pairs with fewer than 5 matches, or without a model that has more than 4 inliers, get ok = 0. */
+typedef struct esfm_two_view_params_t {
+    double ransac_thre;       /* pixels; estimate_motion.h:20 default 1.0 (sfm.cpp passes ransac_reproj_distance) */
+    double ransac_prob;       /* 0.99 */
+    double cheirality_dist;   /* cv::recoverPose distanceThresh, 50 */
+    uint64_t seed;
+    uint64_t first_pair;      /* sampler key of pair 0 of this call (lets a caller split a job into several calls) */
+    int32_t max_iters;        /* cv::findEssentialMat default 1000 */
+    int32_t random_rate;      /* getDepthFast: every random_rate-th inlier, >= 1 */
+} esfm_two_view_params_t;
+typedef struct esfm_two_view_t {
+    double E[9];              /* essential matrix, row-major, unit Frobenius norm */
+    double R[9];              /* rotation of T_21, row-major */
+    double t[3];              /* translation of T_21, unit length */
+    double depth;             /* getDepthFast: mean norm of the triangulated inliers, in baseline lengths */
+    int32_t n_matches, n_inliers, n_good;   /* n_good = inliers in front of both cameras for the chosen (R, t) */
+    int32_t iters;            /* hypotheses the stopping rule evaluated */
+    int32_t ok;
+    int32_t reserved;
+} esfm_two_view_t;
+int esfm_two_view_default_params(esfm_two_view_params_t* params);
+int esfm_two_view_batch(esfm_ctx_t* ctx, int64_t n_pairs, const int64_t* pair_off, const float* pts1, const float* pts2, const double* K,
+                        int k_per_pair, const esfm_two_view_params_t* params, unsigned char* inlier_mask, esfm_two_view_t* out);
+
 #ifdef __cplusplus
 }
 #endif
