@@ -401,24 +401,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
                 const uint32_t qrow0 = qrow - (uint32_t)lane;
                 float k1 = kWinNone, k2 = kWinNone;
                 int w1 = -1, w2 = -1;
+                // ORB: the accumulator of tile tt + 1 is read (and its stage released) BEFORE tile tt's registers are processed: the 16
+                // packed registers of a pass are cheap to double-buffer, and the stage goes back to the tensor pipe one pass earlier --
+                // the MMA -> commit -> epilogue -> release loop is what bounds the ORB sweep, not the arithmetic.
+                uint32_t hn[16];
+                auto acquire = [&](uint32_t gg, int tile) {
+                    const uint32_t as = gg % kWinAccStages, aph = (gg / kWinAccStages) & 1;
+                    mbar_wait_sleep<kTcSleepEpilogue>(&accFull[as], aph);
+                    if (warp == 0 && tile == u.ntt - 1) named_bar_arrive(2, 128 + 32);     // the query slot may be refilled (see the writers)
+                    tc_fence_after();
+                    tmem_ld16_pack(tmem + lane_addr + as * 128 + part * kTcPartCols, hn);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_relaxed(&accEmpty[as]);
+                };
+                if constexpr (kOrb) {
+                    if (u.ntt > 0) acquire(g, 0);
+                }
                 for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                     const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
-                    if (p.need_cols) mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);       // (no cross-check: no thresholds travel)
-                    const uint32_t as = g % kWinAccStages, aph = (g / kWinAccStages) & 1;
-                    mbar_wait_sleep<kTcSleepEpilogue>(&accFull[as], aph);
-                    if (warp == 0 && tt == u.ntt - 1) named_bar_arrive(2, 128 + 32);     // the query slot may be refilled (see the writers)
-                    tc_fence_after();
                     const int wide_id = ((tt * (kTile / 8) + part * (kTcPartCols / 8)) << 1) | 1;     // this pass's 32 columns as a slice id
                     const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols);
                     if constexpr (kOrb) {
                         // ---------------- ORB: 16 registers = 32 fp16 accumulators v = -2 hamming (pads: -inf) ----------------
                         uint32_t hb[16];
-                        tmem_ld16_pack(tmem + lane_addr + as * 128 + part * kTcPartCols, hb);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) hb[c] = hn[c];
+                        if (tt + 1 < u.ntt) acquire(g + 1, tt + 1);
+                        if (p.need_cols) mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);       // (no cross-check: no thresholds travel)
                         const uint4* tp = reinterpret_cast<const uint4*>(Thr + ts * kTcThrBytes + part * (kTcPartCols * 2));
-                        tmem_ld_wait();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_relaxed(&accEmpty[as]);
                         if (!(p.debug_flags & 1)) {
                             if (!(p.debug_flags & 16)) {
                                 // rows: tournament on packed halves (even columns in the low halves, odd in the high ones)
@@ -482,6 +494,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
                         }
                     } else {
                         // ---------------- SURF: 32 fp32 accumulators v = -1/2 d^2 (pads: <= -1e30) ----------------
+                        if (p.need_cols) mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);       // (no cross-check: no thresholds travel)
+                        const uint32_t as = g % kWinAccStages, aph = (g / kWinAccStages) & 1;
+                        mbar_wait_sleep<kTcSleepEpilogue>(&accFull[as], aph);
+                        if (warp == 0 && tt == u.ntt - 1) named_bar_arrive(2, 128 + 32);     // the query slot may be refilled (see the writers)
+                        tc_fence_after();
                         uint32_t vb[32];
                         tmem_ld32(tmem + lane_addr + as * 128 + part * kTcPartCols, vb);
                         const float4* tp = reinterpret_cast<const float4*>(Thr + ts * kTcThrBytes) + part * (kTcPartCols / 4);
