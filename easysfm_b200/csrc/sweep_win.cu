@@ -31,6 +31,13 @@ namespace esfm {
 namespace {
 
 constexpr int kWinStages = 5;                       // shared-memory train stages (36 KB each)
+// MMA issuers: the tcgen05.mma queue is shallow, so the tensor pipe runs dry while ONE issuer thread does a tile's book-keeping (two barrier
+// waits, two commits: ~500 clk against 577 / 833 clk of MMAs per tile; csrc/microbench/pipe_probe.cu).  Three warps take the tiles in turn:
+// while one is blocked issuing its MMAs the next has already passed its waits.  Every barrier must keep ONE issuer (a parity wait may not
+// skip a phase): the accumulator ring has 3 stages = 3 issuers; the load ring indexes its barriers by tile % lcm(stages, issuers).
+constexpr int kWinIssuers = 3;
+constexpr int kWinLoadBars = 15;                    // lcm(kWinStages, kWinIssuers)
+static_assert(kWinLoadBars % kWinStages == 0 && kWinLoadBars % kWinIssuers == 0, "load-ring barriers");
 constexpr int kWinAccStages = 3;                    // (512 - 64) / 128 accumulator stages
 constexpr uint32_t kWinACol0 = 128u * kWinAccStages; // query operand: 64 tensor-memory columns (SURF: a 32 | b 32; ORB: 256 FP8)
 constexpr int kWinTileBytes = kTchTileBytes;        // == kTc8TileBytes
@@ -186,8 +193,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(colsc) + kTcScBytes);
     uint64_t* fullQ = bars;
     uint64_t* fullT = fullQ + 1;
-    uint64_t* emptyT = fullT + kWinStages;
-    uint64_t* accFull = emptyT + kWinStages;
+    uint64_t* emptyT = fullT + kWinLoadBars;
+    uint64_t* accFull = emptyT + kWinLoadBars;
     uint64_t* accEmpty = accFull + kWinAccStages;
     uint64_t* thrFull = accEmpty + kWinAccStages;
     uint64_t* thrEmpty = thrFull + kTcThrStages;
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
 
     if (threadIdx.x == 0) {
         mbar_init(&fullQ[0], 4);                      // the 4 query-writer warps
-        for (int s = 0; s < kWinStages; ++s) {
+        for (int s = 0; s < kWinLoadBars; ++s) {
             mbar_init(&fullT[s], 1);
             mbar_init(&emptyT[s], 1);                 // MMA commit
         }
@@ -231,13 +238,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
                 const unsigned char* tauc = reinterpret_cast<const unsigned char*>(p.col_thr) + (size_t)u.pair * p.stride * (kOrb ? 2 : 4);
                 for (int qt = u.qb0; qt < u.qb1; ++qt) {
                     for (int tt = 0; tt < u.ntt; ++tt, ++g) {
-                        const uint32_t st = g % kWinStages, ph = (g / kWinStages) & 1;
-                        if (nosleep) mbar_wait_sleep<0>(&emptyT[st], ph ^ 1); else mbar_wait_sleep<kTcSleepProducer>(&emptyT[st], ph ^ 1);
-                        mbar_arrive_expect_tx(&fullT[st], kWinTileBytes);
+                        // stage g % 5; its barrier pair g % 15; the stage was last used by tile g - 5, whose barrier is (g - 5) % 15
+                        const uint32_t st = g % kWinStages, bi = g % kWinLoadBars, ph = (g / kWinLoadBars) & 1;
+                        if (g >= kWinStages) {
+                            const uint32_t pg = g - kWinStages, pbi = pg % kWinLoadBars, pph = (pg / kWinLoadBars) & 1;
+                            if (nosleep) mbar_wait_sleep<0>(&emptyT[pbi], pph); else mbar_wait_sleep<kTcSleepProducer>(&emptyT[pbi], pph);
+                        }
+                        (void)ph;
+                        mbar_arrive_expect_tx(&fullT[bi], kWinTileBytes);
                         if (p.debug_flags & 4)
-                            asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&fullT[st])), "r"(kWinTileBytes) : "memory");
+                            asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&fullT[bi])), "r"(kWinTileBytes) : "memory");
                         else
-                            bulk_g2s(Ts + (size_t)st * kWinTileBytes, timg + (size_t)tt * kWinTileBytes, kWinTileBytes, &fullT[st]);
+                            bulk_g2s(Ts + (size_t)st * kWinTileBytes, timg + (size_t)tt * kWinTileBytes, kWinTileBytes, &fullT[bi]);
                         // the running column thresholds of this tile ride along in their own ring (a stale snapshot is only looser)
                         if (p.need_cols) {
                             const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
@@ -249,8 +261,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
                 }
             }
         }
-    } else if (warp == kTcEpiWarps + 1) {
-        // ======================= MMA issuer (warp-uniform control flow, one elected lane issues) =======================
+    } else if (warp >= kTcEpiWarps + 1 && warp <= kTcEpiWarps + kWinIssuers) {
+        // ======================= MMA issuers (warp-uniform control flow, one elected lane issues): tile g belongs to issuer g % 3 =======================
+        const uint32_t me = (uint32_t)(warp - (kTcEpiWarps + 1));
         constexpr uint32_t id_main = kOrb ? tc_idesc_e4m3_h(128, 128) : tc_idesc_f16(128, 128, 0, 0);
         constexpr uint32_t id_aug = kOrb ? tc_idesc_e4m3_h(128, 128) : tc_idesc_tf32(128, 128);
         const uint64_t qad = tc_desc_nosw(smem_u32(Qa), 128, kTcAugGroupBytes);
@@ -260,13 +273,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const WinUnit u = win_decode_unit(p, unit);
             for (int qt = u.qb0; qt < u.qb1; ++qt, ++qn) {
+                // every issuer observes every fill of the query slot (a parity wait may not skip a phase), also in a block none of whose
+                // tiles are its own
+                mbar_wait_sleep<0>(&fullQ[0], qn & 1);
                 for (int tt = 0; tt < u.ntt; ++tt, ++g) {
-                    const uint32_t st = g % kWinStages, ph = (g / kWinStages) & 1;
-                    if (nosleep) mbar_wait_sleep<0>(&fullT[st], ph); else mbar_wait_sleep<kTcSleepIssuer>(&fullT[st], ph);
+                    if (g % kWinIssuers != me) continue;
+                    const uint32_t st = g % kWinStages, bi = g % kWinLoadBars, ph = (g / kWinLoadBars) & 1;
+                    if (nosleep) mbar_wait_sleep<0>(&fullT[bi], ph); else mbar_wait_sleep<kTcSleepIssuer>(&fullT[bi], ph);
                     const uint64_t td = td0 + (uint64_t)(st * (kWinTileBytes >> 4));
                     const uint64_t tad = tad0 + (uint64_t)(st * (kWinTileBytes >> 4));
                     const uint32_t as = g % kWinAccStages, aph = (g / kWinAccStages) & 1;
-                    if (tt == 0) mbar_wait_sleep<0>(&fullQ[0], qn & 1);        // the writers have filled the query slot for this block
                     if (nosleep) mbar_wait_sleep<0>(&accEmpty[as], aph ^ 1); else mbar_wait_sleep<kTcSleepIssuer>(&accEmpty[as], aph ^ 1);
                     tc_fence_after();
                     const uint32_t d = tmem + as * 128;
@@ -276,7 +292,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
 #pragma unroll
                             for (int ks = 0; ks < 8; ++ks)          // 256 FP8 values per row = 8 k-steps of K = 32 (32 bytes each)
                                 tc_mma_f8_ts(d, acol + ks * 8, td + (uint64_t)(((ks >> 2) * 1024 + (ks & 3) * 32) >> 4), id_main, ks > 0);
-                            tc_mma_f8(d, qad, tad, id_aug, true);   // - 256 and the pad-row penalties
+                            // - 256 and the pad-row penalties: only the column thresholds need them (rows-only sweeps mask the pad
+                            // columns of a frame's last tile in the epilogue and report 256 - v: one MMA slot of nine saved)
+                            if (p.need_cols) tc_mma_f8(d, qad, tad, id_aug, true);
                         } else {
                             // small terms first: b_q.a_t, a_q.b_t, then a_q.a_t; a k-step = 16 halves = 32 bytes of the 128-byte row
 #pragma unroll
@@ -291,7 +309,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
                     __syncwarp();
                     if (elect_one()) {
                         tc_commit(&accFull[as]);        // accumulator stage ready for the epilogue
-                        tc_commit(&emptyT[st]);         // shared-memory stage consumed
+                        tc_commit(&emptyT[bi]);         // shared-memory stage consumed
                     }
                     __syncwarp();
                 }
@@ -399,39 +417,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
             for (int qt = u.qb0; qt < u.qb1; ++qt) {
                 const uint32_t qrow = (uint32_t)(qt * kTile + trow);
                 const uint32_t qrow0 = qrow - (uint32_t)lane;
+                const int ft = p.frame_rows[u.t_frame];
+                const float voff = (kOrb && !p.need_cols) ? 256.f : 0.f;       // ORB rows-only: v = 256 - 2 hamming (no augmented MMA)
                 float k1 = kWinNone, k2 = kWinNone;
                 int w1 = -1, w2 = -1;
-                // ORB: the accumulator of tile tt + 1 is read (and its stage released) BEFORE tile tt's registers are processed: the 16
-                // packed registers of a pass are cheap to double-buffer, and the stage goes back to the tensor pipe one pass earlier --
-                // the MMA -> commit -> epilogue -> release loop is what bounds the ORB sweep, not the arithmetic.
-                uint32_t hn[16];
-                auto acquire = [&](uint32_t gg, int tile) {
-                    const uint32_t as = gg % kWinAccStages, aph = (gg / kWinAccStages) & 1;
-                    mbar_wait_sleep<kTcSleepEpilogue>(&accFull[as], aph);
-                    if (warp == 0 && tile == u.ntt - 1) named_bar_arrive(2, 128 + 32);     // the query slot may be refilled (see the writers)
-                    tc_fence_after();
-                    tmem_ld16_pack(tmem + lane_addr + as * 128 + part * kTcPartCols, hn);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_relaxed(&accEmpty[as]);
-                };
-                if constexpr (kOrb) {
-                    if (u.ntt > 0) acquire(g, 0);
-                }
                 for (int tt = 0; tt < u.ntt; ++tt, ++g) {
                     const uint32_t ts = g % kTcThrStages, tph = (g / kTcThrStages) & 1;
+                    if (p.need_cols) mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);       // (no cross-check: no thresholds travel)
+                    const uint32_t as = g % kWinAccStages, aph = (g / kWinAccStages) & 1;
+                    mbar_wait_sleep<kTcSleepEpilogue>(&accFull[as], aph);
+                    if (warp == 0 && tt == u.ntt - 1) named_bar_arrive(2, 128 + 32);     // the query slot may be refilled (see the writers)
+                    tc_fence_after();
                     const int wide_id = ((tt * (kTile / 8) + part * (kTcPartCols / 8)) << 1) | 1;     // this pass's 32 columns as a slice id
                     const uint32_t col0 = (uint32_t)(tt * kTile + part * kTcPartCols);
                     if constexpr (kOrb) {
                         // ---------------- ORB: 16 registers = 32 fp16 accumulators v = -2 hamming (pads: -inf) ----------------
                         uint32_t hb[16];
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) hb[c] = hn[c];
-                        if (tt + 1 < u.ntt) acquire(g + 1, tt + 1);
-                        if (p.need_cols) mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);       // (no cross-check: no thresholds travel)
+                        tmem_ld16_pack(tmem + lane_addr + as * 128 + part * kTcPartCols, hb);
                         const uint4* tp = reinterpret_cast<const uint4*>(Thr + ts * kTcThrBytes + part * (kTcPartCols * 2));
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_relaxed(&accEmpty[as]);
                         if (!(p.debug_flags & 1)) {
+                            if (!p.need_cols) {
+                                // no augmented MMA: v = 256 - 2 hamming, and the pad rows of the train frame (all-zero operands, only in
+                                // its last tile) read as 0 instead of -inf: mask them here
+                                const int rem = ft - (int)col0;
+                                if (rem < kTcPartCols) {
+#pragma unroll
+                                    for (int c = 0; c < 16; ++c)
+                                        hb[c] = 2 * c + 1 < rem ? hb[c] : (2 * c < rem ? ((hb[c] & 0xffffu) | 0xfc000000u) : 0xfc00fc00u);
+                                }
+                            }
                             if (!(p.debug_flags & 16)) {
                                 // rows: tournament on packed halves (even columns in the low halves, odd in the high ones)
                                 uint32_t H[8], L[8];
@@ -494,11 +512,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
                         }
                     } else {
                         // ---------------- SURF: 32 fp32 accumulators v = -1/2 d^2 (pads: <= -1e30) ----------------
-                        if (p.need_cols) mbar_wait_sleep<kTcSleepEpilogue>(&thrFull[ts], tph);       // (no cross-check: no thresholds travel)
-                        const uint32_t as = g % kWinAccStages, aph = (g / kWinAccStages) & 1;
-                        mbar_wait_sleep<kTcSleepEpilogue>(&accFull[as], aph);
-                        if (warp == 0 && tt == u.ntt - 1) named_bar_arrive(2, 128 + 32);     // the query slot may be refilled (see the writers)
-                        tc_fence_after();
                         uint32_t vb[32];
                         tmem_ld32(tmem + lane_addr + as * 128 + part * kTcPartCols, vb);
                         const float4* tp = reinterpret_cast<const float4*>(Thr + ts * kTcThrBytes) + part * (kTcPartCols / 4);
@@ -589,7 +602,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
                     const float kv = e2 ? k2 : k1;
                     const int kw = e2 ? w2 : w1;
                     if (kw >= 0 && kv > (kOrb ? -600.f : -1.0e29f)) {          // a real column (pads: SURF <= -1e30, ORB -inf / -65504)
-                        const u64 k = make_key(__float_as_uint(fmaxf(-kv, 0.f) + 0.f), (uint32_t)kw);   // (+ 0.f: a -0 becomes +0)
+                        const u64 k = make_key(__float_as_uint(fmaxf(voff - kv, 0.f) + 0.f), (uint32_t)kw);   // (+ 0.f: a -0 becomes +0)
                         const u64 old = atomicMin(&mkey[trow], k);
                         atomicMin(&mkey[kTile + trow], old > k ? old : k);
                     }
@@ -618,7 +631,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
 
 size_t sweep_win_smem_bytes() {
     return 1024 + (size_t)kWinStages * kWinTileBytes + kTcAugBytes + (size_t)kTcThrStages * kTcThrBytes + 2 * kTile * sizeof(u64) + (size_t)kTcScBytes +
-           (1 + 2 * kWinStages + 2 * kWinAccStages + 2 * kTcThrStages) * 8 + 16;
+           (1 + 2 * kWinLoadBars + 2 * kWinAccStages + 2 * kTcThrStages) * 8 + 16;
 }
 
 // kind = p.tc_kind: ESFM_KIND_F32X64 (tc_main = the H images of launch_pack_tch) or ESFM_KIND_B256 (tc_main = the +-1 FP8 images)
