@@ -845,11 +845,14 @@ int run_chunk(esfm_ctx* ctx, esfm_bank* b, const ChunkPlan& pl, ChunkBuf& cb, si
     CUDA_TRY(cudaMemsetAsync(cb.d_cursor, 0, 2 * sizeof(unsigned long long), ctx->stream));
     const bool tc = use_tc(ctx, b);
     // ORB "Z" encoding: the column index rides in the key, so every frame must have at most 2^15 rows; else the +-1 encoding
-    const bool win = tc && use_win(ctx, b);
-    // tc16 sweeps, cross-check in TWO PHASES: (1) a rows-only sweep + ratio test, (2) a second rows-only sweep with the roles swapped
-    // over just the train rows the survivors point at (gathered into the query operand), whose answer -- the nearest query row of
-    // each -- decides the cross-check.  The column minima, their thresholds and their events leave the hot sweep altogether.
-    const bool two_phase = win && cross_check && !knn_idx && ctx->two_phase;
+    // tc16 sweeps (sweep_win.cu) are ROWS-ONLY.  Their cross-check runs in TWO PHASES: (1) the rows-only sweep + ratio test, survivors claim
+    // their train rows and histograms of every row's best / second-best value decide which survivors could still be beaten; (2) a second
+    // rows-only sweep with the roles swapped over just the undecided train rows (gathered into the query operand), whose answer -- the
+    // nearest query row of each -- settles them.  What needs column minima inside ONE sweep (esfm_knn2_pair; $ESFM_TWO_PHASE=0) runs on the
+    // fp32-accumulator tensor-core sweep of sweep_l2_tc.cu instead (the bank's operand images are rebuilt on the switch).
+    const bool win_engine = tc && use_win(ctx, b);
+    const bool two_phase = win_engine && cross_check && !knn_idx && ctx->two_phase;
+    const bool win = win_engine && !knn_idx && (two_phase || !cross_check);
     const int zmode = (tc && !win && b->kind == ESFM_KIND_B256 && ctx->orb_z && b->max_rows <= kTcZMaxRows) ? 1 : 0;
     if (tc) { if (int rc = ensure_tc_layout(ctx, b, win && b->kind == ESFM_KIND_F32X64 ? 2 : zmode)) return rc; }
     else if (b->kind == ESFM_KIND_F32X64) { if (int rc = ensure_kmajor_layout(ctx, b)) return rc; }

@@ -106,13 +106,14 @@ __device__ __forceinline__ RowResult eval_row(const FinalizeParams& p, const u64
     return r;
 }
 
-// ---- window keys (sweep_win.cu): a row key's low word names a slice of train columns instead of one column ----
-//     id = (first column / 8) << 1 | wide         wide = 0: 8 columns, 1: 32 columns
+// ---- slice keys (sweep_win.cu): a row key's low word names a slice of train columns instead of one column ----
+//     id = (first column / 8) << 2 | width code         0: 8 columns, 1: 32, 2: 64, 3: 128
 // The column itself is found HERE, by evaluating the slice exactly -- and only for rows that can still pass the ratio test.
 __device__ __forceinline__ void win_range(u64 key, int ft, int& c0, int& c1) {
     const uint32_t id = (uint32_t)key;
-    c0 = (int)(id >> 1) * 8;
-    c1 = min(c0 + ((id & 1u) ? 32 : 8), ft);
+    c0 = (int)(id >> 2) * 8;
+    const uint32_t w = id & 3u;
+    c1 = min(c0 + (w == 0u ? 8 : (w == 1u ? 32 : (w == 2u ? 64 : 128))), ft);
 }
 __device__ __forceinline__ int b256_hamming(const uint4& a0, const uint4& a1, const uint4* __restrict__ t) {
     const uint4 b0 = __ldg(t), b1 = __ldg(t + 1);
