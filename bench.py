@@ -471,16 +471,17 @@ def bench_kind(args, kind, ctx, dev, rank, world, dist, steps, warmup, cpu_budge
         # can be); `executed_tflops` / `frac_executed` are the FP8 tensor FLOPs actually issued over the dense FP8 peak
         # (= 2 x the measured dense bf16 rate).  The kernel is bound by its selection epilogue, not by the tensor pipe.
         fp8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
-        roofline["executed_tflops"] = (comps_per_launch / (sweep_ms * 1e-3)) * TC8_FLOP_PER_CMP / 1e12
+        flop_per_cmp = 512.0 if engine == "tc16" else TC8_FLOP_PER_CMP      # tc16: 8 MMAs of K = 32, no augmented step
+        roofline["executed_tflops"] = (comps_per_launch / (sweep_ms * 1e-3)) * flop_per_cmp / 1e12
         roofline["frac_executed"] = roofline["executed_tflops"] / fp8_peak
         roofline["tensor_peak_tflops"] = fp8_peak
         roofline["note"] = (("Hamming as an exact FP8 dot product on tcgen05 (kind::f8f6f4) with FP16 accumulators (-2 hamming), selection on packed halves: "
                              if engine == "tc16" else
                              "Hamming as an exact FP8 dot product on tcgen05 (kind::f8f6f4) that yields packed (distance, column) keys: ") +
-                            "576 tensor FLOP per comparison; frac is the algorithmic 8-POPC rate over the POPC-pipe peak; the kernel is bound by "
-                            "the instruction issue of its selection epilogue (column events above all), not by the tensor pipe: 9 MMAs = 577 clk per "
-                            "128 x 128 tile would be 8.3e12 comparisons/s")
-        roofline["mma_bound_cmp_per_s"] = sms * sm_max * 1e6 * 16384 / (9 * 64.1)
+                            ("512" if engine == "tc16" else "576") + " tensor FLOP per comparison; frac is the algorithmic 8-POPC rate over the POPC-pipe peak; "
+                            "frac_executed is the tensor work over the dense FP8 peak (2 x the measured bf16 rate); the rest is the latency of the "
+                            "selection epilogue (one tournament per 64 columns and row), not the tensor pipe")
+        roofline["mma_bound_cmp_per_s"] = sms * sm_max * 1e6 * 16384 / ((8 if engine == "tc16" else 9) * 64.1)
         roofline["frac_of_mma_bound"] = (comps_per_launch / (sweep_ms * 1e-3)) / roofline["mma_bound_cmp_per_s"]
     if bound == "tensor" and kind == "surf" and engine == "tc16":
         # `achieved`/`frac`: ALGORITHMIC 128 FLOP per comparison over the dense 16-bit tensor peak.  Executed: 3 x 64 x 2 FLOP on kind::f16

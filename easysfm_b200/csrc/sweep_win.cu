@@ -27,10 +27,11 @@
 //                burst of MMAs the next has already passed its barrier waits -- one issuer left the tensor pipe dry ~45 % of the time,
 //                csrc/microbench/pipe_probe.cu); query operand in tensor memory, 3 accumulator stages of 128 columns;
 //   warps 20-23  query writers (rows of the query tile -> operand columns of tensor memory, augmented block in shared memory);
-//   warps 0-15   epilogue in four GROUPS of four warps (one per TMEM lane quarter = 32 query rows): tile g belongs to group g % 4, whose
-//                warps read ALL 128 columns of their rows (ORB: 64 packed registers at once; SURF: two halves of 64 fp32 registers),
-//                release the stage, and run one tournament over them -- four times the instruction-level parallelism of a 32-column
-//                pass, one running-state merge per tile instead of four, and a slow warp delays its own group's stage only.
+//   warps 0-15   epilogue in four GROUPS of four warps (one per TMEM lane quarter = 32 query rows).  The unit of work is half a tile
+//                (64 train columns): unit 2 g + h belongs to group (2 g + h) % 4, so a group reads one half of every other tile -- ORB: 32
+//                packed registers in one tcgen05.ld; SURF: two loads of 32 -- releases its share of the accumulator stage BEFORE it
+//                computes, and runs one tournament over its columns: twice the columns per barrier hand-shake and per running-state
+//                merge of a 32-column pass, and a slow warp delays nobody else's stage.
 // Every mbarrier keeps ONE producer and ONE consumer role (a parity wait may not skip a phase): the barriers of the load ring are indexed
 // by tile % lcm(5 stages, 3 issuers) = 15, those of the accumulator ring by tile % lcm(3 stages, 3 issuers, 4 groups) = 12.
 #include <cuda_fp16.h>
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
         }
         for (int s = 0; s < kWinAccBars; ++s) {
             mbar_init(&accFull[s], 1);                // MMA commit
-            mbar_init(&accEmpty[s], 4);               // the 4 warps of the owning epilogue group
+            mbar_init(&accEmpty[s], 8);               // the 4 + 4 warps of the two epilogue groups that own the tile's halves
         }
         fence_mbar_init();
     }
@@ -354,65 +355,60 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
                 float k1 = kWinNone, k2 = kWinNone;
                 int w1 = -1, w2 = -1;
                 for (int tt = 0; tt < u.ntt; ++tt, ++g) {
-                    if ((int)(g % kWinGroups) != group) continue;
+                    // unit = (tile, half of 64 columns); unit 2 g + half belongs to group (2 g + half) % 4: a group reads one half of every
+                    // other tile, at once, and releases its share of the stage before it starts computing
+                    const int half = group & 1;
+                    if ((int)(g & 1u) != (group >> 1)) continue;
                     const uint32_t as = g % kWinAccStages, ab = g % kWinAccBars, aph = (g / kWinAccBars) & 1;
                     mbar_wait_sleep<kTcSleepEpilogue>(&accFull[ab], aph);
-                    if (quarter == 0 && tt >= u.ntt - n_last) named_bar_arrive(2, 128 + 32 * n_last);
+                    if (quarter == 0 && half == 0 && tt >= u.ntt - n_last) named_bar_arrive(2, 128 + 32 * n_last);
                     tc_fence_after();
-                    const int col0 = tt * kTile;
+                    const int c0 = tt * kTile + half * 64;
                     if constexpr (kOrb) {
-                        // ---------------- ORB: two halves of 32 registers = 64 fp16 accumulators v = 256 - 2 hamming ----------------
-                        // (the whole tile at once would need 64 data registers: ptxas compiles the kernel for the 80 registers of its launch
-                        // bounds whatever setmaxnreg grants at run time)
-#pragma unroll 1
-                        for (int half = 0; half < 2; ++half) {
-                            uint32_t hb[32];
-                            tmem_ld32_pack(tmem + lane_addr + as * 128 + half * 64, hb);
-                            tmem_ld_wait();
-                            if (half == 1) {
-                                tc_fence_before();
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive_relaxed(&accEmpty[ab]);
-                            }
-                            if (p.debug_flags & 1) continue;
-                            const int c0 = col0 + half * 64;
-                            const int rem = ft - c0;
-                            if (rem < 64) {             // pad rows of the train frame (all-zero operands, only in its last tile) read as 0: mask them
+                        // ---------------- ORB: 32 registers = 64 fp16 accumulators v = 256 - 2 hamming ----------------
+                        uint32_t hb[32];
+                        tmem_ld32_pack(tmem + lane_addr + as * 128 + half * 64, hb);
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_relaxed(&accEmpty[ab]);
+                        if (p.debug_flags & 1) continue;
+                        const int rem = ft - c0;
+                        if (rem < 64) {             // pad rows of the train frame (all-zero operands, only in its last tile) read as 0: mask them
 #pragma unroll
-                                for (int c = 0; c < 32; ++c)
-                                    hb[c] = 2 * c + 1 < rem ? hb[c] : (2 * c < rem ? ((hb[c] & 0xffffu) | 0xfc000000u) : 0xfc00fc00u);
-                            }
-                            // tournament on packed halves (even columns in the low halves, odd in the high ones), in place: sorted pairs ...
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const uint32_t hi = hmax2(hb[2 * j], hb[2 * j + 1]), lo = hmin2(hb[2 * j], hb[2 * j + 1]);
-                                hb[2 * j] = hi; hb[2 * j + 1] = lo;
-                            }
-                            // ... merged down to one (largest, second) pair per 32-column part (8 pairs each): hb[0 / 1], hb[16 / 17]
-#pragma unroll
-                            for (int step = 1; step < 8; step <<= 1) {
-#pragma unroll
-                                for (int j = 0; j < 16; j += 2 * step) {
-                                    const uint32_t ha = hb[2 * j], la = hb[2 * j + 1], hc = hb[2 * (j + step)], lc = hb[2 * (j + step) + 1];
-                                    hb[2 * j] = hmax2(ha, hc);
-                                    hb[2 * j + 1] = hmax2(hmax2(hmin2(ha, hc), la), lc);
-                                }
-                            }
-                            const float pm0 = fmaxf(h_lo(hb[0]), h_hi(hb[0]));
-                            const uint32_t hh = hmax2(hb[0], hb[16]), ll = hmax2(hmax2(hmin2(hb[0], hb[16]), hb[1]), hb[17]);
-                            const float a1 = h_lo(hh), b1 = h_hi(hh), a2 = h_lo(ll), b2 = h_hi(ll);
-                            const float p1 = fmaxf(a1, b1), p2 = fmaxf(fmaxf(fminf(a1, b1), a2), b2);
-                            const int sub = pm0 == p1 ? 0 : 1;                  // the lower part on ties
-                            if (!(p.debug_flags & 16)) win_merge(p1, win_slice(c0 + 32 * sub, 1), p2, win_slice(c0, 2), k1, w1, k2, w2);
+                            for (int c = 0; c < 32; ++c)
+                                hb[c] = 2 * c + 1 < rem ? hb[c] : (2 * c < rem ? ((hb[c] & 0xffffu) | 0xfc000000u) : 0xfc00fc00u);
                         }
+                        // tournament on packed halves (even columns in the low halves, odd in the high ones), in place: sorted pairs ...
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t hi = hmax2(hb[2 * j], hb[2 * j + 1]), lo = hmin2(hb[2 * j], hb[2 * j + 1]);
+                            hb[2 * j] = hi; hb[2 * j + 1] = lo;
+                        }
+                        // ... merged down to one (largest, second) pair per 32-column part (8 pairs each): hb[0 / 1], hb[16 / 17]
+#pragma unroll
+                        for (int step = 1; step < 8; step <<= 1) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 2 * step) {
+                                const uint32_t ha = hb[2 * j], la = hb[2 * j + 1], hc = hb[2 * (j + step)], lc = hb[2 * (j + step) + 1];
+                                hb[2 * j] = hmax2(ha, hc);
+                                hb[2 * j + 1] = hmax2(hmax2(hmin2(ha, hc), la), lc);
+                            }
+                        }
+                        const float pm0 = fmaxf(h_lo(hb[0]), h_hi(hb[0]));
+                        const uint32_t hh = hmax2(hb[0], hb[16]), ll = hmax2(hmax2(hmin2(hb[0], hb[16]), hb[1]), hb[17]);
+                        const float a1 = h_lo(hh), b1 = h_hi(hh), a2 = h_lo(ll), b2 = h_hi(ll);
+                        const float p1 = fmaxf(a1, b1), p2 = fmaxf(fmaxf(fminf(a1, b1), a2), b2);
+                        const int sub = pm0 == p1 ? 0 : 1;                  // the lower part on ties
+                        if (!(p.debug_flags & 16)) win_merge(p1, win_slice(c0 + 32 * sub, 1), p2, win_slice(c0, 2), k1, w1, k2, w2);
                     } else {
-                        // ---------------- SURF: four quarters of 32 fp32 accumulators v = -1/2 d^2 (pads: <= -1e30) ----------------
+                        // ---------------- SURF: two quarters of 32 fp32 accumulators v = -1/2 d^2 (pads: <= -1e30) ----------------
 #pragma unroll 1
-                        for (int qc = 0; qc < 4; ++qc) {
+                        for (int qc = 0; qc < 2; ++qc) {
                             uint32_t vb[32];
-                            tmem_ld32(tmem + lane_addr + as * 128 + qc * 32, vb);
+                            tmem_ld32(tmem + lane_addr + as * 128 + half * 64 + qc * 32, vb);
                             tmem_ld_wait();
-                            if (qc == 3) {
+                            if (qc == 1) {
                                 tc_fence_before();
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive_relaxed(&accEmpty[ab]);
@@ -441,8 +437,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) sweep_win_kernel(const SweepPar
                             const float p1 = fmaxf(h01, h23), p2 = fmaxf(fmaxf(fminf(h01, h23), l01), l23);
                             // the best value's chain of 8 columns (the lowest on ties): finalize evaluates 8 candidates instead of 32
                             const int sub = v[0] == p1 ? 0 : (v[8] == p1 ? 1 : (v[16] == p1 ? 2 : 3));
-                            const int c0 = col0 + qc * 32;
-                            if (!(p.debug_flags & 16)) win_merge(p1, win_slice(c0 + 8 * sub, 0), p2, win_slice(c0, 1), k1, w1, k2, w2);
+                            const int cq = c0 + qc * 32;
+                            if (!(p.debug_flags & 16)) win_merge(p1, win_slice(cq + 8 * sub, 0), p2, win_slice(cq, 1), k1, w1, k2, w2);
                         }
                     }
                 }
