@@ -139,82 +139,138 @@ __device__ __forceinline__ void l2_scan(const float* __restrict__ qrow, const fl
     }
 }
 
+// lexicographic (distance, index) merge of another sorted pair (e1, j1) <= (e2, j2) into (d1, i1) <= (d2, i2)
+__device__ __forceinline__ void top2_merge(float& d1, int& i1, float& d2, int& i2, float e1, int j1, float e2, int j2) {
+    const bool other_first = e1 < d1 || (e1 == d1 && j1 < i1);
+    const float a1 = other_first ? e1 : d1, b1 = other_first ? d1 : e1;           // a = the winner's side, b = the loser's best
+    const int ai = other_first ? j1 : i1, bi = other_first ? i1 : j1;
+    const float a2 = other_first ? e2 : d2;                                          // the winner's own second
+    const int a2i = other_first ? j2 : i2;
+    const bool loser_second = b1 < a2 || (b1 == a2 && bi < a2i);
+    d1 = a1; i1 = ai;
+    d2 = loser_second ? b1 : a2;
+    i2 = loser_second ? bi : a2i;
+}
+
+// The 32 rows of one warp iteration (row q per lane; `valid` lanes only), slice keys.  WARP-COOPERATIVE: the rows that need their slice
+// evaluated are served four at a time by groups of eight lanes -- one candidate column per lane and step, all loads of a step in flight
+// together -- instead of every lane walking its own slice serially (a quarter of the lanes busy, eight dependent gathers each: that walk
+// was 90 % of the kernel's time).  Each distance is still computed by ONE lane with l2_direct (the oracle's summation order).
 template <int KIND>
-__device__ __forceinline__ RowResult eval_row_win(const FinalizeParams& p, const u64* rk1, const u64* rk2, const u64* ck1, const float* qrows,
-                                                  const float* trows, const uint4* qbits, const uint4* tbits, int q, int ft, int32_t* knn_idx,
-                                                  float* knn_dist, bool with_cross_check = true) {
-    RowResult r;
-    r.keep = false;
-    r.t1 = -1;
-    r.d1 = 0.f;
-    const u64 k1 = rk1[q], k2 = rk2[q];
-    const bool has1 = k1 != kKeyInit, has2 = k2 != kKeyInit;
+__device__ __forceinline__ RowResult eval_rows_win(const FinalizeParams& p, u64 k1, u64 k2, const float* qrows, const float* trows, const uint4* qbits,
+                                                   const uint4* tbits, int q, int ft, bool valid) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
+    const bool has1 = valid && k1 != kKeyInit, has2 = valid && k2 != kKeyInit;
     const bool no_ratio = p.ratio == __longlong_as_double(0x7ff0000000000000LL);
     const float inf = __int_as_float(0x7f800000);
     int i1 = -1, i2 = -1;
     float d1 = inf, d2 = inf;
-    bool pass = false;
-    if (has1) {
-        int a0, a1, b0 = 0, b1 = 0;
-        win_range(k1, ft, a0, a1);
-        if (has2) win_range(k2, ft, b0, b1);
+    bool pass = false, scan_a = false, scan_b = false, exact_ratio = false;
+    int a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+    if (has1) win_range(k1, ft, a0, a1);
+    if (has2) win_range(k2, ft, b0, b1);
+    if (KIND == ESFM_KIND_B256) {
+        // the sweep's integer distances are exact: only the column has to be found, and only for rows that pass
+        if (has1) d1 = 0.5f * __uint_as_float((uint32_t)(k1 >> 32));
+        if (has2) d2 = 0.5f * __uint_as_float((uint32_t)(k2 >> 32));
+        pass = has1 && (no_ratio || (has2 && (double)d1 < p.ratio * (double)d2));
+        scan_a = pass;
+    } else if (has1) {
+        // the sweep ranked 1/2 d^2 in expansion form (error ~4e-7 absolute): decide far-from-the-boundary rows on those values,
+        // evaluate the rest -- and every reported distance -- in direct form
+        const float s1 = __uint_as_float((uint32_t)(k1 >> 32)), s2 = has2 ? __uint_as_float((uint32_t)(k2 >> 32)) : inf;
+        if (no_ratio) { pass = true; scan_a = true; }
+        else if (has2 && p.ratio > 0.0) {
+            const float r2 = (float)(p.ratio * p.ratio);
+            const bool clear_fail = s1 > r2 * s2 * 1.001f + 4e-6f;
+            const bool clear_pass = s1 < r2 * s2 * 0.999f - 4e-6f;
+            if (!clear_fail) {
+                scan_a = true;
+                pass = clear_pass;
+                if (!clear_pass) { scan_b = true; exact_ratio = true; }
+            }
+        }
+        if (scan_b && a0 >= b0 && a1 <= b1) scan_a = false;       // slice a lies inside slice b: one evaluation
+    }
+    // ---- the cooperative part: four flagged rows per round, eight lanes each ----
+    unsigned todo = __ballot_sync(full, scan_a || scan_b);
+    while (todo) {
+        // owner lanes of this round's four rows (-1: none)
+        int owner[4];
+        unsigned rest = todo;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            owner[g] = rest ? __ffs(rest) - 1 : -1;
+            rest &= rest - 1;
+        }
+        todo = rest;
+        const int mine_owner = grp == 0 ? owner[0] : (grp == 1 ? owner[1] : (grp == 2 ? owner[2] : owner[3]));
+        const int src = mine_owner < 0 ? 0 : mine_owner;
+        const bool active = mine_owner >= 0;
+        const int rq = __shfl_sync(full, q, src);
+        const int ra0 = __shfl_sync(full, scan_a ? a0 : 0, src), ra1 = __shfl_sync(full, scan_a ? a1 : 0, src);
+        const int rb0 = __shfl_sync(full, scan_b ? b0 : 0, src), rb1 = __shfl_sync(full, scan_b ? b1 : 0, src);
         if (KIND == ESFM_KIND_B256) {
-            // the sweep's integer distances are exact: only the column has to be found
-            d1 = 0.5f * __uint_as_float((uint32_t)(k1 >> 32));
-            if (has2) d2 = 0.5f * __uint_as_float((uint32_t)(k2 >> 32));
-            pass = no_ratio || (has2 && (double)d1 < p.ratio * (double)d2);
-            if (pass || knn_idx) {
-                const uint4 q0 = __ldg(qbits + (size_t)q * 2), q1 = __ldg(qbits + (size_t)q * 2 + 1);
-                i1 = b256_find(q0, q1, tbits, a0, a1, (int)d1, -1);
-                if (knn_idx && has2) i2 = b256_find(q0, q1, tbits, b0, b1, (int)d2, i1);
-                if (i1 < 0) pass = false;       // (cannot happen: the sweep saw this distance in this window)
+            const int want = (int)__shfl_sync(full, d1, src);
+            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+            if (active) { q0 = __ldg(qbits + (size_t)rq * 2); q1 = __ldg(qbits + (size_t)rq * 2 + 1); }
+            int found = -1;
+            const int steps = __reduce_max_sync(full, active ? (ra1 - ra0 + 7) >> 3 : 0);
+            for (int k = 0; k < steps; ++k) {
+                const int c = ra0 + 8 * k + sub;
+                const bool hit = active && c < ra1 && b256_hamming(q0, q1, tbits + (size_t)c * 2) == want;
+                const unsigned m = (__ballot_sync(full, hit) >> (8 * grp)) & 0xffu;
+                if (found < 0 && m) found = ra0 + 8 * k + __ffs(m) - 1;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int v = __shfl_sync(full, found, 8 * g);
+                if (lane == owner[g]) i1 = v;
             }
         } else {
-            // the sweep ranked 1/2 d^2 in expansion form (error ~4e-7 absolute): decide far-from-the-boundary rows on those values,
-            // evaluate the rest -- and every reported distance -- in direct form
-            const float s1 = __uint_as_float((uint32_t)(k1 >> 32)), s2 = has2 ? __uint_as_float((uint32_t)(k2 >> 32)) : inf;
-            bool scan2 = knn_idx != nullptr && has2, skip = false;
-            if (!no_ratio) {
-                if (!has2) skip = true;
-                else if (!(p.ratio > 0.0)) skip = true;
-                else {
-                    const float r2 = (float)(p.ratio * p.ratio);
-                    const bool clear_fail = s1 > r2 * s2 * 1.001f + 4e-6f;
-                    const bool clear_pass = s1 < r2 * s2 * 0.999f - 4e-6f;
-                    if (clear_fail) skip = true;
-                    else if (!clear_pass) scan2 = true;
-                    else pass = true;
+            float e1 = inf, e2 = inf;
+            int j1 = -1, j2 = -1;
+            const float* qrow = qrows + (size_t)rq * kDim;
+#pragma unroll 1
+            for (int part = 0; part < 2; ++part) {
+                const int c0 = part ? rb0 : ra0, c1 = part ? rb1 : ra1;
+                const int steps = __reduce_max_sync(full, active ? (c1 - c0 + 7) >> 3 : 0);
+                for (int k = 0; k < steps; ++k) {
+                    const int c = c0 + 8 * k + sub;
+                    if (active && c < c1) {
+                        const float d = l2_direct(qrow, trows + (size_t)c * kDim);
+                        if (d < e1 || (d == e1 && c < j1)) { e2 = e1; j2 = j1; e1 = d; j1 = c; }
+                        else if (d < e2 || (d == e2 && c < j2)) { e2 = d; j2 = c; }
+                    }
                 }
-            } else pass = true;
-            if (!skip || knn_idx) {
-                const float* qrow = qrows + (size_t)q * kDim;
-                const bool contained = scan2 && a0 >= b0 && a1 <= b1;
-                if (!contained) l2_scan(qrow, trows, a0, a1, d1, i1, d2, i2);
-                if (scan2) {
-                    l2_scan(qrow, trows, b0, b1, d1, i1, d2, i2);
-                    if (!no_ratio && !skip) pass = i2 >= 0 && (double)d1 < p.ratio * (double)d2;
-                }
-                if (i1 < 0) pass = false;
             }
-            if (skip) pass = false;
+#pragma unroll
+            for (int m = 1; m <= 4; m <<= 1) {
+                const float o1 = __shfl_xor_sync(full, e1, m), o2 = __shfl_xor_sync(full, e2, m);
+                const int p1 = __shfl_xor_sync(full, j1, m), p2 = __shfl_xor_sync(full, j2, m);
+                if (p1 >= 0) {
+                    if (j1 < 0) { e1 = o1; j1 = p1; e2 = o2; j2 = p2; }
+                    else top2_merge(e1, j1, e2, j2, o1, p1, p2 >= 0 ? o2 : inf, p2 >= 0 ? p2 : 0x7fffffff);
+                }
+            }
+            if (j2 == 0x7fffffff) j2 = -1;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const float v1 = __shfl_sync(full, e1, 8 * g), v2 = __shfl_sync(full, e2, 8 * g);
+                const int w1 = __shfl_sync(full, j1, 8 * g), w2 = __shfl_sync(full, j2, 8 * g);
+                if (lane == owner[g]) { d1 = v1; i1 = w1; d2 = v2; i2 = w2; }
+            }
         }
     }
-    if (knn_idx) {
-        knn_idx[2 * q] = i1; knn_idx[2 * q + 1] = i2;
-        knn_dist[2 * q] = d1; knn_dist[2 * q + 1] = d2;
+    if (KIND == ESFM_KIND_B256) {
+        if (i1 < 0) pass = false;               // (cannot happen for a passing row: the sweep saw this distance in this slice)
+    } else {
+        if (exact_ratio) pass = i2 >= 0 && (double)d1 < p.ratio * (double)d2;
+        if (i1 < 0) pass = false;
     }
-    if (!pass) return r;
-    if (p.cross_check && with_cross_check) {
-        const u64 c1 = ck1[i1];
-        if (c1 == kKeyInit) return r;
-        const int best = (int)(uint32_t)c1;
-        if (best != q) {
-            if (KIND != ESFM_KIND_F32X64) return r;
-            const float db = l2_direct(qrows + (size_t)best * kDim, trows + (size_t)i1 * kDim);
-            if (!(d1 < db || (d1 == db && q < best))) return r;
-        }
-    }
-    r.keep = true;
+    RowResult r;
+    r.keep = pass;
     r.t1 = i1;
     r.d1 = d1;
     return r;
@@ -281,8 +337,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizePar
         if (p.phase == 1 && threadIdx.x == 0) p.gather_cnt[pair] = 0;
         if (p.knn_idx) {
             for (int q = threadIdx.x; q < fq; q += kFinThreads) {
-                RowResult r = p.win_keys ? eval_row_win<KIND>(p, rk1, rk2, ck1, qrows, trows, qbits, tbits, q, ft, p.knn_idx, p.knn_dist)
-                                         : eval_row<KIND>(p, rk1, rk2, ck1, ck2, qrows, trows, q, fq, p.knn_idx, p.knn_dist);
+                RowResult r = eval_row<KIND>(p, rk1, rk2, ck1, ck2, qrows, trows, q, fq, p.knn_idx, p.knn_dist);     // (knn output: never slice keys)
                 (void)r;
             }
         }
@@ -314,23 +369,33 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const FinalizePar
         if (threadIdx.x == 0) s_targets = 0;
         __syncthreads();
     }
+    if (p.win_keys) {
+        // slice keys: every warp takes 32 consecutive rows per iteration and evaluates their slices cooperatively
+        for (int q0 = warp * 32; q0 < fq; q0 += kFinThreads) {
+            const int q = q0 + lane;
+            const bool valid = q < fq;
+            const u64 k1 = valid ? rk1[q] : kKeyInit, k2 = valid ? rk2[q] : kKeyInit;
+            const RowResult r = eval_rows_win<KIND>(p, k1, k2, qrows, trows, qbits, tbits, q, ft, valid);
+            if (!valid) continue;
+            rk1[q] = r.keep ? make_key(__float_as_uint(r.d1), (uint32_t)r.t1) : kKeyInit;
+            mine += r.keep ? 1u : 0u;
+            if (p.phase == 1) {
+                // Who could beat a survivor (q, t) at its own train row t?  A row whose NEAREST train row is t (another survivor: settled by
+                // the claims below; a row that failed the ratio test: counted in histogram A by its best value), or a row for which t is at
+                // best second (then its second-best value is <= its distance to t: histogram B, every row).  A survivor whose distance
+                // lies below every such value needs no verification sweep.
+                if (k2 != kKeyInit) atomicAdd(&s_hist[1][fin_bucket<KIND>(__uint_as_float((uint32_t)(k2 >> 32)))], 1u);
+                if (!r.keep && k1 != kKeyInit) atomicAdd(&s_hist[0][fin_bucket<KIND>(__uint_as_float((uint32_t)(k1 >> 32)))], 1u);
+                // every train row some survivor points at is claimed by the nearest such query row (lowest index on ties)
+                if (r.keep) atomicMin(const_cast<u64*>(ck1) + r.t1, make_key(__float_as_uint(r.d1), (uint32_t)q));
+            }
+        }
+    } else {
     for (int q = threadIdx.x; q < fq; q += kFinThreads) {
-        u64 k1 = kKeyInit, k2 = kKeyInit;
-        if (p.phase == 1) { k1 = rk1[q]; k2 = rk2[q]; }        // (eval_row_win overwrites nothing; read before rk1[q] is restated below)
-        const RowResult r = p.win_keys ? eval_row_win<KIND>(p, rk1, rk2, ck1, qrows, trows, qbits, tbits, q, ft, p.knn_idx, p.knn_dist, p.phase == 0)
-                                       : eval_row<KIND>(p, rk1, rk2, ck1, ck2, qrows, trows, q, fq, p.knn_idx, p.knn_dist);
+        const RowResult r = eval_row<KIND>(p, rk1, rk2, ck1, ck2, qrows, trows, q, fq, p.knn_idx, p.knn_dist);
         rk1[q] = r.keep ? make_key(__float_as_uint(r.d1), (uint32_t)r.t1) : kKeyInit;
         mine += r.keep ? 1u : 0u;
-        if (p.phase == 1) {
-            // Who could beat a survivor (q, t) at its own train row t?  A row whose NEAREST train row is t (another survivor: settled by
-            // the claims below; a row that failed the ratio test: counted in histogram A by its best value), or a row for which t is at
-            // best second (then its second-best value is <= its distance to t: histogram B, every row).  A survivor whose distance
-            // lies below every such value needs no verification sweep.
-            if (k2 != kKeyInit) atomicAdd(&s_hist[1][fin_bucket<KIND>(__uint_as_float((uint32_t)(k2 >> 32)))], 1u);
-            if (!r.keep && k1 != kKeyInit) atomicAdd(&s_hist[0][fin_bucket<KIND>(__uint_as_float((uint32_t)(k1 >> 32)))], 1u);
-            // every train row some survivor points at is claimed by the nearest such query row (lowest index on ties)
-            if (r.keep) atomicMin(const_cast<u64*>(ck1) + r.t1, make_key(__float_as_uint(r.d1), (uint32_t)q));
-        }
+    }
     }
     }
     if (p.phase == 1) {
