@@ -740,7 +740,7 @@ bool use_win(const esfm_ctx* ctx, const esfm_bank* b) {
     return b->kind == ESFM_KIND_F32X64 ? ctx->l2_engine == ESFM_L2_ENGINE_TC16 : ctx->hamming_engine == ESFM_HAMMING_ENGINE_TC16;
 }
 
-ChunkPlan plan_chunks(const esfm_bank* b, int64_t n_pairs) {
+ChunkPlan plan_chunks(const esfm_bank* b, int64_t n_pairs, bool split_for_overlap = false) {
     ChunkPlan pl;
     const int padded = ((b->max_rows + kTile - 1) / kTile) * kTile;
     pl.stride = std::max(padded, kTile);
@@ -751,7 +751,13 @@ ChunkPlan plan_chunks(const esfm_bank* b, int64_t n_pairs) {
     size_t c = std::min(budget_keys / key_bytes_per_pair, budget_arena / arena_bytes_per_pair);
     c = std::max<size_t>(1, std::min<size_t>(c, 65536));
     if (const char* e = getenv("ESFM_CHUNK_PAIRS")) c = std::max<size_t>(1, std::min<size_t>(c, (size_t)atoll(e)));   // tests: force several chunks
-    pl.chunk_pairs = (size_t)std::min<int64_t>((int64_t)c, std::max<int64_t>(n_pairs, 1));
+    // Balanced chunks: chunk k's matches travel to the host while chunk k + 1 is swept, so (a) chunks of equal size (a full chunk followed by
+    // a small remainder hides almost nothing) and (b) a batch worth splitting (>= 16k pairs) runs as at least four chunks even when it
+    // would fit in one: only the last chunk's download is exposed.  Chunks stay >= 4k pairs (one CTA per pair needs >= 592).
+    const int64_t n = std::max<int64_t>(n_pairs, 1);
+    int64_t n_chunks = (n + (int64_t)c - 1) / (int64_t)c;
+    if (split_for_overlap && n >= 16384 && !getenv("ESFM_CHUNK_PAIRS")) n_chunks = std::max<int64_t>(n_chunks, std::min<int64_t>(4, n / 4096));
+    pl.chunk_pairs = (size_t)((n + n_chunks - 1) / n_chunks);
     return pl;
 }
 
@@ -1013,7 +1019,7 @@ int esfm::match_pairs_impl(esfm_bank* b, const esfm_pair_t* pairs, int64_t n_pai
     }
     if (n_pairs == 0) { guard.r = nullptr; *out = res; return ESFM_OK; }
 
-    const ChunkPlan pl = plan_chunks(b, n_pairs);
+    const ChunkPlan pl = plan_chunks(b, n_pairs, opts.fetch);       // (a device-resident batch must stay one chunk if it can)
     const size_t n_chunks = ((size_t)n_pairs + pl.chunk_pairs - 1) / pl.chunk_pairs;
     const bool streamed = opts.fetch && (n_chunks > 1 || digests_only);   // matches go to pageable memory through the pinned slots
     if (int rc = ensure_scratch(ctx, b, pl, n_chunks > 1 ? 2 : 1)) return rc;
