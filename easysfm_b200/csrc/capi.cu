@@ -751,13 +751,10 @@ ChunkPlan plan_chunks(const esfm_bank* b, int64_t n_pairs, bool split_for_overla
     size_t c = std::min(budget_keys / key_bytes_per_pair, budget_arena / arena_bytes_per_pair);
     c = std::max<size_t>(1, std::min<size_t>(c, 65536));
     if (const char* e = getenv("ESFM_CHUNK_PAIRS")) c = std::max<size_t>(1, std::min<size_t>(c, (size_t)atoll(e)));   // tests: force several chunks
-    // Balanced chunks: chunk k's matches travel to the host while chunk k + 1 is swept, so (a) chunks of equal size (a full chunk followed by
-    // a small remainder hides almost nothing) and (b) a batch worth splitting (>= 16k pairs) runs as at least four chunks even when it
-    // would fit in one: only the last chunk's download is exposed.  Chunks stay >= 4k pairs (one CTA per pair needs >= 592).
-    const int64_t n = std::max<int64_t>(n_pairs, 1);
-    int64_t n_chunks = (n + (int64_t)c - 1) / (int64_t)c;
-    if (split_for_overlap && n >= 16384 && !getenv("ESFM_CHUNK_PAIRS")) n_chunks = std::max<int64_t>(n_chunks, std::min<int64_t>(4, n / 4096));
-    pl.chunk_pairs = (size_t)((n + n_chunks - 1) / n_chunks);
+    // (Measured: splitting a batch that fits in one or two chunks into four equal ones to overlap more of the match download LOSES -- ORB e2e
+    // 3.99e12 -> 3.38e12 comparisons/s: per-chunk launches, synchronisations and the pinned-slot streaming cost more than the exposed copy.)
+    (void)split_for_overlap;
+    pl.chunk_pairs = (size_t)std::min<int64_t>((int64_t)c, std::max<int64_t>(n_pairs, 1));
     return pl;
 }
 
