@@ -134,6 +134,7 @@ SIGNATURES = {
     "esfm_results_segment_count": (c_int, [c_void_p, POINTER(c_int)]),
     "esfm_two_view_default_params": (c_int, [POINTER(TwoViewParams)]),
     "esfm_two_view_batch": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(TwoViewParams), c_void_p, c_void_p]),
+    "esfm_two_view_depth": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_double), POINTER(c_int32)]),
     "esfm_results_segment_at": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_int64)]),
     "esfm_results_pair_layout": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int64)]),
     "esfm_results_device_matches": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64)]),
@@ -314,6 +315,16 @@ class Context:
         _check(self._lib.esfm_two_view_batch(self._h, n_pairs, pair_off.ctypes.data, pts1.ctypes.data, pts2.ctypes.data, K.ctypes.data, k_per_pair,
                                              ctypes.byref(prm), mask.ctypes.data, out.ctypes.data))
         return mask[:total], out[:n_pairs]
+
+    def two_view_depth(self, pts1, pts2, K, R, t, random_rate=20) -> float:
+        """esfm_two_view_depth: MotionEstimator::getDepthFast for one pair (every random_rate-th match, [I|0] and [R|t])."""
+        pts1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        pts2 = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+        K, R, t = (np.ascontiguousarray(a, np.float64) for a in (K, R, t))
+        depth, used = c_double(0.0), c_int32(0)
+        _check(self._lib.esfm_two_view_depth(self._h, len(pts1), pts1.ctypes.data, pts2.ctypes.data, K.ctypes.data, R.ctypes.data, t.ctypes.data,
+                                             int(random_rate), ctypes.byref(depth), ctypes.byref(used)))
+        return depth.value
 
     def bank_from_frames(self, frames) -> "Bank":
         """frames: sequence of 2-D numpy arrays (all float32 x64 or all uint8 x32)."""

@@ -247,6 +247,35 @@ __global__ void __launch_bounds__(kTvPoseThreads) tv_pose_kernel(const double2* 
     }
 }
 
+// getDepthFast on its own (estimate_motion.cpp:234-283): every random_rate-th of the GIVEN matches triangulated with [I|0], [R|t]; mean norm.
+// One block; deterministic summation (per-thread partial sums added in thread order).
+__global__ void __launch_bounds__(kTvPoseThreads) tv_depth_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int n, const double* __restrict__ K,
+                                                                   const double* __restrict__ Rt, int random_rate, double* __restrict__ out) {
+    __shared__ double sh_d[kTvPoseThreads];
+    __shared__ int sh_n[kTvPoseThreads];
+    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    double acc = 0.0;
+    int used = 0;
+    for (int i = threadIdx.x * random_rate; i < n; i += kTvPoseThreads * random_rate) {
+        double Q[4];
+        tv::triangulate_dlt(Rt, Rt + 9, ((double)p1[2 * i] - cx) / fx, ((double)p1[2 * i + 1] - cy) / fy, ((double)p2[2 * i] - cx) / fx,
+                            ((double)p2[2 * i + 1] - cy) / fy, Q);
+        const double x = Q[0] / Q[3], y = Q[1] / Q[3], z = Q[2] / Q[3];
+        acc += sqrt(x * x + y * y + z * z);
+        ++used;
+    }
+    sh_d[threadIdx.x] = acc;
+    sh_n[threadIdx.x] = used;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sum = 0.0;
+        int cnt = 0;
+        for (int w = 0; w < kTvPoseThreads; ++w) { sum += sh_d[w]; cnt += sh_n[w]; }
+        out[0] = cnt > 0 ? sum / cnt : 0.0;
+        out[1] = (double)cnt;
+    }
+}
+
 struct DevBuf {
     void* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -333,5 +362,34 @@ extern "C" int esfm_two_view_batch(esfm_ctx_t* ctx, int64_t n_pairs, const int64
         CUDA_TRY(cudaStreamSynchronize(s));
         ctx->stats.d2h_bytes += (size_t)npts + (size_t)np * sizeof(esfm_two_view_t);
     }
+    return ESFM_OK;
+}
+
+extern "C" int esfm_two_view_depth(esfm_ctx_t* ctx, int64_t n_matches, const float* pts1, const float* pts2, const double* K, const double* R,
+                                   const double* t, int random_rate, double* depth, int32_t* n_used) {
+    if (!ctx || !K || !R || !t || !depth || n_matches < 0 || random_rate < 1) return fail(ESFM_ERR_INVALID, "esfm_two_view_depth: bad argument");
+    if (n_matches > 0 && (!pts1 || !pts2)) return fail(ESFM_ERR_INVALID, "esfm_two_view_depth: NULL point arrays");
+    if (int rc = set_device(ctx)) return rc;
+    *depth = 0.0;
+    if (n_used) *n_used = 0;
+    if (n_matches == 0) return ESFM_OK;
+    cudaStream_t s = ctx->stream;
+    DevBuf d_p1, d_p2, d_par, d_out;
+    CUDA_TRY(d_p1.alloc((size_t)n_matches * 8)); CUDA_TRY(d_p2.alloc((size_t)n_matches * 8)); CUDA_TRY(d_par.alloc(21 * 8)); CUDA_TRY(d_out.alloc(16));
+    double par[21];
+    for (int e = 0; e < 9; ++e) { par[e] = K[e]; par[9 + e] = R[e]; }
+    for (int e = 0; e < 3; ++e) par[18 + e] = t[e];
+    CUDA_TRY(cudaMemcpyAsync(d_p1.p, pts1, (size_t)n_matches * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_p2.p, pts2, (size_t)n_matches * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_par.p, par, sizeof par, cudaMemcpyHostToDevice, s));
+    tv_depth_kernel<<<1, kTvPoseThreads, 0, s>>>(d_p1.as<float>(), d_p2.as<float>(), (int)n_matches, d_par.as<double>(), d_par.as<double>() + 9, random_rate,
+                                                 d_out.as<double>());
+    CUDA_TRY(cudaGetLastError());
+    double out[2];
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    ctx->stats.kernel_launches += 1;
+    *depth = out[0];
+    if (n_used) *n_used = (int32_t)out[1];
     return ESFM_OK;
 }

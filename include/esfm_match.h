@@ -360,6 +360,11 @@ typedef struct esfm_two_view_t {
 int esfm_two_view_default_params(esfm_two_view_params_t* params);
 int esfm_two_view_batch(esfm_ctx_t* ctx, int64_t n_pairs, const int64_t* pair_off, const float* pts1, const float* pts2, const double* K,
                         int k_per_pair, const esfm_two_view_params_t* params, unsigned char* inlier_mask, esfm_two_view_t* out);
+/* MotionEstimator::getDepthFast on its own (estimate_motion.cpp:234-283; decl estimate_motion.h:26-27, random_rate default 20): every
+ * random_rate-th of the given matches (pixel coordinates, as above) triangulated with [I|0] and T_21 = [R | t]; *depth = the mean norm of the
+ * points in baseline lengths, *n_used (optional) = how many were triangulated. */
+int esfm_two_view_depth(esfm_ctx_t* ctx, int64_t n_matches, const float* pts1, const float* pts2, const double* K, const double* R,
+                        const double* t, int random_rate, double* depth, int32_t* n_used);
 
 #ifdef __cplusplus
 }

@@ -27,8 +27,24 @@ struct DMatch {
     int queryIdx = -1, trainIdx = -1, imgIdx = -1;
     float distance = 0.f;
 };
-struct KeyPoint {};
+struct Point2f {
+    float x = 0.f, y = 0.f;
+};
+struct KeyPoint {
+    Point2f pt;
+};
 }  // namespace cv
+
+// the slice of Eigen the two-view shim touches: fixed-size float matrices with element access (utility.h:36-37, estimate_motion.h:17-27)
+namespace Eigen {
+template <int N> struct MatrixNf {
+    float m[N][N] = {};
+    float& operator()(int r, int c) { return m[r][c]; }
+    float operator()(int r, int c) const { return m[r][c]; }
+};
+typedef MatrixNf<3> Matrix3f;
+typedef MatrixNf<4> Matrix4f;
+}  // namespace Eigen
 
 namespace p3dv {
 struct frame_t {
@@ -37,6 +53,7 @@ struct frame_t {
     std::vector<cv::KeyPoint> keypoints;
     cv::Mat descriptors;
     std::vector<int> unique_pixel_ids;
+    Eigen::Matrix3f K_cam;       // intrinsic elements of the camera (utility.h:37)
 };
 
 class FeatureMatching {

@@ -61,3 +61,75 @@ def test_shim_matches_oracle(tmp_path, feature, prepare):
             else:
                 assert cnt == 0
     assert pos == len(raw)
+
+
+# --------------------------------------------------------------------------------------------------
+# the two-view shim: p3dv::MotionEstimator::estimate2D2D_E5P_RANSAC / getDepthFast
+# --------------------------------------------------------------------------------------------------
+MOTION_SHIM = os.path.join(ROOT, "easysfm_b200", "shim", "estimate_motion_gpu.cpp")
+
+
+def build_motion_shim(tmp):
+    exe = os.path.join(tmp, "motion_main")
+    cmd = ["g++", "-std=c++14", "-O1", "-Wall", "-I", os.path.join(ROOT, "tests", "shim"), "-I", os.path.join(ROOT, "include"),
+           MOTION_SHIM, os.path.join(ROOT, "tests", "shim", "motion_main.cpp"), "-L", LIBDIR, "-lesfm_match", f"-Wl,-rpath,{LIBDIR}", "-o", exe]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_motion_shim_compiles_and_links(tmp_path):
+    assert os.path.exists(build_motion_shim(str(tmp_path)))
+
+
+@pytest.mark.gpu
+def test_motion_shim_matches_oracle(tmp_path):
+    """The C++ drop-in keeps the reference's signatures (estimate_motion.h:17-20, :26-27); driven like sfm.cpp:165-166 it must give the
+    oracle's inlier matches, T = [R t; 0 1] (float) and getDepthFast's mean depth (every 20th inlier)."""
+    import oracle
+    from oracle import two_view_oracle as tvo
+    from two_view_util import scene
+    exe = build_motion_shim(str(tmp_path))
+    rng = np.random.default_rng(8)
+    cases = []
+    inp = os.path.join(str(tmp_path), "in.bin")
+    with open(inp, "wb") as f:
+        specs = [(400, 0.4, 0.3), (250, 0.8, 0.1), (4, 0.0, 0.0)]
+        K = scene(5, 0, 0, 0)[0]
+        f.write(np.int32(len(specs)).tobytes())
+        f.write(np.ascontiguousarray(K, np.float64).tobytes())
+        for k, (n, noise, outl) in enumerate(specs):
+            _, x1, x2, R, t = scene(n, noise, outl, 40 + k)
+            p1, p2 = rng.permutation(n), rng.permutation(n)
+            kp1, kp2 = np.zeros((n, 2), np.float32), np.zeros((n, 2), np.float32)
+            kp1[p1], kp2[p2] = x1, x2
+            m = np.zeros(n, oracle.DMATCH_DTYPE)
+            m["queryIdx"], m["trainIdx"], m["distance"] = p1, p2, rng.random(n).astype(np.float32)
+            f.write(np.array([n, n, n], np.int32).tobytes())
+            f.write(kp1.tobytes()); f.write(kp2.tobytes()); f.write(m.tobytes())
+            cases.append((x1, x2, m, K))
+    out = os.path.join(str(tmp_path), "out.bin")
+    subprocess.check_call([exe, inp, out], stdout=subprocess.DEVNULL)
+    raw = open(out, "rb").read()
+    pos = 0
+    for k, (x1, x2, m, K) in enumerate(cases):
+        ok, ni = np.frombuffer(raw, np.int32, 2, pos); pos += 8
+        T = np.frombuffer(raw, np.float32, 16, pos).reshape(4, 4); pos += 64
+        depth = float(np.frombuffer(raw, np.float64, 1, pos)[0]); pos += 8
+        inl = np.frombuffer(raw, oracle.DMATCH_DTYPE, int(ni), pos); pos += 16 * int(ni)
+        pair_key = ((10 + 2 * k) << 32) | (11 + 2 * k)                       # the shim's sampler key: the two frame ids
+        ref = tvo.estimate_two_view(x1, x2, K, 0.99, 1.0, 1000, seed=0, pair=pair_key)
+        assert ok == 1
+        if ref["E"] is None:
+            assert ni == 0
+            continue
+        want = m[ref["mask"].astype(bool)]
+        assert abs(int(ni) - len(want)) <= 1
+        if int(ni) == len(want):
+            assert inl.tobytes() == want.tobytes()
+            np.testing.assert_allclose(T[:3, :3], ref["R"], atol=1e-5)
+            np.testing.assert_allclose(T[:3, 3], ref["t"], atol=1e-5)
+            assert T[3].tolist() == [0.0, 0.0, 0.0, 1.0]
+            # getDepthFast: every 20th INLIER with the float T the caller holds
+            d_ref = tvo.mean_depth(T[:3, :3].astype(np.float64), T[:3, 3].astype(np.float64), x1, x2, K, ref["mask"], 20)
+            np.testing.assert_allclose(depth, d_ref, rtol=1e-6)
+    assert pos == len(raw)
