@@ -25,7 +25,7 @@ namespace esfm {
 
 namespace {
 
-constexpr int kTvRound = 128;          // hypotheses per round and pair
+constexpr int kTvRound = 64;           // hypotheses per round and pair (the stopping rule fires after ~65 on typical pairs: 128 wasted half of round 1)
 constexpr int kTvPoseThreads = 128;
 
 struct TvState {                       // per pair, device
@@ -276,10 +276,16 @@ __global__ void __launch_bounds__(kTvPoseThreads) tv_depth_kernel(const float* _
     }
 }
 
+// device scratch of one call, from the context's private stream-ordered pool (freed blocks stay cached there: repeated calls do not
+// allocate; cudaMalloc / cudaFree per call cost a third of a 2048-pair batch)
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+    esfm_ctx* ctx = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, ctx->stream); }
+    cudaError_t alloc(esfm_ctx* c, size_t bytes) {
+        ctx = c;
+        return cudaMallocFromPoolAsync(&p, std::max<size_t>(bytes, 16), c->mempool, c->stream);
+    }
     template <typename T> T* as() { return static_cast<T*>(p); }
 };
 
@@ -319,12 +325,12 @@ extern "C" int esfm_two_view_batch(esfm_ctx_t* ctx, int64_t n_pairs, const int64
     const int64_t max_pairs = std::min<int64_t>(chunk, n_pairs);
     int64_t max_pts = 0;
     for (int64_t c0 = 0; c0 < n_pairs; c0 += chunk) max_pts = std::max<int64_t>(max_pts, pair_off[std::min(n_pairs, c0 + chunk)] - pair_off[c0]);
-    CUDA_TRY(d_p1.alloc((size_t)max_pts * 8)); CUDA_TRY(d_p2.alloc((size_t)max_pts * 8));
-    CUDA_TRY(d_n1.alloc((size_t)max_pts * 16)); CUDA_TRY(d_n2.alloc((size_t)max_pts * 16));
-    CUDA_TRY(d_K.alloc((size_t)(k_per_pair ? max_pairs : 1) * 72)); CUDA_TRY(d_off.alloc((size_t)(max_pairs + 1) * 8));
-    CUDA_TRY(d_models.alloc((size_t)max_pairs * kTvRound * 90 * 8)); CUDA_TRY(d_nm.alloc((size_t)max_pairs * kTvRound * 4));
-    CUDA_TRY(d_counts.alloc((size_t)max_pairs * kTvRound * 10 * 4)); CUDA_TRY(d_state.alloc((size_t)max_pairs * sizeof(TvState)));
-    CUDA_TRY(d_mask.alloc((size_t)max_pts)); CUDA_TRY(d_out.alloc((size_t)max_pairs * sizeof(esfm_two_view_t)));
+    CUDA_TRY(d_p1.alloc(ctx, (size_t)max_pts * 8)); CUDA_TRY(d_p2.alloc(ctx, (size_t)max_pts * 8));
+    CUDA_TRY(d_n1.alloc(ctx, (size_t)max_pts * 16)); CUDA_TRY(d_n2.alloc(ctx, (size_t)max_pts * 16));
+    CUDA_TRY(d_K.alloc(ctx, (size_t)(k_per_pair ? max_pairs : 1) * 72)); CUDA_TRY(d_off.alloc(ctx, (size_t)(max_pairs + 1) * 8));
+    CUDA_TRY(d_models.alloc(ctx, (size_t)max_pairs * kTvRound * 90 * 8)); CUDA_TRY(d_nm.alloc(ctx, (size_t)max_pairs * kTvRound * 4));
+    CUDA_TRY(d_counts.alloc(ctx, (size_t)max_pairs * kTvRound * 10 * 4)); CUDA_TRY(d_state.alloc(ctx, (size_t)max_pairs * sizeof(TvState)));
+    CUDA_TRY(d_mask.alloc(ctx, (size_t)max_pts)); CUDA_TRY(d_out.alloc(ctx, (size_t)max_pairs * sizeof(esfm_two_view_t)));
     std::vector<long long> off;
     const int rounds = (params->max_iters + kTvRound - 1) / kTvRound;
     for (int64_t c0 = 0; c0 < n_pairs; c0 += chunk) {
@@ -375,7 +381,7 @@ extern "C" int esfm_two_view_depth(esfm_ctx_t* ctx, int64_t n_matches, const flo
     if (n_matches == 0) return ESFM_OK;
     cudaStream_t s = ctx->stream;
     DevBuf d_p1, d_p2, d_par, d_out;
-    CUDA_TRY(d_p1.alloc((size_t)n_matches * 8)); CUDA_TRY(d_p2.alloc((size_t)n_matches * 8)); CUDA_TRY(d_par.alloc(21 * 8)); CUDA_TRY(d_out.alloc(16));
+    CUDA_TRY(d_p1.alloc(ctx, (size_t)n_matches * 8)); CUDA_TRY(d_p2.alloc(ctx, (size_t)n_matches * 8)); CUDA_TRY(d_par.alloc(ctx, 21 * 8)); CUDA_TRY(d_out.alloc(ctx, 16));
     double par[21];
     for (int e = 0; e < 9; ++e) { par[e] = K[e]; par[9 + e] = R[e]; }
     for (int e = 0; e < 3; ++e) par[18 + e] = t[e];
