@@ -83,6 +83,10 @@ TWO_VIEW_DTYPE = np.dtype([("E", "<f8", (3, 3)), ("R", "<f8", (3, 3)), ("t", "<f
                            ("n_good", "<i4"), ("iters", "<i4"), ("ok", "<i4"), ("reserved", "<i4")])
 assert TWO_VIEW_DTYPE.itemsize == ctypes.sizeof(TwoView)
 
+# esfm_keypoint_t: the cv::KeyPoint fields the reference reads (class_id is always -1)
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4")])
+ERR_CAPACITY = 5
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header.
 SIGNATURES = {
     "esfm_abi_version": (c_int, []),
@@ -135,6 +139,9 @@ SIGNATURES = {
     "esfm_two_view_default_params": (c_int, [POINTER(TwoViewParams)]),
     "esfm_two_view_batch": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(TwoViewParams), c_void_p, c_void_p]),
     "esfm_two_view_depth": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_double), POINTER(c_int32)]),
+    "esfm_orb_extract": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_size_t, c_int, c_void_p, c_void_p, c_int, POINTER(c_int)]),
+    "esfm_bank_set_frame_from_image": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_size_t, c_int, c_void_p, c_void_p, c_int, POINTER(c_int)]),
+    "esfm_orb_debug_level": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, POINTER(c_int), POINTER(c_int)]),
     "esfm_results_segment_at": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_int64)]),
     "esfm_results_pair_layout": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int64)]),
     "esfm_results_device_matches": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64)]),
@@ -194,6 +201,16 @@ def _check(rc: int):
     if rc != 0:
         msg = load_library().esfm_last_error()
         raise EsfmError(rc, msg.decode("utf-8", "replace") if msg else "")
+
+
+def _as_image(image):
+    img = np.asarray(image)
+    if img.dtype != np.uint8 or img.ndim not in (2, 3) or (img.ndim == 3 and img.shape[2] not in (1, 3)):
+        raise TypeError("image must be uint8 [rows, cols] (gray) or [rows, cols, 3] (BGR)")
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    if img.strides[-1] != 1 or (img.ndim == 3 and img.strides[1] != ch):
+        img = np.ascontiguousarray(img)
+    return img, img.shape[0], img.shape[1], ch
 
 
 def _as_desc(arr, kind=None):
@@ -326,6 +343,31 @@ class Context:
                                              int(random_rate), ctypes.byref(depth), ctypes.byref(used)))
         return depth.value
 
+    def orb_extract(self, image, max_features: int = 5000, want_descriptors: bool = True):
+        """esfm_orb_extract: FeatureMatching::detectFeaturesORB (feature_matching.cpp:14-41) for one image -- uint8 [rows, cols] (gray) or
+        [rows, cols, 3] (BGR).  Returns (key points as KEYPOINT_DTYPE records in cv2's order, uint8 [n, 32] descriptors)."""
+        img, rows, cols, ch = _as_image(image)
+        cap = int(max_features) + 256
+        while True:
+            kps = np.zeros(cap, KEYPOINT_DTYPE)
+            desc = np.zeros((cap, 32), np.uint8) if want_descriptors else None
+            n = c_int(0)
+            rc = self._lib.esfm_orb_extract(self._h, img.ctypes.data, rows, cols, ch, img.strides[0], int(max_features), kps.ctypes.data,
+                                            desc.ctypes.data if want_descriptors else None, cap, ctypes.byref(n))
+            if rc == ERR_CAPACITY and n.value > cap:
+                cap = n.value
+                continue
+            _check(rc)
+            return kps[:n.value].copy(), (desc[:n.value].copy() if want_descriptors else None)
+
+    def orb_debug_level(self, level: int, blurred: bool = False) -> np.ndarray:
+        """Pyramid level of the last orb_extract call on this context, as resized or after the 7 x 7 blur (tests)."""
+        r, c = c_int(0), c_int(0)
+        _check(self._lib.esfm_orb_debug_level(self._h, int(level), int(blurred), None, 0, ctypes.byref(r), ctypes.byref(c)))
+        out = np.zeros((r.value, c.value), np.uint8)
+        _check(self._lib.esfm_orb_debug_level(self._h, int(level), int(blurred), out.ctypes.data, out.nbytes, ctypes.byref(r), ctypes.byref(c)))
+        return out
+
     def bank_from_frames(self, frames) -> "Bank":
         """frames: sequence of 2-D numpy arrays (all float32 x64 or all uint8 x32)."""
         frames = list(frames)
@@ -385,6 +427,23 @@ class Bank:
         a, _ = _as_desc(desc, self.kind)
         _check(self._lib.esfm_bank_set_frame(self._h, int(frame_id), a.ctypes.data, a.shape[0], a.shape[1],
                                              a.strides[0] if a.shape[0] else a.shape[1] * a.itemsize))
+
+    def set_frame_from_image(self, frame_id: int, image, max_features: int = 5000, want_descriptors: bool = False):
+        """esfm_bank_set_frame_from_image: ORB-extract `image` on the device and make the descriptors frame `frame_id` of this (B256) bank
+        without a round trip through the host.  Returns the key points (and the descriptors when asked for)."""
+        img, rows, cols, ch = _as_image(image)
+        cap = int(max_features) + 256
+        while True:
+            kps = np.zeros(cap, KEYPOINT_DTYPE)
+            desc = np.zeros((cap, 32), np.uint8) if want_descriptors else None
+            n = c_int(0)
+            rc = self._lib.esfm_bank_set_frame_from_image(self._h, int(frame_id), img.ctypes.data, rows, cols, ch, img.strides[0], int(max_features),
+                                                          kps.ctypes.data, desc.ctypes.data if want_descriptors else None, cap, ctypes.byref(n))
+            if rc == ERR_CAPACITY and n.value > cap:
+                cap = n.value
+                continue
+            _check(rc)
+            return (kps[:n.value].copy(), desc[:n.value].copy()) if want_descriptors else kps[:n.value].copy()
 
     def set_frame_pinned(self, frame_id: int, desc):
         """No host-side copy: `desc` must be a C-contiguous array in page-locked memory (e.g. a view of a torch

@@ -323,6 +323,7 @@ extern "C" int esfm_destroy(esfm_ctx_t* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    orb_state_destroy(ctx);
     for (esfm_bank*& pb : ctx->pair_bank) {
         if (pb) esfm_bank_destroy(pb);
         pb = nullptr;
@@ -495,6 +496,38 @@ extern "C" int esfm_bank_set_frame(esfm_bank_t* b, int frame_id, const void* dat
     b->host_ext[frame_id] = nullptr;
     b->up_used += need;
     b->rows[frame_id] = rows;
+    return ESFM_OK;
+}
+
+// ORB extraction straight into the bank (orb.cu): the descriptors are produced on the device and land in the upload mirror at the place
+// esfm_bank_set_frame would have copied them to; the pinned half of the staging pair stays unwritten for this frame (esfm_bank_commit reads
+// staged frames from the mirror only).
+extern "C" int esfm_bank_set_frame_from_image(esfm_bank_t* b, int frame_id, const unsigned char* image, int rows, int cols, int channels,
+                                              size_t row_stride, int max_features, esfm_keypoint_t* keypoints, unsigned char* descriptors_host,
+                                              int capacity, int* n_out) {
+    if (!b) return fail(ESFM_ERR_INVALID, "bank is NULL");
+    if (b->kind != ESFM_KIND_B256) return fail(ESFM_ERR_INVALID, "esfm_bank_set_frame_from_image needs a B256 bank");
+    if (b->committed || b->device_allocated) return fail(ESFM_ERR_STATE, "esfm_bank_set_frame_from_image: bank already committed");
+    if (frame_id < 0 || frame_id >= b->n_frames) return fail(ESFM_ERR_INVALID, "frame_id %d out of range [0,%d)", frame_id, b->n_frames);
+    esfm_ctx* ctx = b->ctx;
+    size_t at = 0;
+    const OrbSink sink = [&](int n, uint8_t** d_dst) -> int {
+        if (int rc = check_frame_limits(b, n)) return rc;
+        if (int rc = staging_reserve(b, (size_t)n * 32)) return rc;
+        at = b->up_used;
+        *d_dst = b->d_up + at;
+        return ESFM_OK;
+    };
+    int n = 0;
+    if (int rc = orb_extract_impl(ctx, image, rows, cols, channels, row_stride, max_features, keypoints, descriptors_host, capacity, &n, sink)) {
+        if (n_out) *n_out = n;
+        return rc;
+    }
+    if (n_out) *n_out = n;
+    b->host_off[frame_id] = at;
+    b->host_ext[frame_id] = nullptr;
+    b->up_used = at + (size_t)n * 32;
+    b->rows[frame_id] = n;
     return ESFM_OK;
 }
 

@@ -5,6 +5,7 @@
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -67,6 +68,8 @@ struct ChunkBuf {
     bool copy_pending = false;                   // a device->host copy of the arena may still be in flight (ev_copied)
 };
 
+struct OrbState;                                 // scratch of the ORB extractor (orb.cu), kept between calls
+
 }  // namespace esfm
 
 struct esfm_ctx {
@@ -102,6 +105,7 @@ struct esfm_ctx {
     esfm_dmatch_t* h_slot[kSlots] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_slot[kSlots] = {nullptr, nullptr, nullptr, nullptr};
     esfm_dmatch_t* h_scratch = nullptr; size_t h_scratch_cap = 0;   // pageable scratch of digests-only batches (one chunk's matches)
+    esfm::OrbState* orb = nullptr;
     struct esfm_bank* pair_bank[2] = {nullptr, nullptr};   // reusable two-frame banks of esfm_match_descriptors, one per kind
 };
 
@@ -173,6 +177,12 @@ uint64_t digest_matches(const esfm_dmatch_t* m, int n);
 void* pool_acquire(esfm_ctx* ctx, size_t bytes, size_t* got);
 void pool_release(esfm_ctx* ctx, void* ptr);
 esfm_dmatch_t* heap_segment_alloc(size_t n_matches);
+// orb.cu: the extractor behind esfm_orb_extract / esfm_bank_set_frame_from_image.  `sink`, when set, is called once the number of key points
+// is known and returns the device address the n x 32 descriptor bytes go to (nullptr: the extractor's own scratch).
+using OrbSink = std::function<int(int n, uint8_t** d_dst)>;
+int orb_extract_impl(esfm_ctx* ctx, const unsigned char* image, int rows, int cols, int channels, size_t row_stride, int max_features,
+                     esfm_keypoint_t* keypoints, unsigned char* h_desc, int capacity, int* n_out, const OrbSink& sink);
+void orb_state_destroy(esfm_ctx* ctx);
 int reserve_stream_slots(esfm_ctx* ctx);     // allocate the pinned slots now (esfm_multi_init: outside any job's clock)
 
 }  // namespace esfm

@@ -5,6 +5,9 @@ Mirrors, name for name:
       cpp_code/include/feature_matching.h:17-21, cpp_code/src/feature_matching.cpp:71-158
       (bool return, matches APPENDED to the caller's list, ratio defaults 0.8 / 0.5, `show` accepted and ignored:
        it only opens GUI windows in the reference, :99-110)
+  p3dv::FeatureMatching::detectFeaturesORB
+      cpp_code/include/feature_matching.h:13, cpp_code/src/feature_matching.cpp:14-41
+      (cv::ORB::create(max_num)->detect + ->compute; fills frame.keypoints and frame.descriptors; `show` ignored)
   frame_t (only the fields the path touches)   cpp_code/include/utility.h:21-54
   pairwise_match's two matcher strategies      python_code/feature_match.py:24-39
       ('mutual_nn' = BFMatcher(crossCheck=True).match sorted by distance, 'ratio_test' = knn-2 + ratio 0.7)
@@ -31,8 +34,9 @@ from .capi import DMATCH_DTYPE, KIND_B256, KIND_F32X64, Context
 class Frame:
     """The slice of frame_t the matching path reads: frame_id and descriptors (utility.h:23,31)."""
     frame_id: int
-    descriptors: np.ndarray
+    descriptors: Optional[np.ndarray] = None
     keypoints: Optional[Sequence] = None
+    rgb_image: Optional[np.ndarray] = None        # utility.h:25 (BGR or gray, uint8)
     image_file_path: str = ""
     unique_pixel_ids: List[int] = field(default_factory=list)
 
@@ -43,6 +47,27 @@ class FeatureMatching:
         self.cross_check = bool(cross_check)
         self.verbose = bool(verbose)
         self._prepared = None  # (kind, ratio, cross_check, results, {frame_id: bank index})
+
+    # ---- extraction (feature_matching.cpp:14-41) ----
+    def detectFeaturesORB(self, cur_frame: Frame, max_num: int = 5000, show: bool = False) -> bool:
+        """Key points (KEYPOINT_DTYPE records, cv2's order) and 32-byte descriptors of cur_frame.rgb_image, computed on the device."""
+        cur_frame.keypoints, cur_frame.descriptors = self.ctx.orb_extract(cur_frame.rgb_image, max_num)
+        if self.verbose:  # feature_matching.cpp:30 (the reference prints descriptors.size(), a cv::Size)
+            print(f"Found [32 x {len(cur_frame.keypoints)}] features")
+        return True
+
+    def prepare_from_images(self, frames: Sequence[Frame], ratio_thre: float, max_num: int = 5000, cross_check: Optional[bool] = None):
+        """detectFeaturesORB for every frame with the descriptors going straight into the bank (they never visit the host), then the
+        all-pairs pass of prepare().  frame.keypoints is filled; frame.descriptors is left as it was."""
+        cc = self.cross_check if cross_check is None else bool(cross_check)
+        from .capi import Bank
+        bank = Bank(self.ctx, KIND_B256, len(frames))
+        for k, f in enumerate(frames):
+            f.keypoints = bank.set_frame_from_image(k, f.rgb_image, max_num)
+        bank.commit()
+        res = bank.match_all_pairs(ratio_thre, cc)
+        self._prepared = (bank.kind, float(ratio_thre), cc, res, {int(f.frame_id): k for k, f in enumerate(frames)}, bank)
+        return res
 
     # ---- all-pairs pre-pass (the hook a maintainer inserts at cpp_code/test/sfm.cpp:131) ----
     def prepare(self, frames: Sequence[Frame], ratio_thre: float, cross_check: Optional[bool] = None):

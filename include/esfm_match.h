@@ -366,6 +366,37 @@ int esfm_two_view_batch(esfm_ctx_t* ctx, int64_t n_pairs, const int64_t* pair_of
 int esfm_two_view_depth(esfm_ctx_t* ctx, int64_t n_matches, const float* pts1, const float* pts2, const double* K, const double* R,
                         const double* t, int random_rate, double* depth, int32_t* n_used);
 
+/* ---- ORB extraction: the step before the path -------------------------------------------------------------
+ * Replaces FeatureMatching::detectFeaturesORB (cpp_code/src/feature_matching.cpp:14-41; decl cpp_code/include/feature_matching.h:13, called
+ * once per frame at cpp_code/test/sfm.cpp:116): cv::ORB::create(max_num)->detect(image, keypoints) followed by
+ * cv::ORB::create(max_num)->compute(image, keypoints, descriptors), with OpenCV's defaults (scale factor 1.2f, 8 levels, edge threshold 31,
+ * WTA_K 2, Harris score, patch size 31, FAST threshold 20).  image: 8-bit, 1 channel (gray) or 3 channels (BGR, converted as cv::cvtColor
+ * does), rows x cols, row_stride bytes between rows.  The pyramid (INTER_LINEAR_EXACT), FAST-9/16 score + non-maximum suppression, Harris
+ * responses, intensity-centroid angles, the 7 x 7 blur and the steered 256-bit rBRIEF tests run on the device; the host only replays
+ * KeyPointsFilter::retainBest's std::nth_element / std::partition on the device-computed responses, because the order that leaves the key
+ * points in is the row order of the frame's descriptors (and with it every lowest-index tie-break of the matcher).  Outputs are what cv2
+ * 4.13.0 returns, bit for bit: key points in the same order with the same pt / size / angle / response / octave (class_id is always -1),
+ * 32-byte descriptors.  keypoints / descriptors have room for `capacity` entries (descriptors may be NULL); ORB can return a few more than
+ * max_features when Harris responses tie at the cut, so leave slack; if capacity is too small the call fails with ESFM_ERR_CAPACITY and
+ * *n_out = the number needed. */
+typedef struct esfm_keypoint_t {
+    float x, y;               /* cv::KeyPoint::pt, full-resolution pixels */
+    float size;               /* 31 * level scale */
+    float angle;              /* degrees, [0, 360) */
+    float response;           /* Harris response */
+    int32_t octave;           /* pyramid level */
+} esfm_keypoint_t;
+int esfm_orb_extract(esfm_ctx_t* ctx, const unsigned char* image, int rows, int cols, int channels, size_t row_stride, int max_features,
+                     esfm_keypoint_t* keypoints, unsigned char* descriptors, int capacity, int* n_out);
+/* The same, with the descriptors written straight into a B256 bank that is being filled (in place of esfm_bank_set_frame): they never leave
+ * the device.  descriptors_host may be NULL. */
+int esfm_bank_set_frame_from_image(esfm_bank_t* bank, int frame_id, const unsigned char* image, int rows, int cols, int channels,
+                                   size_t row_stride, int max_features, esfm_keypoint_t* keypoints, unsigned char* descriptors_host,
+                                   int capacity, int* n_out);
+/* Intermediate results of the device stages, for tests: the pyramid level `level` of the last esfm_orb_extract call on this context
+ * (blurred = 0: as resized; 1: after the 7 x 7 blur), copied to out (rows * cols bytes, dense); *rows / *cols receive the level size. */
+int esfm_orb_debug_level(esfm_ctx_t* ctx, int level, int blurred, unsigned char* out, size_t out_bytes, int* rows, int* cols);
+
 #ifdef __cplusplus
 }
 #endif
