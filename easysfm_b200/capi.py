@@ -141,6 +141,7 @@ SIGNATURES = {
     "esfm_two_view_depth": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_double), POINTER(c_int32)]),
     "esfm_orb_extract": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_size_t, c_int, c_void_p, c_void_p, c_int, POINTER(c_int)]),
     "esfm_bank_set_frame_from_image": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_size_t, c_int, c_void_p, c_void_p, c_int, POINTER(c_int)]),
+    "esfm_orb_last_timing": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int)]),
     "esfm_orb_debug_level": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, POINTER(c_int), POINTER(c_int)]),
     "esfm_results_segment_at": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_int64)]),
     "esfm_results_pair_layout": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int64)]),
@@ -359,6 +360,13 @@ class Context:
                 continue
             _check(rc)
             return kps[:n.value].copy(), (desc[:n.value].copy() if want_descriptors else None)
+
+    def orb_last_timing(self) -> dict:
+        """Host wall-clock phases of the last orb_extract / set_frame_from_image on this context (esfm_orb_last_timing)."""
+        ms, corners = (c_double * 5)(), c_int(0)
+        _check(self._lib.esfm_orb_last_timing(self._h, ms, ctypes.byref(corners)))
+        return {"front_end_ms": ms[0], "corner_records_ms": ms[1], "host_selection_ms": ms[2], "descriptors_ms": ms[3], "total_ms": ms[4],
+                "corners": corners.value}
 
     def orb_debug_level(self, level: int, blurred: bool = False) -> np.ndarray:
         """Pyramid level of the last orb_extract call on this context, as resized or after the 7 x 7 blur (tests)."""

@@ -10,8 +10,9 @@
 //   orb_fast_kernel      FAST-9/16 corner test + corner score for every pixel of every level                 1 launch, all levels
 //   orb_nms_kernel       strict 8-neighbour maxima inside the 31-pixel edge band: one bit per pixel + per-row counts
 //   orb_scan_kernel      exclusive scan of the row counts (raster order is the order cv::FAST emits corners in)
-//   orb_cand_kernel      one warp per corner: position from the bit map, Harris response (7 x 7 block, integer gradients), intensity-
-//                        centroid moments over the radius-15 disc, fastAtan2
+//   orb_pos_kernel       one warp per row: the row's corners, left to right, into their slots
+//   orb_cand_kernel      one warp per corner: Harris response (7 x 7 block, integer gradients), intensity-centroid moments over the
+//                        radius-15 disc, fastAtan2
 //   orb_blur_kernel      7 x 7 sigma-2 blur of every level that has key points: float32 separable, fused multiply-adds in the order
 //                        OpenCV's AVX2 build executes them, round-half-even
 //   orb_desc_kernel      one warp per key point, one descriptor byte per lane: 16 rotated samples, 8 comparisons
@@ -24,7 +25,13 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/esfm_match.h"
@@ -54,7 +61,7 @@ struct OrbLevels {
 };
 
 struct OrbCand {
-    int xy;            // x | y << 16, level coordinates
+    int xy;            // x | y << 14 | level << 28, level coordinates
     float score;       // FAST corner score
     float harris;
     float angle;
@@ -250,10 +257,9 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-// One warp per image row: every corner of the row, left to right, gets its record at row_off[row] + rank -- position, FAST score, Harris
-// response (orb.cpp HarrisResponses: block 7, k 0.04) and orientation (orb.cpp ICAngles).
-__global__ void orb_cand_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ score, OrbLevels L, const unsigned* __restrict__ bits,
-                                const int* __restrict__ row_off, float harris_k, float scale4, OrbCand* __restrict__ cand) {
+// One warp per image row: the corners of the row, left to right, get the slots row_off[row] .. and their packed position
+// (x | y << 14 | level << 28) -- raster order is the order cv::FAST emits corners in.
+__global__ void orb_pos_kernel(OrbLevels L, const unsigned* __restrict__ bits, const int* __restrict__ row_off, OrbCand* __restrict__ cand) {
     const int grow = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (grow >= L.row0[L.n]) return;
@@ -261,54 +267,73 @@ __global__ void orb_cand_kernel(const uint8_t* __restrict__ pyr, const uint8_t* 
     if (row_off[grow + 1] == at) return;
     int l = 0;
     while (l + 1 < L.n && grow >= L.row0[l + 1]) ++l;
-    const int y0 = grow - L.row0[l], pitch = L.pitch[l];
-    const uint8_t* img = pyr + L.off[l];
+    const int y0 = grow - L.row0[l];
     const unsigned* wrow = bits + L.word0[l] + (size_t)y0 * L.words[l];
-    for (int wi = 0; wi < L.words[l]; ++wi) {
-        unsigned m = wrow[wi];
+    for (int base = 0; base < L.words[l]; base += 32) {
+        const int wi = base + lane;
+        unsigned m = wi < L.words[l] ? wrow[wi] : 0u;
+        const int cnt = __popc(m);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        int slot = at + incl - cnt;
         while (m) {
             const int x0 = wi * 32 + __ffs(m) - 1;
             m &= m - 1;
-            const uint8_t* c = img + (size_t)y0 * pitch + x0;
-            // Harris: 49 block pixels over the lanes
-            int a = 0, b = 0, cc = 0;
-            for (int t = lane; t < 49; t += 32) {
-                const uint8_t* p = c + (t / 7 - 3) * pitch + (t % 7 - 3);
-                const int ix = ((int)p[1] - (int)p[-1]) * 2 + ((int)p[-pitch + 1] - (int)p[-pitch - 1]) + ((int)p[pitch + 1] - (int)p[pitch - 1]);
-                const int iy = ((int)p[pitch] - (int)p[-pitch]) * 2 + ((int)p[pitch - 1] - (int)p[-pitch - 1]) + ((int)p[pitch + 1] - (int)p[-pitch + 1]);
-                a += ix * ix; b += iy * iy; cc += ix * iy;
-            }
-            // intensity centroid: lane <-> column u = lane - 15 of the disc
-            int m10 = 0, m01 = 0;
-            if (lane < 31) {
-                const int u = lane - kOrbHalfPatch, au = abs(u);
-                m10 = u * (int)c[u];
-                for (int v = 1; v <= kOrbHalfPatch; ++v) {
-                    if (au <= c_umax[v]) {
-                        const int plus = c[v * pitch + u], minus = c[-v * pitch + u];
-                        m01 += v * (plus - minus);
-                        m10 += u * (plus + minus);
-                    }
-                }
-            }
-            a = __reduce_add_sync(0xffffffffu, a);
-            b = __reduce_add_sync(0xffffffffu, b);
-            cc = __reduce_add_sync(0xffffffffu, cc);
-            m10 = __reduce_add_sync(0xffffffffu, m10);
-            m01 = __reduce_add_sync(0xffffffffu, m01);
-            if (lane == 0) {
-                const float fa = (float)a, fb = (float)b, fc = (float)cc;
-                const float tr = __fadd_rn(fa, fb);
-                const float r = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(harris_k, tr), tr)), scale4);
-                OrbCand o;
-                o.xy = x0 | (y0 << 16);
-                o.score = (float)score[L.off[l] + (size_t)y0 * pitch + x0];
-                o.harris = r;
-                o.angle = fast_atan2_deg((float)m01, (float)m10);
-                cand[at] = o;
-            }
-            ++at;
+            cand[slot++].xy = x0 | (y0 << 14) | (l << 28);
         }
+        at += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// One warp per corner: FAST score, Harris response (orb.cpp HarrisResponses: block 7, k 0.04) and orientation (orb.cpp ICAngles).
+__global__ void __launch_bounds__(256) orb_cand_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ score, OrbLevels L, int n_cand,
+                                                      float harris_k, float scale4, OrbCand* __restrict__ cand) {
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (idx >= n_cand) return;
+    const int xy = cand[idx].xy;
+    const int x0 = xy & 0x3fff, y0 = (xy >> 14) & 0x3fff, l = xy >> 28;
+    const int pitch = L.pitch[l];
+    const uint8_t* c = pyr + L.off[l] + (size_t)y0 * pitch + x0;
+    // Harris: 49 block pixels over the lanes
+    int a = 0, b = 0, cc = 0;
+    for (int t = lane; t < 49; t += 32) {
+        const uint8_t* p = c + (t / 7 - 3) * pitch + (t % 7 - 3);
+        const int ix = ((int)p[1] - (int)p[-1]) * 2 + ((int)p[-pitch + 1] - (int)p[-pitch - 1]) + ((int)p[pitch + 1] - (int)p[pitch - 1]);
+        const int iy = ((int)p[pitch] - (int)p[-pitch]) * 2 + ((int)p[pitch - 1] - (int)p[-pitch - 1]) + ((int)p[pitch + 1] - (int)p[-pitch + 1]);
+        a += ix * ix; b += iy * iy; cc += ix * iy;
+    }
+    // intensity centroid: lane <-> column u = lane - 15 of the disc
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - kOrbHalfPatch, au = abs(u);
+        m10 = u * (int)c[u];
+        for (int v = 1; v <= kOrbHalfPatch; ++v) {
+            if (au <= c_umax[v]) {
+                const int plus = c[v * pitch + u], minus = c[-v * pitch + u];
+                m01 += v * (plus - minus);
+                m10 += u * (plus + minus);
+            }
+        }
+    }
+    a = __reduce_add_sync(0xffffffffu, a);
+    b = __reduce_add_sync(0xffffffffu, b);
+    cc = __reduce_add_sync(0xffffffffu, cc);
+    m10 = __reduce_add_sync(0xffffffffu, m10);
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+    if (lane == 0) {
+        const float fa = (float)a, fb = (float)b, fc = (float)cc;
+        const float tr = __fadd_rn(fa, fb);
+        OrbCand o;
+        o.xy = xy;
+        o.score = (float)score[L.off[l] + (size_t)y0 * pitch + x0];
+        o.harris = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(harris_k, tr), tr)), scale4);
+        o.angle = fast_atan2_deg((float)m01, (float)m10);
+        cand[idx] = o;
     }
 }
 
@@ -422,6 +447,73 @@ int grow_host(T** p, size_t* cap, size_t need) {
     return ESFM_OK;
 }
 
+// A few persistent host threads for the per-level selection (levels are independent; level 0 holds ~31 % of the corners).
+class TaskPool {
+public:
+    explicit TaskPool(int helpers) {
+        for (int k = 0; k < helpers; ++k) threads_.emplace_back([this] { worker(); });
+    }
+    ~TaskPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            ++epoch_;
+        }
+        cv_work_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    // fn(i) for i in [0, count), on the helpers and the calling thread; returns when all are done
+    void run(int count, const std::function<void(int)>& fn) {
+        if (threads_.empty() || count <= 1) {
+            for (int i = 0; i < count; ++i) fn(i);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn;
+            count_ = count;
+            next_.store(0);
+            active_ = (int)threads_.size();
+            ++epoch_;
+        }
+        cv_work_.notify_all();
+        for (int i; (i = next_.fetch_add(1)) < count;) fn(i);
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return active_ == 0; });
+        fn_ = nullptr;
+    }
+private:
+    void worker() {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* fn;
+            int count;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_work_.wait(lk, [&] { return epoch_ != seen; });
+                seen = epoch_;
+                if (stop_) return;
+                fn = fn_;
+                count = count_;
+            }
+            for (int i; (i = next_.fetch_add(1)) < count;) (*fn)(i);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                --active_;
+            }
+            cv_done_.notify_one();
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void(int)>* fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int count_ = 0, active_ = 0;
+    uint64_t epoch_ = 0;
+    bool stop_ = false;
+};
+
 }  // namespace
 
 // Per-context scratch of the extractor: kept between calls, so a run over many frames of one size allocates once.
@@ -441,6 +533,11 @@ struct OrbState {
     int* h_level_off = nullptr;  size_t h_level_cap = 0;
     OrbLevels levels{};
     bool have_levels = false;
+    TaskPool* pool = nullptr;                               // host threads of the selection step
+    std::vector<esfm_keypoint_t> sel_kp[kOrbLevels];
+    std::vector<OrbKp> sel_dk[kOrbLevels];
+    double phase_ms[5] = {0, 0, 0, 0, 0};                   // last call: front end | corner records | host selection | descriptors | total
+    int last_corners = 0;
 };
 
 void orb_state_destroy(esfm_ctx* ctx) {
@@ -450,6 +547,7 @@ void orb_state_destroy(esfm_ctx* ctx) {
     for (void* p : dev) if (p) cudaFreeAsync(p, ctx->stream);
     void* host[] = {s->h_src, s->h_cand, s->h_kp, s->h_level_off};
     for (void* p : host) if (p) cudaFreeHost(p);
+    delete s->pool;
     delete s;
     ctx->orb = nullptr;
 }
@@ -457,15 +555,24 @@ void orb_state_destroy(esfm_ctx* ctx) {
 int orb_extract_impl(esfm_ctx* ctx, const unsigned char* image, int rows, int cols, int channels, size_t row_stride, int max_features,
                      esfm_keypoint_t* keypoints, unsigned char* h_desc, int capacity, int* n_out, const OrbSink& sink) {
     if (!ctx || !image || !n_out) return fail(ESFM_ERR_INVALID, "esfm_orb_extract: NULL argument");
-    if (rows < 1 || cols < 1 || rows > 32767 || cols > 32767) return fail(ESFM_ERR_INVALID, "image size %d x %d out of range", cols, rows);
+    if (rows < 1 || cols < 1 || rows > 16383 || cols > 16383) return fail(ESFM_ERR_INVALID, "image size %d x %d out of range", cols, rows);
     if (channels != 1 && channels != 3) return fail(ESFM_ERR_INVALID, "image must have 1 (gray) or 3 (BGR) 8-bit channels, got %d", channels);
     if (row_stride < (size_t)cols * channels) return fail(ESFM_ERR_INVALID, "row_stride %zu smaller than a row", row_stride);
     if (max_features < 0 || capacity < 0 || (capacity > 0 && !keypoints)) return fail(ESFM_ERR_INVALID, "bad max_features / capacity / keypoints");
     if (int rc = set_device(ctx)) return rc;
-    if (!ctx->orb) ctx->orb = new OrbState();
+    if (!ctx->orb) {
+        ctx->orb = new OrbState();
+        const char* e = getenv("ESFM_ORB_THREADS");
+        const int want = e ? atoi(e) : std::min(kOrbLevels, (int)std::thread::hardware_concurrency());
+        ctx->orb->pool = new TaskPool(std::max(want, 1) - 1);
+    }
     OrbState& S = *ctx->orb;
     cudaStream_t st = ctx->stream;
     *n_out = 0;
+    using clk = std::chrono::steady_clock;
+    auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+    const clk::time_point t_start = clk::now();
+    clk::time_point t_phase = t_start;
 
     // ---- level geometry (orb.cpp detectAndCompute): scale_l = (float)pow(1.2f as double, l); size = cvRound(cols * (1.f / scale_l)) ----
     const double scale_factor = (double)1.2f;
@@ -523,10 +630,18 @@ int orb_extract_impl(esfm_ctx* ctx, const unsigned char* image, int rows, int co
     int* d_row_cnt = S.d_rows;
     int* d_row_off = S.d_rows + n_rows;
     int* d_level_off = S.d_rows + 2 * n_rows + 1;
-    if (row_stride == src_row) ctx->copier->copy(S.h_src, image, src_bytes);
-    else for (int r = 0; r < rows; ++r) memcpy(S.h_src + (size_t)r * src_row, image + (size_t)r * row_stride, src_row);
-    CUDA_TRY(cudaMemcpyAsync(S.d_src, S.h_src, src_bytes, cudaMemcpyHostToDevice, st));
-    ctx->stats.h2d_bytes += src_bytes;
+    {
+        // pageable image -> pinned staging -> device in a few row bands, so the host copy of band k + 1 overlaps the upload of band k
+        const int bands = src_bytes > ((size_t)1 << 20) ? 4 : 1;
+        for (int k = 0; k < bands; ++k) {
+            const int r0 = (int)((long long)rows * k / bands), r1 = (int)((long long)rows * (k + 1) / bands);
+            uint8_t* dst = S.h_src + (size_t)r0 * src_row;
+            if (row_stride == src_row) ctx->copier->copy(dst, image + (size_t)r0 * row_stride, (size_t)(r1 - r0) * src_row);
+            else for (int r = r0; r < r1; ++r) memcpy(S.h_src + (size_t)r * src_row, image + (size_t)r * row_stride, src_row);
+            CUDA_TRY(cudaMemcpyAsync(S.d_src + (size_t)r0 * src_row, dst, (size_t)(r1 - r0) * src_row, cudaMemcpyHostToDevice, st));
+        }
+        ctx->stats.h2d_bytes += src_bytes;
+    }
     {
         dim3 blk(32, 8), grd((cols + 31) / 32, (rows + 7) / 8);
         orb_gray_kernel<<<grd, blk, 0, st>>>(S.d_src, src_row, channels, cols, rows, S.d_pyr + L.off[0], L.pitch[0]);
@@ -544,6 +659,8 @@ int orb_extract_impl(esfm_ctx* ctx, const unsigned char* image, int rows, int co
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     const int n_cand = S.h_level_off[kOrbLevels];
+    S.phase_ms[0] = ms_since(t_phase); t_phase = clk::now();
+    S.last_corners = n_cand;
 
     // ---- per-corner responses and angles ----
     if (int rc = grow_dev(ctx, &S.d_cand, &S.cand_cap, (size_t)std::max(n_cand, 1))) return rc;
@@ -551,41 +668,43 @@ int orb_extract_impl(esfm_ctx* ctx, const unsigned char* image, int rows, int co
     if (n_cand > 0) {
         const float harris_scale = 1.f / ((1 << 2) * 7 * 255.f);
         const float scale4 = harris_scale * harris_scale * harris_scale * harris_scale;
-        const int warps_per_block = 4;
-        orb_cand_kernel<<<(n_rows + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(S.d_pyr, S.d_score, L, S.d_bits, d_row_off,
-                                                                                                          0.04f, scale4, S.d_cand);
+        orb_pos_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(L, S.d_bits, d_row_off, S.d_cand);
+        orb_cand_kernel<<<(n_cand + 7) / 8, 256, 0, st>>>(S.d_pyr, S.d_score, L, n_cand, 0.04f, scale4, S.d_cand);
         CUDA_TRY(cudaMemcpyAsync(S.h_cand, S.d_cand, (size_t)n_cand * sizeof(OrbCand), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaGetLastError());
         ctx->stats.d2h_bytes += (size_t)n_cand * sizeof(OrbCand);
     }
 
+    S.phase_ms[1] = ms_since(t_phase); t_phase = clk::now();
+
     // ---- selection (orb.cpp computeKeyPoints: retainBest(2 n) on the FAST score, Harris, retainBest(n)), level by level ----
-    std::vector<esfm_keypoint_t> out;
-    std::vector<OrbKp> kps;
-    std::vector<RespItem> a, b;
-    unsigned blur_mask = 0;
-    for (int l = 0; l < kOrbLevels; ++l) {
+    S.pool->run(kOrbLevels, [&](int l) {
+        std::vector<esfm_keypoint_t>& okp = S.sel_kp[l];
+        std::vector<OrbKp>& odk = S.sel_dk[l];
+        okp.clear();
+        odk.clear();
         const int lo = S.h_level_off[l], hi = S.h_level_off[l + 1];
-        if (hi == lo) continue;
-        a.resize(hi - lo);
+        if (hi == lo) return;
+        std::vector<RespItem> a((size_t)(hi - lo)), b;
         for (int i = lo; i < hi; ++i) a[i - lo] = RespItem{S.h_cand[i].score, i};
         retain_best(a, 2 * per_level[l]);
         b.resize(a.size());
         for (size_t i = 0; i < a.size(); ++i) b[i] = RespItem{S.h_cand[a[i].index].harris, a[i].index};
         retain_best(b, per_level[l]);
-        if (!b.empty()) blur_mask |= 1u << l;
         const float sc = scale[l], inv = 1.f / sc;
+        okp.reserve(b.size());
+        odk.reserve(b.size());
         for (const RespItem& it : b) {
             const OrbCand& c = S.h_cand[it.index];
             esfm_keypoint_t k;
-            k.x = (float)(c.xy & 0xffff) * sc;
-            k.y = (float)(c.xy >> 16) * sc;
+            k.x = (float)(c.xy & 0x3fff) * sc;
+            k.y = (float)((c.xy >> 14) & 0x3fff) * sc;
             k.size = 31.f * sc;
             k.angle = c.angle;
             k.response = c.harris;
             k.octave = l;
-            out.push_back(k);
+            okp.push_back(k);
             // orb.cpp computeOrbDescriptors re-derives the level position and the rotation from the key point it is handed
             OrbKp d;
             d.level = l;
@@ -595,11 +714,22 @@ int orb_extract_impl(esfm_ctx* ctx, const unsigned char* image, int rows, int co
             ang *= (float)(3.141592653589793238462643383279502884 / 180.f);
             d.a = (float)std::cos((double)ang);
             d.b = (float)std::sin((double)ang);
-            kps.push_back(d);
+            odk.push_back(d);
         }
+    });
+    std::vector<esfm_keypoint_t> out;
+    std::vector<OrbKp> kps;
+    unsigned blur_mask = 0;
+    for (int l = 0; l < kOrbLevels; ++l) {
+        if (!S.sel_kp[l].empty()) blur_mask |= 1u << l;
+        out.insert(out.end(), S.sel_kp[l].begin(), S.sel_kp[l].end());
+        kps.insert(kps.end(), S.sel_dk[l].begin(), S.sel_dk[l].end());
     }
     const int n = (int)out.size();
     *n_out = n;
+    S.phase_ms[2] = ms_since(t_phase); t_phase = clk::now();
+    S.phase_ms[3] = 0.0;
+    S.phase_ms[4] = ms_since(t_start);
     S.levels = L;
     S.levels.blur_mask = blur_mask;
     S.have_levels = true;
@@ -644,6 +774,8 @@ int orb_extract_impl(esfm_ctx* ctx, const unsigned char* image, int rows, int co
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
+    S.phase_ms[3] = ms_since(t_phase);
+    S.phase_ms[4] = ms_since(t_start);
     return ESFM_OK;
 }
 
@@ -654,6 +786,14 @@ using namespace esfm;
 extern "C" int esfm_orb_extract(esfm_ctx_t* ctx, const unsigned char* image, int rows, int cols, int channels, size_t row_stride, int max_features,
                                 esfm_keypoint_t* keypoints, unsigned char* descriptors, int capacity, int* n_out) {
     return orb_extract_impl(ctx, image, rows, cols, channels, row_stride, max_features, keypoints, descriptors, capacity, n_out, OrbSink());
+}
+
+extern "C" int esfm_orb_last_timing(esfm_ctx_t* ctx, double* phase_ms, int* corners) {
+    if (!ctx || !phase_ms) return fail(ESFM_ERR_INVALID, "esfm_orb_last_timing: NULL argument");
+    if (!ctx->orb || !ctx->orb->have_levels) return fail(ESFM_ERR_STATE, "esfm_orb_last_timing: no esfm_orb_extract call on this context yet");
+    for (int i = 0; i < 5; ++i) phase_ms[i] = ctx->orb->phase_ms[i];
+    if (corners) *corners = ctx->orb->last_corners;
+    return ESFM_OK;
 }
 
 extern "C" int esfm_orb_debug_level(esfm_ctx_t* ctx, int level, int blurred, unsigned char* out, size_t out_bytes, int* rows, int* cols) {

@@ -1,5 +1,5 @@
 // feature_matching_gpu.cpp -- drop-in replacement for the two matching methods of p3dv::FeatureMatching
-// (EasySFM cpp_code/src/feature_matching.cpp:71-158), forwarding to libesfm_match.so through the C ABI.
+// (EasySFM cpp_code/src/feature_matching.cpp:71-158) and for detectFeaturesORB (:14-41), forwarding to libesfm_match.so through the C ABI.
 //
 // Build it INSTEAD of the two method bodies in feature_matching.cpp: the signatures
 // below are verbatim from cpp_code/include/feature_matching.h:17-21, so cpp_code/test/sfm.cpp compiles and
@@ -226,6 +226,52 @@ bool esfm_load_matches(std::vector<frame_t>& frames, char feature, double ratio_
     s.have_mode = true;
     s.frame_index.clear();
     for (size_t i = 0; i < frames.size(); ++i) s.frame_index[frames[i].frame_id] = (int)i;
+    return true;
+}
+
+// cpp_code/src/feature_matching.cpp:14-41 (decl feature_matching.h:13): cv::ORB::create(max_num)->detect + ->compute on cur_frame.rgb_image,
+// filling cur_frame.keypoints and cur_frame.descriptors.  The device computes what cv2 4.13 computes, bit for bit and in the same order
+// (esfm_orb_extract); `show` only opens a GUI window in the reference (:32-38) and is ignored.
+bool FeatureMatching::detectFeaturesORB(frame_t& cur_frame, int max_num, bool show) {
+    (void)show;
+    if (!ensure_ctx()) return false;
+    const cv::Mat& img = cur_frame.rgb_image;
+    if (img.empty() || (img.type() != CV_8UC3 && img.type() != CV_8UC1)) {
+        std::cerr << "detectFeaturesORB: rgb_image must be a non-empty CV_8UC3 or CV_8UC1 image" << std::endl;
+        return false;
+    }
+    std::chrono::steady_clock::time_point tic = std::chrono::steady_clock::now();
+    std::vector<esfm_keypoint_t> kp((size_t)(max_num > 0 ? max_num : 0) + 256);
+    std::vector<unsigned char> desc(kp.size() * 32);
+    int n = 0;
+    int rc = esfm_orb_extract(state().ctx, img.data, img.rows, img.cols, img.channels(), (size_t)img.step, max_num, kp.data(), desc.data(),
+                              (int)kp.size(), &n);
+    if (rc == ESFM_ERR_CAPACITY && n > (int)kp.size()) {   // more Harris ties at the cut than the slack: once more with room for all
+        kp.resize((size_t)n);
+        desc.resize((size_t)n * 32);
+        rc = esfm_orb_extract(state().ctx, img.data, img.rows, img.cols, img.channels(), (size_t)img.step, max_num, kp.data(), desc.data(), n, &n);
+    }
+    if (rc != ESFM_OK) {
+        std::cerr << "esfm_orb_extract failed: " << esfm_last_error() << std::endl;
+        return false;
+    }
+    cur_frame.keypoints.resize((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        cv::KeyPoint& k = cur_frame.keypoints[(size_t)i];
+        k.pt.x = kp[(size_t)i].x;
+        k.pt.y = kp[(size_t)i].y;
+        k.size = kp[(size_t)i].size;
+        k.angle = kp[(size_t)i].angle;
+        k.response = kp[(size_t)i].response;
+        k.octave = kp[(size_t)i].octave;
+        k.class_id = -1;
+    }
+    cur_frame.descriptors.create(n, 32, CV_8UC1);
+    if (n) std::memcpy(cur_frame.descriptors.data, desc.data(), (size_t)n * 32);
+    std::chrono::steady_clock::time_point toc = std::chrono::steady_clock::now();
+    std::chrono::duration<double> time_used = std::chrono::duration_cast<std::chrono::duration<double>>(toc - tic);
+    std::cout << "extract ORB cost = " << time_used.count() << " seconds. " << std::endl;    // :28-30
+    std::cout << "Found [32 x " << n << "] features" << std::endl;
     return true;
 }
 

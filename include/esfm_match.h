@@ -395,6 +395,10 @@ int esfm_bank_set_frame_from_image(esfm_bank_t* bank, int frame_id, const unsign
                                    int capacity, int* n_out);
 /* Intermediate results of the device stages, for tests: the pyramid level `level` of the last esfm_orb_extract call on this context
  * (blurred = 0: as resized; 1: after the 7 x 7 blur), copied to out (rows * cols bytes, dense); *rows / *cols receive the level size. */
+/* Host wall-clock milliseconds of the last extraction on this context: [0] upload + gray + pyramid + FAST + NMS + scan, [1] corner records
+ * (Harris, angle) and their download, [2] host selection, [3] key-point upload + blur + descriptors + download, [4] the whole call;
+ * *corners (optional) = NMS survivors inside the edge band, all levels. */
+int esfm_orb_last_timing(esfm_ctx_t* ctx, double* phase_ms, int* corners);
 int esfm_orb_debug_level(esfm_ctx_t* ctx, int level, int blurred, unsigned char* out, size_t out_bytes, int* rows, int* cols);
 
 #ifdef __cplusplus

@@ -226,6 +226,10 @@ def retain_best(responses, n_points):
     global _SELECT
     import ctypes
     if _SELECT is None:
+        here = os.path.dirname(os.path.abspath(__file__))
+        if not os.path.exists(os.path.join(here, "liborbselect.so")):
+            import subprocess
+            subprocess.check_call(["make", "-s", "-C", here, "liborbselect.so"])
         _SELECT = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "liborbselect.so"))
         _SELECT.orb_oracle_retain_best.restype = ctypes.c_int
     r = np.ascontiguousarray(responses, np.float32)

@@ -5,10 +5,12 @@
 #ifndef TESTS_SHIM_FEATURE_MATCHING_H_
 #define TESTS_SHIM_FEATURE_MATCHING_H_
 #include <cstddef>
+#include <memory>
 #include <string>
 #include <vector>
 
 #define CV_8UC1 0
+#define CV_8UC3 16
 #define CV_32FC1 5
 
 namespace cv {
@@ -21,7 +23,15 @@ struct Mat {
     int rows = 0, cols = 0;
     unsigned char* data = nullptr;
     MatStep step;
+    std::shared_ptr<std::vector<unsigned char> > owned;   // cv::Mat's reference-counted buffer, for create()
     int type() const { return flags_type; }
+    int channels() const { return (flags_type >> 3) + 1; }
+    bool empty() const { return rows == 0 || cols == 0 || !data; }
+    void create(int r, int c, int type) {                 // cv::Mat::create: a continuous r x c matrix of `type`
+        const size_t elem = (size_t)((type >> 3) + 1) * ((type & 7) == 5 ? 4 : 1);
+        owned = std::make_shared<std::vector<unsigned char> >((size_t)r * c * elem + 1);
+        flags_type = type; rows = r; cols = c; data = owned->data(); step.v = (size_t)c * elem;
+    }
 };
 struct DMatch {
     int queryIdx = -1, trainIdx = -1, imgIdx = -1;
@@ -30,8 +40,10 @@ struct DMatch {
 struct Point2f {
     float x = 0.f, y = 0.f;
 };
-struct KeyPoint {
+struct KeyPoint {             // member order of cv::KeyPoint
     Point2f pt;
+    float size = 0.f, angle = -1.f, response = 0.f;
+    int octave = 0, class_id = -1;
 };
 }  // namespace cv
 
@@ -50,6 +62,7 @@ namespace p3dv {
 struct frame_t {
     unsigned int frame_id = 0;
     std::string image_file_path;
+    cv::Mat rgb_image;           // utility.h:25
     std::vector<cv::KeyPoint> keypoints;
     cv::Mat descriptors;
     std::vector<int> unique_pixel_ids;
@@ -58,6 +71,7 @@ struct frame_t {
 
 class FeatureMatching {
 public:
+    bool detectFeaturesORB(frame_t& cur_frame, int max_num = 5000, bool show = false);
     bool matchFeaturesORB(frame_t& cur_frame_1, frame_t& cur_frame_2, std::vector<cv::DMatch>& matches,
                           double ratio_thre = 0.8, bool show = false);
     bool matchFeaturesSURF(frame_t& cur_frame_1, frame_t& cur_frame_2, std::vector<cv::DMatch>& matches,

@@ -133,3 +133,42 @@ def test_motion_shim_matches_oracle(tmp_path):
             d_ref = tvo.mean_depth(T[:3, :3].astype(np.float64), T[:3, 3].astype(np.float64), x1, x2, K, ref["mask"], 20)
             np.testing.assert_allclose(depth, d_ref, rtol=1e-6)
     assert pos == len(raw)
+
+
+# --------------------------------------------------------------------------------------------------
+# detectFeaturesORB through the shim, against cv2's golden output
+# --------------------------------------------------------------------------------------------------
+def build_orb_shim(tmp):
+    exe = os.path.join(tmp, "orb_main")
+    cmd = ["g++", "-std=c++14", "-O1", "-Wall", "-I", os.path.join(ROOT, "tests", "shim"), "-I", os.path.join(ROOT, "include"),
+           SHIM, os.path.join(ROOT, "tests", "shim", "orb_main.cpp"), "-L", LIBDIR, "-lesfm_match", f"-Wl,-rpath,{LIBDIR}", "-o", exe]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_orb_shim_compiles_and_links(tmp_path):
+    assert os.path.exists(build_orb_shim(str(tmp_path)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["odd_bgr_2000", "vga_500"])
+def test_orb_shim_equals_cv2_golden(tmp_path, name):
+    from orb_util import CASES, image
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "orb_extract.npz"))
+    seed, h, w, shapes, bgr, nf = CASES[name]
+    img = image(seed, h, w, shapes, bgr)
+    exe = build_orb_shim(str(tmp_path))
+    raw_path, out = os.path.join(str(tmp_path), "img.bin"), os.path.join(str(tmp_path), "kp.bin")
+    with open(raw_path, "wb") as f:
+        f.write(np.ascontiguousarray(img).tobytes())
+    subprocess.check_call([exe, raw_path, str(h), str(w), "3" if bgr else "1", str(nf), out], stdout=subprocess.DEVNULL)
+    raw = open(out, "rb").read()
+    n = int(np.frombuffer(raw, np.int32, 1, 0)[0])
+    rec = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+    kp = np.frombuffer(raw, rec, n, 4)
+    desc = np.frombuffer(raw, np.uint8, n * 32, 4 + n * rec.itemsize).reshape(n, 32)
+    ref = gold[name + "_kp"]
+    assert n == len(ref) and (kp["class_id"] == -1).all()
+    for fld in ref.dtype.names:
+        assert np.array_equal(kp[fld], ref[fld]), fld
+    assert np.array_equal(desc, gold[name + "_desc"])

@@ -35,6 +35,11 @@ def main():
         t0 = time.perf_counter()
         outs = [ctx.orb_extract(im, nf) for im in imgs]
         t_gpu = (time.perf_counter() - t0) / a.frames
+        phases = {}
+        for im in imgs:
+            ctx.orb_extract(im, nf)
+            for k, v in ctx.orb_last_timing().items():
+                phases[k] = phases.get(k, 0.0) + v / a.frames
         bank = capi.Bank(ctx, capi.KIND_B256, a.frames)
         t0 = time.perf_counter()
         for k, im in enumerate(imgs):
@@ -42,7 +47,7 @@ def main():
         bank.commit()
         t_bank = (time.perf_counter() - t0) / a.frames
         case = {"case": name, "rows": h, "cols": w, "max_features": nf, "keypoints_mean": float(np.mean([len(k) for k, _ in outs])),
-                "gpu_ms_per_frame": t_gpu * 1e3, "gpu_into_bank_ms_per_frame": t_bank * 1e3, "timing": "host wall clock around the C-ABI call, image in "
+                "gpu_ms_per_frame": t_gpu * 1e3, "gpu_into_bank_ms_per_frame": t_bank * 1e3, "phases_mean": phases, "timing": "host wall clock around the C-ABI call, image in "
                 "pageable host memory, key points (and descriptors for the first figure) back on the host"}
         if cv2 is not None:
             det, ext = cv2.ORB_create(nf), cv2.ORB_create(nf)
