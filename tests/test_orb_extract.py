@@ -34,6 +34,12 @@ def test_extract_equals_cv2_golden(octx, name):
     assert_same(kp, desc, GOLD[name + "_kp"], GOLD[name + "_desc"])
 
 
+def test_extract_equals_cv2_on_a_photograph(octx):
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "orb_fountain.npz"))
+    kp, desc = octx.orb_extract(g["image"], int(g["max_features"]))
+    assert_same(kp, desc, g["kp"], g["desc"])
+
+
 def test_levels_equal_oracle(octx):
     img = image(31, 301, 417, 30, True)
     kp, desc = octx.orb_extract(img, 1500)

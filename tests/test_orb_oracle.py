@@ -26,6 +26,12 @@ def test_oracle_equals_cv2_golden(name):
     assert_same(kp, desc, GOLD[name + "_kp"], GOLD[name + "_desc"])
 
 
+def test_oracle_equals_cv2_on_a_photograph():
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "orb_fountain.npz"))
+    kp, desc = oo.detect_and_compute(g["image"], int(g["max_features"]))
+    assert_same(kp, desc, g["kp"], g["desc"])
+
+
 def test_pieces_known_answers():
     # BGR -> gray weights sum to 1 << 15; the measured sampling pattern stays inside the 31 x 31 patch and has no degenerate test
     g = oo.bgr_to_gray(np.full((2, 2, 3), 200, np.uint8))
