@@ -15,6 +15,7 @@
 #   multi       N-device tests + N-rank bench (N = $N, default 2): use with gpurun --gpus N
 #   fulljob     tools/full_job.py on $N devices (KINDS="surf orb")
 #   sanitizer   compute-sanitizer memcheck + racecheck on the smoke shapes
+#   orb         ORB extraction: tools/orb_bench.py (vs cv2 on the host cores) + ncu launch list of one 1080p frame
 mkdir -p gpurun_out
 N=${N:-2}
 for stage in "$@"; do
@@ -65,6 +66,9 @@ sanitizer)
     timeout ${SAN_TIMEOUT:-240} compute-sanitizer --tool $tool --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/sanitizer_$tool.log 2>&1
     echo "compute-sanitizer $tool exit $?"; tail -4 gpurun_out/sanitizer_$tool.log | cut -c1-200
   done ;;
+orb)
+  timeout 200 python tools/orb_bench.py --frames ${ORB_FRAMES:-12} 2>&1 | tail -4 | cut -c1-700
+  timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/orb_launches.csv python tools/orb_profile.py 2>&1 | tail -1 ;;
 *)
   if [ -f "$stage" ]; then timeout ${SCRIPT_TIMEOUT:-300} python "$stage" > "gpurun_out/$(basename "$stage" .py).txt" 2>&1; tail -30 "gpurun_out/$(basename "$stage" .py).txt"
   else echo "unknown stage $stage"; fi ;;
