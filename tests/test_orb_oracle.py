@@ -70,3 +70,57 @@ def test_oracle_equals_cv2_live():
             ref[i] = (p.pt[0], p.pt[1], p.size, p.angle, p.response, p.octave)
         kp, desc = oo.detect_and_compute(img, nf)
         assert_same(kp, desc, ref, d)
+
+
+# ---- stage-by-stage pins against the cv2 functions ORB is built from (live; skipped where cv2 is absent) --------------------------------
+def test_stages_equal_cv2_live():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(7)
+    # color_rgb BGR2GRAY
+    bgr = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    assert np.array_equal(oo.bgr_to_gray(bgr), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+    # resize.cpp INTER_LINEAR_EXACT, including the 1-pixel-smaller and strongly reduced cases
+    img = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+    for dw, dh in [(533, 400), (444, 333), (639, 479), (100, 77), (179, 134)]:
+        assert np.array_equal(oo.resize_linear_exact(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT)), (dw, dh)
+    # fast.cpp + fast_score.cpp: corners, order and scores of cv2's FAST-9/16 with non-maximum suppression
+    tex = image(303, 200, 260, 30)
+    ref = cv2.FastFeatureDetector_create(oo.FAST_THRESHOLD, True).detect(tex, None)
+    ys, xs = oo.fast_nms(oo.fast_scores(tex))
+    assert len(ref) == len(xs) > 100
+    assert [(int(k.pt[0]), int(k.pt[1])) for k in ref] == list(zip(xs.tolist(), ys.tolist()))          # raster order
+    assert [k.response for k in ref] == oo.fast_scores(tex)[ys, xs].astype(np.float32).tolist()
+    # without suppression: every corner pixel
+    allc = cv2.FastFeatureDetector_create(oo.FAST_THRESHOLD, False).detect(tex, None)
+    yy, xx = np.nonzero(oo.fast_scores(tex))
+    assert sorted((int(k.pt[0]), int(k.pt[1])) for k in allc) == sorted(zip(xx.tolist(), yy.tolist()))
+    # core fastAtan2
+    for _ in range(2000):
+        y, x = (float(v) for v in rng.integers(-70000, 70000, 2))
+        assert oo.fast_atan2(y, x) == np.float32(cv2.fastAtan2(y, x)), (y, x)
+    # getGaussianKernel(7, 2, CV_32F)
+    assert np.array_equal(oo.gaussian_kernel_7(), cv2.getGaussianKernel(7, 2, cv2.CV_32F).ravel())
+
+
+def test_compute_on_given_keypoints_equals_cv2_live():
+    """ORB::compute alone (the reference's second call, feature_matching.cpp:22): hand-placed key points with arbitrary angles and octaves."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(9)
+    img = image(404, 300, 400, 40)
+    levels, scales = oo.build_pyramid(img)
+    kps, arr = [], np.zeros(300, oo.KP_DTYPE)
+    for i in range(300):
+        l = int(rng.integers(0, 5))
+        h, w = levels[l].shape
+        x = float(np.float32(rng.integers(40, w - 40)) * scales[l])
+        y = float(np.float32(rng.integers(40, h - 40)) * scales[l])
+        ang = float(np.float32(rng.random() * 360.0))
+        kps.append(cv2.KeyPoint(x, y, 31.0 * float(scales[l]), ang, 1.0, l, -1))
+        arr[i] = (x, y, 31.0 * float(scales[l]), ang, 1.0, l)
+    out_kps, desc = cv2.ORB_create(500).compute(img, kps)
+    assert len(out_kps) == 300
+    # key points that are not sorted by level come back grouped by level (a stable regrouping inside ORB); detect()'s output, which is what
+    # the reference passes, already is
+    order = np.argsort(arr["octave"], kind="stable")
+    assert [(k.pt[0], k.pt[1], k.octave) for k in out_kps] == [(float(arr["x"][i]), float(arr["y"][i]), int(arr["octave"][i])) for i in order]
+    assert np.array_equal(oo.compute_descriptors(levels, scales, arr[order]), desc)
