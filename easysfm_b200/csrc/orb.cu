@@ -37,6 +37,7 @@
 #include "../../include/esfm_match.h"
 #include "esfm_internal.cuh"
 #include "host_internal.h"
+#include "orb_host.h"
 
 namespace esfm {
 
@@ -413,17 +414,8 @@ __global__ void __launch_bounds__(256) orb_desc_kernel(const uint8_t* __restrict
     desc[(size_t)k * 32 + lane] = (uint8_t)byte;
 }
 
-// KeyPointsFilter::retainBest (features2d keypoint.cpp): see the file header for why this is the library's nth_element / partition.
-struct RespItem { float response; int index; };
-void retain_best(std::vector<RespItem>& v, int n_points) {
-    if (n_points >= 0 && v.size() > (size_t)n_points) {
-        if (n_points == 0) { v.clear(); return; }
-        std::nth_element(v.begin(), v.begin() + n_points - 1, v.end(), [](const RespItem& a, const RespItem& b) { return a.response > b.response; });
-        const float ambiguous = v[n_points - 1].response;
-        auto new_end = std::partition(v.begin() + n_points, v.end(), [ambiguous](const RespItem& a) { return a.response >= ambiguous; });
-        v.resize(new_end - v.begin());
-    }
-}
+using orbhost::RespItem;
+using orbhost::retain_best;
 
 template <typename T>
 int grow_dev(esfm_ctx* ctx, T** p, size_t* cap, size_t need) {
@@ -575,17 +567,16 @@ int orb_extract_impl(esfm_ctx* ctx, const unsigned char* image, int rows, int co
     clk::time_point t_phase = t_start;
 
     // ---- level geometry (orb.cpp detectAndCompute): scale_l = (float)pow(1.2f as double, l); size = cvRound(cols * (1.f / scale_l)) ----
-    const double scale_factor = (double)1.2f;
+    static_assert(kOrbLevels == orbhost::kLevels, "level count");
     float scale[kOrbLevels];
     OrbLevels L{};
     L.n = kOrbLevels;
     long long off = 0, word = 0;
     int row = 0, tile_fast = 0;
     for (int l = 0; l < kOrbLevels; ++l) {
-        scale[l] = (float)std::pow(scale_factor, (double)l);
-        const float inv = 1.f / scale[l];
-        L.w[l] = l == 0 ? cols : (int)std::lrint((double)((float)cols * inv));
-        L.h[l] = l == 0 ? rows : (int)std::lrint((double)((float)rows * inv));
+        scale[l] = orbhost::level_scale(l);
+        L.w[l] = orbhost::level_extent(cols, l);
+        L.h[l] = orbhost::level_extent(rows, l);
         if (L.w[l] < 1 || L.h[l] < 1) return fail(ESFM_ERR_INVALID, "image %d x %d is too small for 8 pyramid levels", cols, rows);
         L.pitch[l] = (L.w[l] + 15) & ~15;
         L.off[l] = off;
@@ -605,17 +596,7 @@ int orb_extract_impl(esfm_ctx* ctx, const unsigned char* image, int rows, int co
 
     // features per level (orb.cpp computeKeyPoints), float arithmetic as written there
     int per_level[kOrbLevels];
-    {
-        const float factor = (float)(1.0 / scale_factor);
-        float desired = max_features * (1 - factor) / (1 - (float)std::pow((double)factor, (double)kOrbLevels));
-        int sum = 0;
-        for (int l = 0; l < kOrbLevels - 1; ++l) {
-            per_level[l] = (int)std::lrint((double)desired);
-            sum += per_level[l];
-            desired *= factor;
-        }
-        per_level[kOrbLevels - 1] = std::max(max_features - sum, 0);
-    }
+    orbhost::features_per_level(max_features, per_level);
 
     // ---- upload, gray, pyramid, FAST, NMS, scan ----
     const size_t src_row = (size_t)cols * channels, src_bytes = src_row * rows;
@@ -666,8 +647,7 @@ int orb_extract_impl(esfm_ctx* ctx, const unsigned char* image, int rows, int co
     if (int rc = grow_dev(ctx, &S.d_cand, &S.cand_cap, (size_t)std::max(n_cand, 1))) return rc;
     if (int rc = grow_host(&S.h_cand, &S.h_cand_cap, (size_t)std::max(n_cand, 1))) return rc;
     if (n_cand > 0) {
-        const float harris_scale = 1.f / ((1 << 2) * 7 * 255.f);
-        const float scale4 = harris_scale * harris_scale * harris_scale * harris_scale;
+        const float scale4 = orbhost::harris_scale4();
         orb_pos_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(L, S.d_bits, d_row_off, S.d_cand);
         orb_cand_kernel<<<(n_cand + 7) / 8, 256, 0, st>>>(S.d_pyr, S.d_score, L, n_cand, 0.04f, scale4, S.d_cand);
         CUDA_TRY(cudaMemcpyAsync(S.h_cand, S.d_cand, (size_t)n_cand * sizeof(OrbCand), cudaMemcpyDeviceToHost, st));
@@ -692,28 +672,28 @@ int orb_extract_impl(esfm_ctx* ctx, const unsigned char* image, int rows, int co
         b.resize(a.size());
         for (size_t i = 0; i < a.size(); ++i) b[i] = RespItem{S.h_cand[a[i].index].harris, a[i].index};
         retain_best(b, per_level[l]);
-        const float sc = scale[l], inv = 1.f / sc;
+        const float sc = scale[l];
         okp.reserve(b.size());
         odk.reserve(b.size());
         for (const RespItem& it : b) {
             const OrbCand& c = S.h_cand[it.index];
+            const orbhost::KeyPointOut ko = orbhost::keypoint_of(c.xy & 0x3fff, (c.xy >> 14) & 0x3fff, sc);
             esfm_keypoint_t k;
-            k.x = (float)(c.xy & 0x3fff) * sc;
-            k.y = (float)((c.xy >> 14) & 0x3fff) * sc;
-            k.size = 31.f * sc;
+            k.x = ko.x;
+            k.y = ko.y;
+            k.size = ko.size;
             k.angle = c.angle;
             k.response = c.harris;
             k.octave = l;
             okp.push_back(k);
             // orb.cpp computeOrbDescriptors re-derives the level position and the rotation from the key point it is handed
+            const orbhost::SampleFrame sf = orbhost::sample_frame_of(ko, c.angle, sc);
             OrbKp d;
             d.level = l;
-            d.cx = (int)std::lrint((double)(k.x * inv));
-            d.cy = (int)std::lrint((double)(k.y * inv));
-            float ang = k.angle;
-            ang *= (float)(3.141592653589793238462643383279502884 / 180.f);
-            d.a = (float)std::cos((double)ang);
-            d.b = (float)std::sin((double)ang);
+            d.cx = sf.cx;
+            d.cy = sf.cy;
+            d.a = sf.a;
+            d.b = sf.b;
             odk.push_back(d);
         }
     });
@@ -752,11 +732,8 @@ int orb_extract_impl(esfm_ctx* ctx, const unsigned char* image, int rows, int co
     CUDA_TRY(cudaMemcpyAsync(S.d_kp, S.h_kp, (size_t)n * sizeof(OrbKp), cudaMemcpyHostToDevice, st));
     ctx->stats.h2d_bytes += (size_t)n * sizeof(OrbKp);
     {
-        // getGaussianKernel(7, 2, CV_32F): exp(-x^2 / (2 sigma^2)) in double, normalised, cast
-        double kd[7], sum = 0;
-        for (int i = 0; i < 7; ++i) { const double x = i - 3.0; kd[i] = std::exp(-(x * x) / 8.0); sum += kd[i]; }
         float kf[7];
-        for (int i = 0; i < 7; ++i) kf[i] = (float)(kd[i] / sum);
+        orbhost::gaussian_kernel_7(kf);
         OrbLevels B = S.levels;
         int tiles = 0;
         for (int l = 0; l < kOrbLevels; ++l) {
